@@ -1,0 +1,33 @@
+"""Shared loaders for the golden fixtures (tests/golden/, written by gen_golden.py)."""
+import glob
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden_case_names():
+    return sorted(os.path.basename(p)[len('loglik_'):-len('.json')]
+                  for p in glob.glob(os.path.join(GOLDEN, 'loglik_*.json')))
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN, 'loglik_%s.json' % name)) as f:
+        return json.load(f)
+
+
+def load_tp_kat():
+    with open(os.path.join(GOLDEN, 'tp_kat.json')) as f:
+        return json.load(f)
+
+
+def case_hist(case):
+    return {int(j): int(h) for j, h in case['hist']}
+
+
+def case_ctor_kwargs(case):
+    kw = dict(max_error=case['max_error'], max_cov=case.get('max_cov'))
+    if case['model'] == 'repeats':
+        kw['min_single_copy_ratio'] = case.get('min_q1', 0.3)
+        kw['threshold'] = case.get('threshold', 1e-8)
+    return kw
