@@ -1,0 +1,155 @@
+/*
+ * cvmodel.h -- per-point / per-term arithmetic of the CovEst mixture model, shared by the
+ * sm_100a kernels (loglik_kernel.cu) and the test-only host emulation (tests/host_math).
+ *
+ * Formulation.  For one parameter point the reference evaluates
+ *
+ *     p_j = sum_o b(o) * sum_s a_os * tp(o*l_s, j)                    (models.py:235-241)
+ *     tp(L, j) = (prod_{i<=j} L/i) / D(L)                               (covest_poissonmodule.c:7-35)
+ *
+ * Every (o, s) pair is one *term* with rate L = o*l_s and weight w = b(o)*a_os.  Its value at
+ * bin j is w * L^j / j! / D(L) = exp(j*log L - lgamma(j+1) - log D(L) + log w).  The kernels
+ * evaluate that exponential once per (term, chain of bins) -- the *seed*, in double-double so
+ * the large cancelling parts j*log L, lgamma(j+1) and L keep ~1e-15 absolute accuracy -- and
+ * walk the following bins with the recurrence value(j+1) = value(j) * L / (j+1), which is the
+ * same product the reference's inner loop forms.
+ *
+ * D(L) is the reference's denominator *as implemented* (c:25-31), not e^L - 1:
+ *     n = number of times 200 can be taken off L while it stays > 200,  r = L - 200 n
+ *     D = e^(200 n) * (e^r - 1)     if r > 1e-8
+ *     D = e^(200 n) * L             otherwise (the ORIGINAL L, c:19 `p3 = l`)
+ */
+#pragma once
+#include "cvmath.h"
+
+/* exp(CV_SCALE_LOG) multiplies every seed so that terms that are still far below the double
+ * range at the head of a chain, but grow inside it, keep full precision; the epilogue divides it
+ * out again.  420 leaves room both ways for chains of up to 64 bins and rates up to the
+ * reference's own overflow limit (~11 360). */
+#define CV_SCALE_LOG 420.0
+#define CV_DEAD_TERM (-1.0e30)
+#define CV_MAX_ERR 64
+
+struct CvTerm {
+    double lam;    /* rate o*l_s */
+    double lh, ll; /* log(lam) as double-double */
+    double ch, cl; /* log w - log D(lam) [the part not proportional to the bin], double-double */
+};
+
+/* models.py:60-69 fit_to_bounds for one coordinate; NaN bound = open */
+CV_HD double cv_clip(double v, double lo, double hi)
+{
+    if (lo == lo && v < lo)
+        return lo;
+    if (hi == hi && v > hi)
+        return hi;
+    return v;
+}
+
+/* models.py:71-72 */
+CV_HD double cv_kmer_coverage(double c, int k, int r)
+{
+    return cv_div(cv_mul(c, (double)(r - k + 1)), (double)r);
+}
+
+/* models.py:75-79: l_s = c_k * 3**-s * (1-err)**(k-s) * err**s, multiplied left to right.
+ * pow3_neg_s is the host libm's pow(3.0, -s) (1.0 for s = 0). */
+CV_HD double cv_error_class_rate(double ck, double pow3_neg_s, double err, int k, int s)
+{
+    double keep = cv_pow_uint(cv_sub(1.0, err), k - s);
+    double miss = cv_pow_uint(err, s);
+    return cv_mul(cv_mul(cv_mul(ck, pow3_neg_s), keep), miss);
+}
+
+/* models.py:193-208 get_b_o.  two = (1-q1)*q2, many = (1-q1)*(1-q2)*q, base = 1-q. */
+CV_HD double cv_copy_weight(int o, double q1, double two, double many, double base)
+{
+    if (o == 1)
+        return q1;
+    if (o == 2)
+        return two;
+    return cv_mul(many, pow(base, (double)(o - 3)));
+}
+
+/* weight numerator comb[s] * (1.0 - exp(-lam)), models.py:87 / :221 */
+CV_HD double cv_class_mass(double comb_s, double lam)
+{
+    return cv_mul(comb_s, cv_one_minus_exp_neg(lam));
+}
+
+/* Everything of a term that does not depend on the bin.  `w` is b(o) * a_os. */
+CV_HD CvTerm cv_term_make(double lam, double w)
+{
+    CvTerm t;
+    if (lam != lam || w != w) {
+        t.lam = 1.0;
+        t.lh = t.ll = 0.0;
+        t.ch = NAN;
+        t.cl = 0.0;
+        return t;
+    }
+    if (!(lam > 0.0) || !(w > 0.0)) { /* zero weight: contributes exactly 0 (a_os * tp = 0) */
+        t.lam = 1.0;
+        t.lh = t.ll = 0.0;
+        t.ch = CV_DEAD_TERM;
+        t.cl = 0.0;
+        return t;
+    }
+    /* c:25-28: staged reduction by 200 */
+    double n = 0.0;
+    double r = lam;
+    if (lam > 200.0) {
+        n = ceil(lam * (1.0 / 200.0)) - 1.0;
+        r = cv_fma(-200.0, n, lam); /* exact */
+        while (r > 200.0) {
+            r = cv_sub(r, 200.0);
+            n += 1.0;
+        }
+        while (r <= 0.0 && n > 0.0) {
+            r = cv_add(r, 200.0);
+            n -= 1.0;
+        }
+    }
+    double lin, dterm;
+    if (r > 1e-8) { /* c:29-31 */
+        lin = lam;                /* log D = lam + log(1 - e^-r) */
+        dterm = log(-expm1(-r));
+    } else {
+        lin = 200.0 * n;          /* log D = 200 n + log(lam) */
+        dterm = log(lam);
+    }
+    cv_dd lg = cv_log_dd(lam);
+    cv_dd c = cv_two_sum(-lin, log(w) - dterm);
+    t.lam = lam;
+    t.lh = lg.hi;
+    t.ll = lg.lo;
+    t.ch = c.hi;
+    t.cl = c.lo;
+    return t;
+}
+
+/* Scaled value of a term at the head bin of a chain:
+ *   exp(j0 * log(lam) + [CV_SCALE_LOG - lgamma(j0+1)] + [log w - log D])
+ * (head_h, head_l) is the bracketed chain constant as a double-double. */
+CV_HD double cv_seed(double j0, double head_h, double head_l, double lh, double ll, double ch,
+                     double cl)
+{
+    double p = cv_mul(j0, lh);
+    double pe = cv_fma(j0, ll, cv_fma(j0, lh, -p));
+    cv_dd s1 = cv_two_sum(p, head_h);
+    cv_dd s2 = cv_two_sum(s1.hi, ch);
+    double lo = cv_add(cv_add(cv_add(pe, head_l), cl), cv_add(s1.lo, s2.lo));
+    double eh = cv_add(s2.hi, lo);
+    double el = cv_sub(lo, cv_sub(eh, s2.hi));
+    double u = exp(eh);
+    return cv_fma(u, el, u);
+}
+
+/* models.py:103-107 for the last step: total mass, tail term */
+CV_HD double cv_finish_loglik(double weighted_logs, double mass, double tail)
+{
+    double tail_term = 0.0;
+    if (mass < 1.0)
+        tail_term = tail * log(1.0 - mass); /* 1 - mass > 0 here; utils.py:32-35 */
+    return weighted_logs + tail_term;
+}
