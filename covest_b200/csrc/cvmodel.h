@@ -111,7 +111,20 @@ CV_HD CvTerm cv_term_make(double lam, double w)
         }
     }
     double lin, dterm;
-    if (r > 1e-8) { /* c:29-31 */
+    if (r > 1e-8 && r < 0x1p-11) {
+        /* c:30 `expl(l) - 1` in x87 long double: e^r lies in [1, 2), where the 64-bit format has
+         * a spacing of 2^-63, so the difference is e^r - 1 rounded to a multiple of 2^-63 -- a
+         * relative perturbation of up to 5e-12 at r = 1e-8 that the high error classes carry
+         * straight into p_1.  expm1(r) = r + tail, tail = r^2/2 + ... + r^5/120 (r^6/720 is
+         * below 2^-63 * 1e-3 here); both parts are split into integer and fraction of 2^-63. */
+        double tail = cv_mul(cv_mul(r, r),
+                             cv_fma(r, cv_fma(r, cv_fma(r, 1.0 / 120.0, 1.0 / 24.0), 1.0 / 6.0), 0.5));
+        double x1 = cv_mul(r, 0x1p63), x2 = cv_mul(tail, 0x1p63);
+        double i1 = floor(x1), i2 = floor(x2);
+        double units = cv_add(cv_add(i1, i2), rint(cv_add(cv_sub(x1, i1), cv_sub(x2, i2))));
+        lin = 200.0 * n;
+        dterm = log(cv_mul(units, 0x1p-63));
+    } else if (r > 1e-8) { /* c:29-31 */
         lin = lam;                /* log D = lam + log(1 - e^-r) */
         dterm = log(-expm1(-r));
     } else {

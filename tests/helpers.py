@@ -31,3 +31,17 @@ def case_ctor_kwargs(case):
         kw['min_single_copy_ratio'] = case.get('min_q1', 0.3)
         kw['threshold'] = case.get('threshold', 1e-8)
     return kw
+
+
+def rel_err_ll(got, want):
+    """Relative error per point; equal infinities / NaNs count as exact."""
+    import numpy as np
+    got = np.asarray(got, dtype=float)
+    want = np.asarray(want, dtype=float)
+    with np.errstate(all='ignore'):
+        rel = np.abs(got - want) / np.abs(want)
+    same = (np.isnan(got) & np.isnan(want)) | (np.isinf(got) & np.isinf(want) & (got == want))
+    rel[same] = 0.0
+    rel[np.isnan(rel)] = np.inf
+    rel[(got == want)] = 0.0
+    return rel
