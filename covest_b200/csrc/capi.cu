@@ -1,0 +1,574 @@
+/*
+ * capi.cu -- the C ABI of libcovest_b200.so (include/covest_b200.h): contexts, staging of host
+ * buffers, kernel launches.  No arithmetic of the likelihood lives here -- and no CPU fallback:
+ * every entry point needs a CUDA device.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/covest_b200.h"
+#include "cvtables.h"
+#include "kernels.h"
+
+#define CVB_CHUNK_POINTS (1LL << 22) /* staging granularity for host-resident batches */
+#define CVB_MAX_TIMED_CHUNKS 64
+
+struct cvb_ctx {
+    int device = 0;
+    int n_sm = 0;
+    CvModelDesc desc;
+    std::vector<void *> owned; /* device allocations that live as long as the context */
+    cudaStream_t stream = nullptr;
+    /* growable staging */
+    double *d_params = nullptr;
+    size_t cap_params = 0; /* doubles */
+    double *d_ll = nullptr;
+    size_t cap_ll = 0;
+    double *d_probs = nullptr;
+    size_t cap_probs = 0;
+    double *d_cand_ll = nullptr, *d_sel_ll = nullptr, *d_rows = nullptr;
+    long long *d_cand_idx = nullptr, *d_sel_idx = nullptr;
+    int cap_k = 0;
+    int topk_ctas = 0;
+    double *d_axes = nullptr;
+    size_t cap_axes = 0;
+    unsigned long long *d_counter = nullptr;
+    double *d_sink = nullptr;
+    /* timing */
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    int timed_chunks = 0;
+    int last_launches = 0;
+    cudaStream_t timed_stream = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(cvb_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+static int fail_cuda(cvb_ctx *ctx, cudaError_t e, const char *what)
+{
+    return fail(ctx, CVB_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call, what)                        \
+    do {                                      \
+        cudaError_t e_ = (call);              \
+        if (e_ != cudaSuccess)                \
+            return fail_cuda(ctx, e_, what);  \
+    } while (0)
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p)
+        return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+static cudaError_t grow(T **buf, size_t *cap, size_t want)
+{
+    if (want <= *cap)
+        return cudaSuccess;
+    if (*buf)
+        cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc((void **)buf, want * sizeof(T));
+    if (e == cudaSuccess)
+        *cap = want;
+    return e;
+}
+
+template <typename T>
+static cudaError_t upload(cvb_ctx *ctx, const std::vector<T> &v, const T **out)
+{
+    void *d = nullptr;
+    size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess)
+        return e;
+    ctx->owned.push_back(d);
+    if (!v.empty())
+        e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T *)d;
+    return e;
+}
+
+extern "C" const char *cvb_version(void) { return "covest_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *cvb_last_error(const cvb_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int cvb_n_param(const cvb_ctx *ctx) { return ctx ? ctx->desc.n_param : CVB_EINVAL; }
+
+extern "C" int cvb_device_sm_count(const cvb_ctx *ctx) { return ctx ? ctx->n_sm : CVB_EINVAL; }
+
+extern "C" void cvb_ctx_destroy(cvb_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    for (void *p : ctx->owned)
+        cudaFree(p);
+    void *bufs[] = {ctx->d_params, ctx->d_ll,      ctx->d_probs, ctx->d_cand_ll, ctx->d_sel_ll,
+                    ctx->d_rows,   ctx->d_cand_idx, ctx->d_sel_idx, ctx->d_axes,   ctx->d_counter,
+                    ctx->d_sink};
+    for (void *p : bufs)
+        if (p)
+            cudaFree(p);
+    for (cudaEvent_t e : ctx->ev)
+        cudaEventDestroy(e);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n_bins,
+                              const int32_t *bin_j, const double *bin_h, double tail,
+                              double threshold, const double *bounds, const double *comb,
+                              const double *pow3, int device, cvb_ctx **out_ctx)
+{
+    cvb_ctx *ctx = nullptr; /* errors before the context exists go to the thread-local slot */
+    if (!out_ctx)
+        return fail(ctx, CVB_EINVAL, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    if (model_kind != CVB_MODEL_BASIC && model_kind != CVB_MODEL_REPEATS)
+        return fail(ctx, CVB_EINVAL, "model_kind must be 0 (basic) or 1 (repeats)");
+    if (k < 1 || r < k)
+        return fail(ctx, CVB_EINVAL, "need 1 <= k <= r");
+    if (max_error < 1 || max_error > k + 1 || max_error > CV_MAX_ERR)
+        return fail(ctx, CVB_EINVAL, "max_error must be in [1, min(k+1, 64)]");
+    if (!bin_j || !bin_h || !bounds)
+        return fail(ctx, CVB_EINVAL, "bin_j, bin_h and bounds are required");
+    CvHostTables T;
+    std::string why = cv_build_tables(n_bins, bin_j, bin_h, T);
+    if (!why.empty())
+        return fail(ctx, CVB_EINVAL, why);
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(ctx, CVB_ECUDA,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
+                        " (libcovest_b200 has no CPU path)");
+    }
+    if (device < 0 || device >= n_dev)
+        return fail(ctx, CVB_EINVAL, "device ordinal out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return fail_cuda(ctx, e, "cudaSetDevice");
+
+    cvb_ctx *c = new cvb_ctx();
+    c->device = device;
+    CvModelDesc &m = c->desc;
+    memset(&m, 0, sizeof(m));
+    m.model_kind = model_kind;
+    m.k = k;
+    m.r = r;
+    m.n_err = max_error;
+    m.n_param = model_kind ? 5 : 2;
+    m.n_bins = n_bins;
+    m.n_rows = T.n_rows;
+    m.n_blocks = T.n_blocks;
+    m.max_bin = T.max_bin;
+    m.tail = tail;
+    m.threshold = threshold;
+    for (int i = 0; i < CV_MAX_PARAMS; i++) {
+        m.lo[i] = i < m.n_param ? bounds[2 * i] : NAN;
+        m.hi[i] = i < m.n_param ? bounds[2 * i + 1] : NAN;
+    }
+    for (int s = 0; s < max_error; s++) {
+        if (comb) {
+            m.comb[s] = comb[s];
+        } else { /* C(k,s) * 3^s, exact in long double for every k <= 63 */
+            long double v = 1.0L;
+            for (int i = 1; i <= s; i++)
+                v = v * (long double)(k - s + i) / (long double)i;
+            m.comb[s] = (double)(v * powl(3.0L, (long double)s));
+        }
+        m.pow3[s] = pow3 ? pow3[s] : (s == 0 ? 1.0 : pow(3.0, (double)-s));
+    }
+
+    int rc = CVB_OK;
+    do {
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+            break;
+        c->n_sm = prop.multiProcessorCount;
+        if (prop.major < 10) {
+            rc = fail(nullptr, CVB_ECUDA,
+                      std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
+                          std::to_string(prop.minor) + "); this library holds sm_100a code only");
+            break;
+        }
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess)
+            break;
+        CvTables &t = m.tab;
+        if ((e = upload(c, T.row_j0, &t.row_j0)) != cudaSuccess) break;
+        if ((e = upload(c, T.row_head_h, &t.row_head_h)) != cudaSuccess) break;
+        if ((e = upload(c, T.row_head_l, &t.row_head_l)) != cudaSuccess) break;
+        if ((e = upload(c, T.row_up, &t.row_up)) != cudaSuccess) break;
+        if ((e = upload(c, T.row_dn, &t.row_dn)) != cudaSuccess) break;
+        if ((e = upload(c, T.slot_mult, &t.slot_mult)) != cudaSuccess) break;
+        if ((e = upload(c, T.slot_h, &t.slot_h)) != cudaSuccess) break;
+        if ((e = upload(c, T.slot_bin, &t.slot_bin)) != cudaSuccess) break;
+        if ((e = upload(c, T.seg_first, &t.seg_first)) != cudaSuccess) break;
+        if ((e = upload(c, T.seg_len, &t.seg_len)) != cudaSuccess) break;
+        if ((e = upload(c, T.blk_seg_begin, &t.blk_seg_begin)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&c->d_counter, sizeof(unsigned long long))) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&c->d_sink, 64)) != cudaSuccess) break;
+    } while (0);
+    if (rc == CVB_OK && e != cudaSuccess)
+        rc = fail_cuda(nullptr, e, "context setup");
+    if (rc != CVB_OK) {
+        cvb_ctx_destroy(c);
+        return rc;
+    }
+    *out_ctx = c;
+    return CVB_OK;
+}
+
+/* ---- timing ------------------------------------------------------------------------------- */
+extern "C" int cvb_set_timing(cvb_ctx *ctx, int enabled)
+{
+    if (!ctx)
+        return CVB_EINVAL;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (enabled && ctx->ev.empty()) {
+        ctx->ev.resize(2 * CVB_MAX_TIMED_CHUNKS);
+        for (auto &e : ctx->ev)
+            CU(cudaEventCreate(&e), "cudaEventCreate");
+    }
+    ctx->timing = enabled != 0;
+    ctx->timed_chunks = 0;
+    return CVB_OK;
+}
+
+extern "C" int cvb_last_kernel_ms(cvb_ctx *ctx, double *out_ms, int *out_launches)
+{
+    if (!ctx)
+        return CVB_EINVAL;
+    if (out_launches)
+        *out_launches = ctx->last_launches;
+    if (out_ms) {
+        *out_ms = 0.0;
+        if (!ctx->timing)
+            return fail(ctx, CVB_EINVAL, "timing is off (cvb_set_timing)");
+        CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+        for (int i = 0; i < ctx->timed_chunks; i++) {
+            float ms = 0.f;
+            CU(cudaEventSynchronize(ctx->ev[2 * i + 1]), "cudaEventSynchronize");
+            CU(cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]), "cudaEventElapsedTime");
+            *out_ms += ms;
+        }
+    }
+    return CVB_OK;
+}
+
+/* one loglik launch, optionally bracketed by events */
+static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_params, long long n,
+                         int clip, double *d_ll, double *d_probs, cudaStream_t s)
+{
+    bool timed = ctx->timing && ctx->timed_chunks < CVB_MAX_TIMED_CHUNKS;
+    if (timed)
+        CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks], s), "cudaEventRecord");
+    CU(cv_launch_loglik(ctx->desc, lat, d_params, n, clip, d_ll, d_probs, ctx->d_counter, ctx->n_sm, s),
+       "cv_loglik_kernel launch");
+    if (timed) {
+        CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks + 1], s), "cudaEventRecord");
+        ctx->timed_chunks++;
+    }
+    ctx->last_launches++;
+    return CVB_OK;
+}
+
+static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int clip, double *out_p,
+                      double *out_ll, void *stream)
+{
+    if (!ctx)
+        return CVB_EINVAL;
+    if (n_points < 0 || (n_points > 0 && !params))
+        return fail(ctx, CVB_EINVAL, "n_points < 0 or params is NULL");
+    if (!out_ll && !out_p)
+        return fail(ctx, CVB_EINVAL, "no output buffer");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->timed_chunks = 0;
+    ctx->last_launches = 0;
+    if (n_points == 0)
+        return CVB_OK;
+    const int np = ctx->desc.n_param;
+    const long long nb = ctx->desc.n_bins;
+    const bool p_dev = is_device_ptr(params);
+    const bool l_dev = out_ll ? is_device_ptr(out_ll) : true;
+    const bool q_dev = out_p ? is_device_ptr(out_p) : true;
+    const bool all_dev = p_dev && l_dev && q_dev;
+    CvLattice lat;
+    memset(&lat, 0, sizeof(lat));
+
+    long long chunk = all_dev ? n_points : CVB_CHUNK_POINTS;
+    if (out_p && !q_dev) { /* keep the probability staging buffer below ~1 GiB */
+        long long lim = (1LL << 27) / (nb > 0 ? nb : 1);
+        if (lim < 1)
+            lim = 1;
+        if (chunk > lim)
+            chunk = lim;
+    }
+    if (chunk > n_points)
+        chunk = n_points;
+    if (!p_dev)
+        CU(grow(&ctx->d_params, &ctx->cap_params, (size_t)chunk * np), "cudaMalloc(params staging)");
+    if (!l_dev || !out_ll)
+        CU(grow(&ctx->d_ll, &ctx->cap_ll, (size_t)chunk), "cudaMalloc(loglik staging)");
+    if (out_p && !q_dev)
+        CU(grow(&ctx->d_probs, &ctx->cap_probs, (size_t)chunk * nb), "cudaMalloc(probs staging)");
+
+    for (long long off = 0; off < n_points; off += chunk) {
+        long long n = n_points - off < chunk ? n_points - off : chunk;
+        const double *dp = params + off * np;
+        if (!p_dev) {
+            CU(cudaMemcpyAsync(ctx->d_params, dp, (size_t)n * np * sizeof(double),
+                               cudaMemcpyHostToDevice, s),
+               "cudaMemcpyAsync(params)");
+            dp = ctx->d_params;
+        }
+        double *dl = (out_ll && l_dev) ? out_ll + off : ctx->d_ll;
+        double *dq = out_p ? (q_dev ? out_p + off * nb : ctx->d_probs) : nullptr;
+        int rc = launch_loglik(ctx, lat, dp, n, clip, dl, dq, s);
+        if (rc != CVB_OK)
+            return rc;
+        if (out_ll && !l_dev)
+            CU(cudaMemcpyAsync(out_ll + off, dl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s),
+               "cudaMemcpyAsync(loglik)");
+        if (out_p && !q_dev)
+            CU(cudaMemcpyAsync(out_p + off * nb, dq, (size_t)n * nb * sizeof(double),
+                               cudaMemcpyDeviceToHost, s),
+               "cudaMemcpyAsync(probs)");
+        if (!all_dev && off + chunk < n_points)
+            CU(cudaStreamSynchronize(s), "cudaStreamSynchronize"); /* staging is reused */
+    }
+    if (!all_dev)
+        CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    return CVB_OK;
+}
+
+extern "C" int cvb_loglik_batch(cvb_ctx *ctx, int64_t n_points, const double *params, double *out_ll,
+                                void *stream)
+{
+    if (ctx && !out_ll)
+        return fail(ctx, CVB_EINVAL, "out_ll is NULL");
+    return eval_batch(ctx, n_points, params, 1, nullptr, out_ll, stream);
+}
+
+extern "C" int cvb_probs_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int clip,
+                               double *out_p, double *out_ll, void *stream)
+{
+    if (ctx && !out_p)
+        return fail(ctx, CVB_EINVAL, "out_p is NULL");
+    return eval_batch(ctx, n_points, params, clip ? 1 : 0, out_p, out_ll, stream);
+}
+
+/* ---- top-K -------------------------------------------------------------------------------- */
+static int ensure_topk(cvb_ctx *ctx, int K)
+{
+    if (K <= ctx->cap_k)
+        return CVB_OK;
+    void *old[] = {ctx->d_cand_ll, ctx->d_cand_idx, ctx->d_sel_ll, ctx->d_sel_idx, ctx->d_rows};
+    for (void *p : old)
+        if (p)
+            cudaFree(p);
+    ctx->d_cand_ll = ctx->d_sel_ll = ctx->d_rows = nullptr;
+    ctx->d_cand_idx = ctx->d_sel_idx = nullptr;
+    ctx->cap_k = 0;
+    ctx->topk_ctas = 2 * ctx->n_sm;
+    size_t nc = (size_t)ctx->topk_ctas * K;
+    CU(cudaMalloc((void **)&ctx->d_cand_ll, nc * sizeof(double)), "cudaMalloc(topk)");
+    CU(cudaMalloc((void **)&ctx->d_cand_idx, nc * sizeof(long long)), "cudaMalloc(topk)");
+    CU(cudaMalloc((void **)&ctx->d_sel_ll, (size_t)K * sizeof(double)), "cudaMalloc(topk)");
+    CU(cudaMalloc((void **)&ctx->d_sel_idx, (size_t)K * sizeof(long long)), "cudaMalloc(topk)");
+    CU(cudaMalloc((void **)&ctx->d_rows, (size_t)K * (1 + CV_MAX_PARAMS) * sizeof(double)),
+       "cudaMalloc(topk)");
+    ctx->cap_k = K;
+    return CVB_OK;
+}
+
+/* d_ll: device, n entries.  params: device or null (lattice). */
+static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, const double *d_params,
+                       long long n, int K, double *out_rows, cudaStream_t s)
+{
+    int rc = ensure_topk(ctx, K);
+    if (rc != CVB_OK)
+        return rc;
+    int ctas = ctx->topk_ctas;
+    if ((long long)ctas * 1024 > n) /* small inputs: fewer, fuller slices */
+        ctas = (int)((n + 1023) / 1024);
+    if (ctas < 1)
+        ctas = 1;
+    CU(cv_launch_topk(d_ll, n, K, ctx->d_cand_ll, ctx->d_cand_idx, ctas, ctx->d_sel_ll,
+                      ctx->d_sel_idx, s),
+       "cv_topk_select launch");
+    const int np = ctx->desc.n_param;
+    const bool r_dev = is_device_ptr(out_rows);
+    double *dr = r_dev ? out_rows : ctx->d_rows;
+    CU(cv_launch_gather_rows(lat, d_params, np, ctx->d_sel_ll, ctx->d_sel_idx, K, dr, s),
+       "cv_gather_rows launch");
+    ctx->last_launches += 3;
+    if (!r_dev) {
+        CU(cudaMemcpyAsync(out_rows, dr, (size_t)K * (1 + np) * sizeof(double), cudaMemcpyDeviceToHost, s),
+           "cudaMemcpyAsync(rows)");
+        CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    }
+    return CVB_OK;
+}
+
+extern "C" int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const double *params,
+                        int k_best, double *out_rows, void *stream)
+{
+    if (!ctx)
+        return CVB_EINVAL;
+    if (n_points < 0 || k_best < 1 || !out_rows || (n_points > 0 && (!ll || !params)))
+        return fail(ctx, CVB_EINVAL, "bad arguments to cvb_topk");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const int np = ctx->desc.n_param;
+    ctx->last_launches = 0;
+    const double *dl = ll, *dp = params;
+    if (n_points > 0 && !is_device_ptr(ll)) {
+        CU(grow(&ctx->d_ll, &ctx->cap_ll, (size_t)n_points), "cudaMalloc(loglik staging)");
+        CU(cudaMemcpyAsync(ctx->d_ll, ll, (size_t)n_points * sizeof(double), cudaMemcpyHostToDevice, s),
+           "cudaMemcpyAsync(ll)");
+        dl = ctx->d_ll;
+    }
+    if (n_points > 0 && !is_device_ptr(params)) {
+        CU(grow(&ctx->d_params, &ctx->cap_params, (size_t)n_points * np), "cudaMalloc(params staging)");
+        CU(cudaMemcpyAsync(ctx->d_params, params, (size_t)n_points * np * sizeof(double),
+                           cudaMemcpyHostToDevice, s),
+           "cudaMemcpyAsync(params)");
+        dp = ctx->d_params;
+    }
+    CvLattice lat;
+    memset(&lat, 0, sizeof(lat));
+    return topk_device(ctx, lat, dl, dp, n_points, k_best, out_rows, s);
+}
+
+/* ---- lattice ------------------------------------------------------------------------------ */
+extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double *axis_values,
+                                int64_t first, int64_t stride, int64_t count, double *out_ll,
+                                int k_best, double *out_rows, void *stream)
+{
+    if (!ctx)
+        return CVB_EINVAL;
+    if (!axis_len || !axis_values || first < 0 || stride < 1 || count < 0)
+        return fail(ctx, CVB_EINVAL, "bad lattice arguments");
+    if (k_best < 0 || (k_best > 0 && !out_rows))
+        return fail(ctx, CVB_EINVAL, "k_best > 0 needs out_rows");
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const int np = ctx->desc.n_param;
+    ctx->timed_chunks = 0;
+    ctx->last_launches = 0;
+    size_t total_vals = 0;
+    double total_pts = 1.0;
+    for (int a = 0; a < np; a++) {
+        if (axis_len[a] < 1)
+            return fail(ctx, CVB_EINVAL, "empty lattice axis");
+        total_vals += (size_t)axis_len[a];
+        total_pts *= (double)axis_len[a];
+    }
+    if (count > 0 && (double)first + (double)(count - 1) * (double)stride >= total_pts)
+        return fail(ctx, CVB_EINVAL, "lattice slice runs past the end of the lattice");
+    CU(grow(&ctx->d_axes, &ctx->cap_axes, total_vals), "cudaMalloc(axes)");
+    CU(cudaMemcpyAsync(ctx->d_axes, axis_values, total_vals * sizeof(double), cudaMemcpyHostToDevice, s),
+       "cudaMemcpyAsync(axes)");
+    CvLattice lat;
+    memset(&lat, 0, sizeof(lat));
+    lat.enabled = 1;
+    lat.n_axes = np;
+    size_t at = 0;
+    for (int a = 0; a < np; a++) {
+        lat.len[a] = axis_len[a];
+        lat.axis[a] = ctx->d_axes + at;
+        at += (size_t)axis_len[a];
+    }
+    lat.first = first;
+    lat.stride = stride;
+    const bool l_dev = out_ll && is_device_ptr(out_ll);
+    double *dl = l_dev ? out_ll : nullptr;
+    if (!dl) {
+        CU(grow(&ctx->d_ll, &ctx->cap_ll, (size_t)(count > 0 ? count : 1)), "cudaMalloc(loglik staging)");
+        dl = ctx->d_ll;
+    }
+    if (count > 0) {
+        int rc = launch_loglik(ctx, lat, nullptr, count, 1, dl, nullptr, s);
+        if (rc != CVB_OK)
+            return rc;
+    }
+    bool need_sync = false;
+    if (out_ll && !l_dev && count > 0) {
+        CU(cudaMemcpyAsync(out_ll, dl, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, s),
+           "cudaMemcpyAsync(loglik)");
+        need_sync = true;
+    }
+    if (k_best > 0) {
+        int rc = topk_device(ctx, lat, dl, nullptr, count, k_best, out_rows, s);
+        if (rc != CVB_OK)
+            return rc;
+    }
+    if (need_sync)
+        CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    return CVB_OK;
+}
+
+/* ---- roofline probe ----------------------------------------------------------------------- */
+extern "C" int cvb_fp64_peak(cvb_ctx *ctx, int kind, int reps, double *out_tflops)
+{
+    if (!ctx || !out_tflops || (kind != 0 && kind != 1))
+        return ctx ? fail(ctx, CVB_EINVAL, "bad arguments to cvb_fp64_peak") : CVB_EINVAL;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a), "cudaEventCreate");
+    CU(cudaEventCreate(&b), "cudaEventCreate");
+    double best = 0.0, flop = 0.0;
+    if (reps < 1)
+        reps = 1;
+    for (int rep = 0; rep < reps + 1; rep++) { /* first pass warms up */
+        CU(cudaEventRecord(a, ctx->stream), "cudaEventRecord");
+        CU(cv_launch_peak_probe(kind, ctx->n_sm * 8, 4096, ctx->d_sink, &flop, ctx->stream),
+           "cv_peak_probe launch");
+        CU(cudaEventRecord(b, ctx->stream), "cudaEventRecord");
+        CU(cudaEventSynchronize(b), "cudaEventSynchronize");
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b), "cudaEventElapsedTime");
+        if (rep > 0 && ms > 0.f) {
+            double tf = flop / (ms * 1e-3) / 1e12;
+            if (tf > best)
+                best = tf;
+        }
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *out_tflops = best;
+    return CVB_OK;
+}

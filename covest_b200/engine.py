@@ -1,0 +1,198 @@
+"""LikelihoodContext: a histogram resident on one B200 plus the batched evaluators over it.
+
+Thin object wrapper over the C ABI (include/covest_b200.h).  Buffers may be numpy arrays (host;
+the copies to and from the device are part of the call) or CUDA torch tensors (used in place).
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+from . import _capi
+
+
+class DeviceError(RuntimeError):
+    """An error reported by libcovest_b200 (bad argument or CUDA failure)."""
+
+
+def default_device():
+    for var in ('COVEST_B200_DEVICE', 'LOCAL_RANK'):
+        v = os.environ.get(var)
+        if v not in (None, ''):
+            return int(v)
+    return 0
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, 'data_ptr') and hasattr(x, 'is_cuda') and x.is_cuda
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch_cuda(x):
+        return ctypes.c_void_p(x.data_ptr())
+    return ctypes.c_void_p(x.ctypes.data)
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    if hasattr(stream, 'cuda_stream'):
+        return ctypes.c_void_p(stream.cuda_stream)
+    return ctypes.c_void_p(int(stream))
+
+
+class LikelihoodContext:
+    """Device copies of one histogram and its tables (models.py:19-31, :175-183 state)."""
+
+    def __init__(self, model_kind, k, r, max_error, bin_j, bin_h, tail, threshold, bounds, comb,
+                 pow3=None, device=None):
+        self._lib = _capi.load()
+        self._ctx = ctypes.c_void_p()
+        self.n_param = 5 if model_kind == _capi.MODEL_REPEATS else 2
+        self.n_bins = len(bin_j)
+        self.device = default_device() if device is None else int(device)
+        j = np.ascontiguousarray(bin_j, dtype=np.int32)
+        h = np.ascontiguousarray(bin_h, dtype=np.float64)
+        b = []
+        for lo, hi in bounds:
+            b += [math.nan if lo is None else float(lo), math.nan if hi is None else float(hi)]
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        cm = np.ascontiguousarray([float(v) for v in comb[:max_error]], dtype=np.float64)
+        if pow3 is None:
+            pow3 = [1.0 if s == 0 else float(3 ** -s) for s in range(max_error)]
+        p3 = np.ascontiguousarray(pow3, dtype=np.float64)
+        thr = math.nan if threshold is None else float(threshold)
+        rc = self._lib.cvb_ctx_create(int(model_kind), int(k), int(r), int(max_error), len(j),
+                                      j.ctypes.data_as(_capi.c_int32_p),
+                                      h.ctypes.data_as(_capi.c_double_p), float(tail), thr,
+                                      b.ctypes.data_as(_capi.c_double_p),
+                                      cm.ctypes.data_as(_capi.c_double_p),
+                                      p3.ctypes.data_as(_capi.c_double_p), self.device,
+                                      ctypes.byref(self._ctx))
+        if rc != _capi.CVB_OK:
+            msg = self._lib.cvb_last_error(None).decode()
+            self._ctx = ctypes.c_void_p()
+            raise DeviceError('cvb_ctx_create failed (%d): %s' % (rc, msg))
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != _capi.CVB_OK:
+            raise DeviceError('%s failed (%d): %s' % (what, rc, self._lib.cvb_last_error(self._ctx).decode()))
+
+    def close(self):
+        if getattr(self, '_ctx', None) is not None and self._ctx.value:
+            self._lib.cvb_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _points(self, points):
+        if _is_torch_cuda(points):
+            import torch
+            if points.dtype != torch.float64 or not points.is_contiguous():
+                raise ValueError('device points must be a contiguous float64 tensor')
+            if points.numel() % self.n_param:
+                raise ValueError('points must have %d columns' % self.n_param)
+            return points, points.numel() // self.n_param
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.n_param)
+        return pts, len(pts)
+
+    # -- evaluators ------------------------------------------------------------------------
+    def loglik(self, points, out=None, stream=None):
+        """compute_loglikelihood over the rows of `points` (models.py:100-117)."""
+        pts, n = self._points(points)
+        if out is None:
+            if _is_torch_cuda(pts):
+                import torch
+                out = torch.empty(n, dtype=torch.float64, device=pts.device)
+            else:
+                out = np.empty(n, dtype=np.float64)
+        self._check(self._lib.cvb_loglik_batch(self._ctx, n, _ptr(pts), _ptr(out), _stream_ptr(stream)),
+                    'cvb_loglik_batch')
+        return out
+
+    def probs(self, points, clip=False, with_loglik=False, stream=None):
+        """compute_probabilities over the rows of `points` (models.py:81-98, :211-242): an
+        (n_points, n_bins) array whose columns follow the key order of `hist`."""
+        pts, n = self._points(points)
+        if _is_torch_cuda(pts):
+            import torch
+            out = torch.zeros((n, self.n_bins), dtype=torch.float64, device=pts.device)
+            ll = torch.empty(n, dtype=torch.float64, device=pts.device) if with_loglik else None
+        else:
+            out = np.zeros((n, self.n_bins), dtype=np.float64)
+            ll = np.empty(n, dtype=np.float64) if with_loglik else None
+        self._check(self._lib.cvb_probs_batch(self._ctx, n, _ptr(pts), int(bool(clip)), _ptr(out),
+                                              _ptr(ll), _stream_ptr(stream)), 'cvb_probs_batch')
+        return (out, ll) if with_loglik else out
+
+    def topk(self, ll, points, k_best, stream=None):
+        """Best-first (k_best, 1 + n_param) rows (loglik, params...)."""
+        pts, n = self._points(points)
+        if _is_torch_cuda(pts):
+            import torch
+            rows = torch.empty((k_best, 1 + self.n_param), dtype=torch.float64, device=pts.device)
+            llb = ll
+        else:
+            rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64)
+            llb = np.ascontiguousarray(ll, dtype=np.float64)
+        self._check(self._lib.cvb_topk(self._ctx, n, _ptr(llb), _ptr(pts), int(k_best), _ptr(rows),
+                                       _stream_ptr(stream)), 'cvb_topk')
+        return rows
+
+    def lattice_eval(self, axes, first=0, stride=1, count=None, want_ll=True, k_best=0,
+                     out_ll=None, stream=None):
+        """Evaluate the Cartesian lattice of `axes` (one 1-D array per model parameter, last axis
+        fastest) at indices first + i*stride, i < count, generating the points on the device.
+        Returns (ll or None, rows or None)."""
+        if len(axes) != self.n_param:
+            raise ValueError('need %d axes' % self.n_param)
+        lens = np.ascontiguousarray([len(a) for a in axes], dtype=np.int32)
+        vals = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in axes]))
+        total = int(np.prod(lens.astype(np.int64)))
+        if count is None:
+            count = max(0, (total - first + stride - 1) // stride)
+        ll = out_ll
+        if ll is None and want_ll:
+            ll = np.empty(count, dtype=np.float64)
+        rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64) if k_best > 0 else None
+        self._check(self._lib.cvb_lattice_eval(self._ctx, lens.ctypes.data_as(_capi.c_int32_p),
+                                               vals.ctypes.data_as(_capi.c_double_p), int(first),
+                                               int(stride), int(count), _ptr(ll), int(k_best),
+                                               _ptr(rows), _stream_ptr(stream)), 'cvb_lattice_eval')
+        return ll, rows
+
+    # -- measurement -----------------------------------------------------------------------
+    def fp64_peak(self, kind=0, reps=5):
+        """Measured FP64 throughput (TFLOP/s) of register-resident DFMA (0) / DMMA (1) chains."""
+        out = ctypes.c_double()
+        self._check(self._lib.cvb_fp64_peak(self._ctx, int(kind), int(reps), ctypes.byref(out)),
+                    'cvb_fp64_peak')
+        return out.value
+
+    def set_timing(self, on=True):
+        self._check(self._lib.cvb_set_timing(self._ctx, int(bool(on))), 'cvb_set_timing')
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_double()
+        n = ctypes.c_int()
+        self._check(self._lib.cvb_last_kernel_ms(self._ctx, ctypes.byref(ms), ctypes.byref(n)),
+                    'cvb_last_kernel_ms')
+        return ms.value, n.value
+
+    @property
+    def sm_count(self):
+        return self._lib.cvb_device_sm_count(self._ctx)

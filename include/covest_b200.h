@@ -1,0 +1,119 @@
+/*
+ * covest_b200.h -- C ABI of libcovest_b200.so, the B200 (sm_100a) implementation of CovEst's
+ * likelihood hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / CUDA types.  The caller in
+ * the reference is Python (covest/models.py); the binding a maintainer would add is a ctypes stub
+ * (INTEGRATION.md shows it; covest_b200/_capi.py is this repo's own).  Reference lines are relative
+ * to the upstream mhozza/covest tree.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative CVB_E* code on failure; the message is
+ *     available from cvb_last_error(ctx) (ctx may be NULL for the error of a failed create);
+ *   - the caller owns every buffer it passes; a context owns device copies of the histogram and
+ *     the tables derived from it;
+ *   - buffer arguments documented "host or device" are inspected with cudaPointerGetAttributes:
+ *     device pointers are used in place, host pointers are staged through context-owned device
+ *     buffers (the copies are part of the call);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).  Calls with
+ *     host buffers return after the results are in the host buffer; calls where all buffers are
+ *     device pointers only enqueue work on the stream;
+ *   - a context is bound to one device and is not re-entrant; distinct contexts are independent;
+ *   - there is no CPU fallback: without a CUDA device every call fails with CVB_ECUDA.
+ */
+#ifndef COVEST_B200_H
+#define COVEST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CVB_API __attribute__((visibility("default")))
+#else
+#define CVB_API
+#endif
+
+#define CVB_OK 0
+#define CVB_EINVAL (-1) /* bad argument */
+#define CVB_ECUDA (-2)  /* CUDA runtime error (cvb_last_error has cudaGetErrorString) */
+#define CVB_ENOMEM (-3)
+
+#define CVB_MODEL_BASIC 0   /* covest/models.py:17  BasicModel   params (coverage, error_rate) */
+#define CVB_MODEL_REPEATS 1 /* covest/models.py:173 RepeatsModel params + (q1, q2, q) */
+
+typedef struct cvb_ctx cvb_ctx;
+
+/* Replaces the state BasicModel.__init__ / RepeatsModel.__init__ keep (covest/models.py:19-31,
+ * :175-183).
+ *   k, r        k-mer size and read length
+ *   max_error   number of error classes S actually summed (models.py:28-31: min(k+1, max_error))
+ *   n_bins      len(hist); bin_j[b] / bin_h[b] are the keys and counts of `hist` in dict order
+ *   tail        models.py:27
+ *   threshold   models.py:183 (repeats only); NaN = None (no cut-off)
+ *   bounds      n_param x 2 doubles (lo, hi) as models.py:23 / :179; NaN = open end
+ *   comb        max_error doubles comb[s] = C(k,s) * 3**s exactly as the host computed them
+ *               (models.py:25 uses scipy's floating comb); NULL = computed here in long double
+ *   pow3        max_error doubles 3 ** -s as the host computed them (models.py:77); NULL = here
+ *   device      CUDA device ordinal
+ */
+CVB_API int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n_bins, const int32_t *bin_j,
+                   const double *bin_h, double tail, double threshold, const double *bounds,
+                   const double *comb, const double *pow3, int device, cvb_ctx **out_ctx);
+
+CVB_API void cvb_ctx_destroy(cvb_ctx *ctx);
+
+CVB_API const char *cvb_last_error(const cvb_ctx *ctx);
+
+/* Replaces compute_loglikelihood (models.py:100-107) mapped over a batch, i.e.
+ * compute_loglikelihood_multi (models.py:109-117): out_ll[i] = loglikelihood of params row i
+ * (row-major n_points x n_param), arguments clipped to the bounds first (fit_to_bounds,
+ * models.py:60-69).  params / out_ll: host or device. */
+CVB_API int cvb_loglik_batch(cvb_ctx *ctx, int64_t n_points, const double *params, double *out_ll,
+                     void *stream);
+
+/* Replaces compute_probabilities (models.py:81-98, :211-242) over a batch: out_p is row-major
+ * n_points x n_bins, column b pairs with bin_j[b].  clip = 0 evaluates at the arguments as given
+ * (what compute_probabilities does), clip = 1 clips first.  out_ll may be NULL.
+ * params / out_p / out_ll: host or device. */
+CVB_API int cvb_probs_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int clip, double *out_p,
+                    double *out_ll, void *stream);
+
+/* The K best rows of a batch already evaluated: out_rows is row-major K x (1 + n_param),
+ * (loglik, params...), best first; ties resolved towards the lower index, NaN never preferred;
+ * rows beyond n_points are (-inf, NaN...).  Replaces the arg-max over Pool.map results in
+ * covest/grid.py:61-69 and covest/covest.py:69-78.  All buffers host or device. */
+CVB_API int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const double *params, int k_best,
+             double *out_rows, void *stream);
+
+/* A Cartesian lattice of candidate points generated on the device (no host->device parameter
+ * traffic): n_param axes, axis a has axis_len[a] values stored consecutively in axis_values
+ * (host).  Point i of the call is lattice index first + i * stride, last axis fastest -- the
+ * order of itertools.product in covest/grid.py:33.  Evaluates `count` points; out_ll (host or
+ * device, may be NULL) receives them; if k_best > 0, out_rows (host or device) receives the
+ * k_best best rows as in cvb_topk. */
+CVB_API int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double *axis_values,
+                     int64_t first, int64_t stride, int64_t count, double *out_ll, int k_best,
+                     double *out_rows, void *stream);
+
+/* Measures the FP64 roofline denominator on the context's device: kind 0 = dependent-free DFMA
+ * chains, kind 1 = DMMA m8n8k4 chains, both register resident.  *out_tflops = best of `reps`. */
+CVB_API int cvb_fp64_peak(cvb_ctx *ctx, int kind, int reps, double *out_tflops);
+
+/* Device time (ms, CUDA events on the launch stream) of the dominant kernel of the most recent
+ * cvb_loglik_batch / cvb_probs_batch / cvb_lattice_eval call, and how many kernels that call
+ * launched.  Timing is only recorded after cvb_set_timing(ctx, 1). */
+CVB_API int cvb_set_timing(cvb_ctx *ctx, int enabled);
+CVB_API int cvb_last_kernel_ms(cvb_ctx *ctx, double *out_ms, int *out_launches);
+
+/* number of model parameters of the context (2 or 5), number of SMs of its device */
+CVB_API int cvb_n_param(const cvb_ctx *ctx);
+CVB_API int cvb_device_sm_count(const cvb_ctx *ctx);
+CVB_API const char *cvb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

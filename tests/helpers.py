@@ -45,3 +45,11 @@ def rel_err_ll(got, want):
     rel[np.isnan(rel)] = np.inf
     rel[(got == want)] = 0.0
     return rel
+
+
+def context_for(oracle_model, device=None):
+    """A device LikelihoodContext holding the same model description as an oracle Model."""
+    from covest_b200.engine import LikelihoodContext
+    m = oracle_model
+    return LikelihoodContext(m.kind, m.k, m.r, m.max_error, m.bin_j, m.bin_h, m.tail, m.threshold,
+                             m.bounds, m.comb, device=device)
