@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched log-likelihood path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg5]
+
+Metric (BASELINE.json): log-likelihood evaluations per second counted as parameter point x
+histogram bin.  A step is one pass of the hot path over one batch of candidate points: every rank
+evaluates its slice of the candidate lattice (points resident in HBM), keeps its 64 best rows on
+the device and -- for N > 1 -- all-gathers them (NCCL) so that every rank holds the global best
+rows.  Weak scaling: the lattice is refined with N so that every rank always evaluates the same
+number of points.
+
+  value      device-resident inputs, CUDA-event timed, max over ranks
+  e2e        the same batch through the C ABI with HOST buffers (pinned), copies in the timed region
+  roofline   FP64 pipe: algorithmic flop of one launch / its CUDA-event duration / the DFMA peak
+             measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline / --impl reference: the reference's own C module (oracle/_ref) driven by a Python
+             restatement of models.py with a fork pool over all host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_BEST = 64
+METRIC = 'loglik_point_bin_evals_per_sec'
+UNIT = 'point*bin/s'
+POINTS_PER_RANK = {'cfg3': 1000000, 'cfg5': 12500000}
+
+
+def workload_axes(name, world):
+    """cfg3: 40 x 25 x 10 x 10 x 10 = 1e6 points; with N ranks the
+    coverage axis is refined N-fold (weak scaling).  cfg5: 1e8 points over 8 ranks."""
+    from covest_b200 import workload
+    theta = workload.CONFIGS[name]['theta']
+    if name == 'cfg3':
+        return workload.lattice_axes(theta, n_c=40 * world, n_e=25)
+    return workload.lattice_axes(theta, n_c=25 * world, n_e=50, n_q1=10, n_q2=10, n_q=100)
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons of one GPU while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_points(axes, n, seed=4242):
+    from covest_b200 import workload
+    total = int(np.prod([len(a) for a in axes]))
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(total, size=n, replace=False))
+    return np.vstack([workload.lattice_points(axes, first=int(i), count=1) for i in idx])
+
+
+def cpu_reference_rate(hist, cfg, axes, n_points, cores):
+    """point*bin/s of the reference's C module + models.py restatement over a fork pool."""
+    from oracle import covest_oracle as orc
+    kind = 'reference' if orc.ref_module() is not None else 'port'
+    m = orc.Model(cfg['model'], cfg['k'], cfg['r'], hist, 0, max_error=8)
+    pts = cpu_sample_points(axes, n_points)
+    t0 = time.perf_counter()
+    if kind == 'reference':
+        orc.ref_loglik_batch(m, pts, processes=cores)
+    else:
+        m.loglik_batch(pts, mode=orc.FAITHFUL, threads=cores)
+    dt = time.perf_counter() - t0
+    return n_points * len(hist) / dt, dt, kind
+
+
+def reference_histogram(name):
+    """The workload histogram for the CPU-only reference arm: drawn from the oracle's p_j (the
+    product arm draws it from the device's, the same numbers to ~1e-15)."""
+    from covest_b200 import workload
+    from oracle import covest_oracle as orc
+    c = workload.CONFIGS[name]
+    probe = orc.Model(c['model'], c['k'], c['r'], {j: 1 for j in range(1, c['bins'] + 1)}, 0, max_error=8)
+    p = probe.probs(list(c['theta']))
+    rng = np.random.default_rng(c['seed'])
+    h = rng.poisson(c['kmers'] * np.maximum(p, 0.0))
+    return {j: int(v) for j, v in zip(range(1, c['bins'] + 1), h)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from covest_b200 import workload
+    cfg = workload.CONFIGS[args.workload]
+    axes = workload_axes(args.workload, world)
+    hist = reference_histogram(args.workload)
+    cores = os.cpu_count() or 1
+    n = max(cores, 2 * cores if args.workload == 'cfg3' else cores)
+    rates, secs, kind = [], [], 'reference'
+    for step in range(args.warmup + args.steps):
+        rate, dt, kind = cpu_reference_rate(hist, cfg, axes, n, cores)
+        if step >= args.warmup:
+            rates.append(rate)
+            secs.append(dt)
+    value = float(np.mean(rates))
+    sample = '%d lattice points (seeded) x %d bins per step, fork pool of %d' % (n, len(hist), cores)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(secs) * 1e3),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (x87 f80 inside truncated_poisson)',
+        'data': 'synthetic', 'config': workload_config(args.workload, world, len(hist), axes),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, world, n_bins, axes):
+    lens = [len(a) for a in axes]
+    return {'workload': '%s: repeats model k=21 r=100, lattice %s = %d points x %d bins, %d per rank' % (
+        name, 'x'.join(map(str, lens)), int(np.prod(lens)), n_bins, int(np.prod(lens)) // world),
+        'bins': n_bins, 'points_per_rank': int(np.prod(lens)) // world, 'lattice': lens,
+        'max_error': 8, 'k_best': K_BEST, 'sharding': 'strided lattice slices, rank r takes index r + i*N',
+        'l2': 'flushed between timed steps (256 MiB write)'}
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from covest_b200 import parallel, workload
+    from covest_b200.models import RepeatsModel
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the library has no CPU path)')
+    torch.cuda.set_device(local_rank)
+    os.environ['COVEST_B200_DEVICE'] = str(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+
+    cfg = workload.CONFIGS[args.workload]
+    hist = workload.synthetic_histogram(args.workload)
+    model = RepeatsModel(cfg['k'], cfg['r'], hist, 0, max_error=8)
+    ctx = model.device_context
+    n_bins = len(hist)
+    axes = workload_axes(args.workload, world)
+    total = int(np.prod([len(a) for a in axes]))
+    count = total // world
+    if args.points:
+        count = min(count, args.points)
+
+    # the rank's candidate points, resident in HBM
+    host_pts = workload.lattice_points(axes, first=rank, stride=world, count=count)
+    dev_pts = torch.from_numpy(host_pts).to(dev)
+    dev_ll = torch.empty(count, dtype=torch.float64, device=dev)
+    pin_pts = torch.from_numpy(host_pts).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    terms = workload.term_counts(model, host_pts)
+    flop_launch = workload.algorithmic_flop(n_bins, terms)
+
+    peak_tflops = ctx.fp64_peak(0) if rank == 0 else None
+    peak_dmma = ctx.fp64_peak(1) if rank == 0 else None
+
+    def step_device():
+        ctx.loglik(dev_pts, out=dev_ll, stream=stream)
+        rows = ctx.topk(dev_ll, dev_pts, K_BEST, stream=stream)
+        if world > 1:
+            rows = parallel.merge_topk(parallel.allgather_rows(rows), K_BEST)
+        return rows
+
+    def step_host():
+        ll, rows = ctx.loglik_topk(pin_pts.numpy(), K_BEST)
+        if world > 1:
+            rows = parallel.merge_topk(parallel.allgather_rows(torch.from_numpy(rows).to(dev)), K_BEST)
+            rows = rows.cpu().numpy()
+        return rows
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    # ---- timed: device-resident inputs ----
+    ctx.set_timing(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms, launches = [], 0
+    with ClockSampler(local_rank) as clocks:
+        for a, b in ev:
+            flush.fill_(1)
+            barrier()
+            a.record(stream)
+            rows = step_device()
+            b.record(stream)
+            barrier()
+            ms, n = ctx.last_kernel_ms()
+            # last_kernel_ms reports the most recent call (top-K); the loglik launch is timed below
+            launches += 4  # loglik kernel + 2 top-K passes + row gather
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        # dominant kernel alone, CUDA events around the launch on the launching stream
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ctx.loglik(dev_pts, out=dev_ll, stream=stream)
+            torch.cuda.synchronize()
+            kernel_ms.append(ctx.last_kernel_ms()[0])
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * count * n_bins * args.steps / (total_ms * 1e-3)
+
+    # ---- timed: end to end with host buffers ----
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rows_host = step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * count * n_bins * args.steps / float(t.item())
+
+    best = rows if isinstance(rows, np.ndarray) else rows.cpu().numpy()
+    if rank == 0:
+        km = float(np.mean(kernel_ms))
+        achieved = flop_launch / (km * 1e-3) / 1e12
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args.workload, world, n_bins, axes),
+            'e2e': {'value': e2e_value, 'unit': UNIT,
+                    'h2d_bytes_per_step': int(count * 5 * 8),
+                    'd2h_bytes_per_step': int(count * 8 + K_BEST * 6 * 8)},
+            'gpu_launches': launches + args.steps,
+            'clocks': clocks.summary(),
+            'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                         'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': None,
+                         'kernel': 'cv_loglik_kernel', 'kernel_ms': km,
+                         'flop_per_launch': flop_launch, 'mean_terms_per_point': float(terms.mean()),
+                         'peak_source': 'register-resident DFMA chain measured in this run (cvb_fp64_peak); '
+                                        'DMMA m8n8k4 chain: %.2f TFLOP/s' % peak_dmma,
+                         'kernel_share_of_step': km * args.steps / total_ms if world == 1 else None},
+            'best_row': [float(x) for x in best[0]],
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            ref_hist = {j: int(v) for j, v in hist.items()}
+            n_cpu = 2 * cores
+            rate, dt, kind = cpu_reference_rate(ref_hist, cfg, axes, n_cpu, cores)
+            if dt < 8.0:  # aim for 10-30 s of CPU work
+                n_cpu = int(min(64 * cores, max(n_cpu, n_cpu * 15.0 / max(dt, 1e-3))))
+                rate, dt, kind = cpu_reference_rate(ref_hist, cfg, axes, n_cpu, cores)
+            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                    'sample': '%d seeded lattice points x %d bins in %.1f s' % (n_cpu, n_bins, dt)}
+        print(json.dumps(line), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5'])
+    ap.add_argument('--points', type=int, default=0, help='cap the points per rank (development)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -6,3 +6,5 @@ implementation of the likelihood in this package: without the compiled library a
 every evaluation raises.
 """
 __version__ = '0.1.0'
+# `covest --version`; 0.5.6 is the CovEst release whose interface and numerics are mirrored
+version_string = 'CovEst 0.5.6 (covest_b200 %s)' % __version__

@@ -53,6 +53,8 @@ def load():
     L.cvb_probs_batch.argtypes = [vp, i64, vp, ctypes.c_int, vp, vp, vp]
     L.cvb_topk.restype = ctypes.c_int
     L.cvb_topk.argtypes = [vp, i64, vp, vp, ctypes.c_int, vp, vp]
+    L.cvb_loglik_topk.restype = ctypes.c_int
+    L.cvb_loglik_topk.argtypes = [vp, i64, vp, vp, ctypes.c_int, vp, vp]
     L.cvb_lattice_eval.restype = ctypes.c_int
     L.cvb_lattice_eval.argtypes = [vp, c_int32_p, c_double_p, i64, i64, i64, vp, ctypes.c_int, vp,
                                    vp]
@@ -71,5 +73,5 @@ def load():
 
 
 EXPORTS = ('cvb_ctx_create', 'cvb_ctx_destroy', 'cvb_last_error', 'cvb_loglik_batch',
-           'cvb_probs_batch', 'cvb_topk', 'cvb_lattice_eval', 'cvb_fp64_peak', 'cvb_set_timing',
+           'cvb_probs_batch', 'cvb_topk', 'cvb_loglik_topk', 'cvb_lattice_eval', 'cvb_fp64_peak', 'cvb_set_timing',
            'cvb_last_kernel_ms', 'cvb_n_param', 'cvb_device_sm_count', 'cvb_version')

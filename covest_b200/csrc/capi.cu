@@ -304,20 +304,25 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
     return CVB_OK;
 }
 
+static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, const double *d_params,
+                       long long n, int K, double *out_rows, cudaStream_t s);
+
 static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int clip, double *out_p,
-                      double *out_ll, void *stream)
+                      double *out_ll, int k_best, double *out_rows, void *stream)
 {
     if (!ctx)
         return CVB_EINVAL;
     if (n_points < 0 || (n_points > 0 && !params))
         return fail(ctx, CVB_EINVAL, "n_points < 0 or params is NULL");
-    if (!out_ll && !out_p)
+    if (!out_ll && !out_p && k_best <= 0)
         return fail(ctx, CVB_EINVAL, "no output buffer");
+    if (k_best < 0 || (k_best > 0 && !out_rows))
+        return fail(ctx, CVB_EINVAL, "k_best > 0 needs out_rows");
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     ctx->timed_chunks = 0;
     ctx->last_launches = 0;
-    if (n_points == 0)
+    if (n_points == 0 && k_best <= 0)
         return CVB_OK;
     const int np = ctx->desc.n_param;
     const long long nb = ctx->desc.n_bins;
@@ -328,7 +333,10 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
     CvLattice lat;
     memset(&lat, 0, sizeof(lat));
 
-    long long chunk = all_dev ? n_points : CVB_CHUNK_POINTS;
+    /* the row gather of a top-K needs the whole batch resident: no chunking then */
+    long long chunk = (all_dev || k_best > 0) ? n_points : CVB_CHUNK_POINTS;
+    if (chunk < 1)
+        chunk = 1;
     if (out_p && !q_dev) { /* keep the probability staging buffer below ~1 GiB */
         long long lim = (1LL << 27) / (nb > 0 ? nb : 1);
         if (lim < 1)
@@ -342,6 +350,8 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
         CU(grow(&ctx->d_params, &ctx->cap_params, (size_t)chunk * np), "cudaMalloc(params staging)");
     if (!l_dev || !out_ll)
         CU(grow(&ctx->d_ll, &ctx->cap_ll, (size_t)chunk), "cudaMalloc(loglik staging)");
+    const double *dp_all = p_dev ? params : ctx->d_params;
+    const double *dl_all = (out_ll && l_dev) ? out_ll : ctx->d_ll;
     if (out_p && !q_dev)
         CU(grow(&ctx->d_probs, &ctx->cap_probs, (size_t)chunk * nb), "cudaMalloc(probs staging)");
 
@@ -369,6 +379,11 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
         if (!all_dev && off + chunk < n_points)
             CU(cudaStreamSynchronize(s), "cudaStreamSynchronize"); /* staging is reused */
     }
+    if (k_best > 0) {
+        int rc = topk_device(ctx, lat, dl_all, dp_all, n_points, k_best, out_rows, s);
+        if (rc != CVB_OK)
+            return rc;
+    }
     if (!all_dev)
         CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
     return CVB_OK;
@@ -379,7 +394,7 @@ extern "C" int cvb_loglik_batch(cvb_ctx *ctx, int64_t n_points, const double *pa
 {
     if (ctx && !out_ll)
         return fail(ctx, CVB_EINVAL, "out_ll is NULL");
-    return eval_batch(ctx, n_points, params, 1, nullptr, out_ll, stream);
+    return eval_batch(ctx, n_points, params, 1, nullptr, out_ll, 0, nullptr, stream);
 }
 
 extern "C" int cvb_probs_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int clip,
@@ -387,7 +402,15 @@ extern "C" int cvb_probs_batch(cvb_ctx *ctx, int64_t n_points, const double *par
 {
     if (ctx && !out_p)
         return fail(ctx, CVB_EINVAL, "out_p is NULL");
-    return eval_batch(ctx, n_points, params, clip ? 1 : 0, out_p, out_ll, stream);
+    return eval_batch(ctx, n_points, params, clip ? 1 : 0, out_p, out_ll, 0, nullptr, stream);
+}
+
+extern "C" int cvb_loglik_topk(cvb_ctx *ctx, int64_t n_points, const double *params, double *out_ll,
+                               int k_best, double *out_rows, void *stream)
+{
+    if (ctx && (k_best < 1 || !out_rows))
+        return fail(ctx, CVB_EINVAL, "cvb_loglik_topk needs k_best >= 1 and out_rows");
+    return eval_batch(ctx, n_points, params, 1, nullptr, out_ll, k_best, out_rows, stream);
 }
 
 /* ---- top-K -------------------------------------------------------------------------------- */

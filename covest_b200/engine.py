@@ -153,6 +153,20 @@ class LikelihoodContext:
                                        _stream_ptr(stream)), 'cvb_topk')
         return rows
 
+    def loglik_topk(self, points, k_best, want_ll=True, stream=None):
+        """loglik + topk in one call (the batch crosses the bus once): (ll or None, rows)."""
+        pts, n = self._points(points)
+        if _is_torch_cuda(pts):
+            import torch
+            ll = torch.empty(n, dtype=torch.float64, device=pts.device) if want_ll else None
+            rows = torch.empty((k_best, 1 + self.n_param), dtype=torch.float64, device=pts.device)
+        else:
+            ll = np.empty(n, dtype=np.float64) if want_ll else None
+            rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64)
+        self._check(self._lib.cvb_loglik_topk(self._ctx, n, _ptr(pts), _ptr(ll), int(k_best),
+                                              _ptr(rows), _stream_ptr(stream)), 'cvb_loglik_topk')
+        return ll, rows
+
     def lattice_eval(self, axes, first=0, stride=1, count=None, want_ll=True, k_best=0,
                      out_ll=None, stream=None):
         """Evaluate the Cartesian lattice of `axes` (one 1-D array per model parameter, last axis

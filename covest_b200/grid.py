@@ -1,0 +1,142 @@
+"""Candidate generators of the estimator, evaluated a whole set per device launch
+(reference: covest/grid.py).
+
+initial_grid      the random multi-start points (grid.py:82-114)
+optimize_grid     the multiplicative grid refinement (grid.py:17-79): every round's Cartesian
+                  candidate set -- 6^n points, 7776 for the repeats model -- is one batched
+                  evaluation instead of a Pool.map over pickled calls.
+
+`fn` may be any scalar objective.  If it has a `batch` attribute (CoverageEstimator.likelihood_f
+does) the round is a single call `fn.batch(list_of_points)`; a plain function is simply mapped.
+"""
+import itertools
+import random
+
+import numpy as np
+
+from . import constants
+from .perf import running_time, running_time_decorator
+from .utils import verbose_print
+
+
+def evaluate_all(fn, points):
+    """Objective values of `points`, through fn.batch when the objective offers it."""
+    points = list(points)
+    if not points:
+        return []
+    batch = getattr(fn, 'batch', None)
+    if batch is not None:
+        return [float(v) for v in batch(points)]
+    return [fn(p) for p in points]
+
+
+def _interval_in_bounds(interval, bounds, i):
+    if bounds is None or len(bounds) <= i or len(bounds[i]) != 2:
+        return interval
+    lo, hi = interval
+    b_lo, b_hi = bounds[i]
+    if b_lo is not None:
+        lo = max(lo, b_lo)
+    if b_hi is not None:
+        hi = min(hi, b_hi)
+    return lo, hi
+
+
+def _inside(value, bounds, i):
+    if bounds is None or len(bounds) <= i or len(bounds[i]) != 2:
+        return True
+    lo, hi = bounds[i]
+    return (lo is None or value >= lo) and (hi is None or value <= hi)
+
+
+def grid_candidates(center, step, depth, bounds=None, fix=None):
+    """Cartesian product of center_i * step**d, d in -depth..depth without 0, kept inside the
+    bounds; a fixed coordinate contributes its fixed value only (grid.py:20-43).  The centre
+    itself is never a candidate and a zero coordinate stays zero."""
+    axes = []
+    for i, var in enumerate(center):
+        if fix is not None and fix[i] is not None:
+            axes.append([fix[i]])
+            continue
+        axes.append([v for v in (var * step ** d for d in range(-depth, depth + 1) if d != 0)
+                     if _inside(v, bounds, i)])
+    return list(itertools.product(*axes))
+
+
+@running_time_decorator
+def optimize_grid(fn, initial_guess, bounds=None, maximize=False, fix=None,
+                  n_threads=constants.DEFAULT_THREAD_COUNT):
+    """Shrinking multiplicative grid search around the best point so far; returns the best
+    arguments.  `n_threads` is accepted for compatibility (the reference forks that many
+    workers); evaluation is batched instead."""
+    if fix is None:
+        fix = [None] * len(initial_guess)
+    sign = -1 if maximize else 1
+    best_val = sign * evaluate_all(fn, [initial_guess])[0]
+    best_args = initial_guess
+    step = constants.STEP
+    depth = constants.GRID_DEPTH
+    diff = 1
+    rounds = 0
+    try:
+        while diff > 0.1 or step > 1.001:
+            rounds += 1
+            diff = 0.0
+            grid = grid_candidates(best_args, step, depth, bounds, fix)
+            verbose_print('Iter : {}, Grid size: {}'.format(rounds, len(grid)))
+            with running_time('grid iteration'):
+                values = evaluate_all(fn, grid)
+            # same sequential bookkeeping as grid.py:65-69, including its use of the raw value
+            for args, val in zip(grid, values):
+                if sign * val < best_val:
+                    diff += best_val - val
+                    best_val = sign * val
+                    best_args = args
+            if diff < 1.0:
+                step = 1 + (step - 1) * 0.75
+            verbose_print('d:{} s:{}'.format(diff, step))
+            verbose_print('New args: {}, ll: {}'.format(best_args, best_val))
+    except KeyboardInterrupt:
+        verbose_print('Grid search interrupted')
+    verbose_print('Number of iterations in grid search:{}'.format(rounds))
+    return best_args
+
+
+def initial_grid(initial_guess, count=constants.INITIAL_GRID_COUNT, bounds=None, fix=None):
+    """`count` starting points: the guess itself, then count-1 points with every free coordinate
+    drawn uniformly from [v / 3, 3 v] cut to the bounds (grid.py:82-114; Python's global
+    `random`, seed it for reproducible runs)."""
+    if fix is None:
+        fix = [None] * len(initial_guess)
+    if count < 1:
+        return []
+    step = constants.INITIAL_GRID_STEP
+    points = [initial_guess]
+    for _ in range(count - 1):
+        boxes = [_interval_in_bounds((v / step, v * step), bounds, i)
+                 for i, v in enumerate(initial_guess)]
+        points.append([random.uniform(*box) if fix[i] is None else fix[i]
+                       for i, box in enumerate(boxes)])
+    return points
+
+
+def lattice_search(model, axes, k_best=64):
+    """Best rows of a Cartesian candidate lattice, sharded over the ranks of torch.distributed
+    when it is initialised: every rank evaluates a strided slice with
+    points generated on the device, the per-rank best rows are all-gathered, and every rank
+    returns the same global (k_best, 1 + n_param) best-first array."""
+    from . import parallel
+    total = int(np.prod([len(a) for a in axes]))
+    ctx = model.device_context
+
+    def evaluate_slice(first, stride, count):
+        _, rows = ctx.lattice_eval(axes, first=first, stride=stride, count=count, want_ll=False,
+                                   k_best=k_best)
+        rank, world = parallel.world()
+        if world > 1:
+            import torch
+            return torch.from_numpy(rows).to(torch.device('cuda', ctx.device))
+        return rows
+
+    rows = parallel.sharded_best_rows(evaluate_slice, total, k_best)
+    return rows.cpu().numpy() if hasattr(rows, 'cpu') else np.asarray(rows)

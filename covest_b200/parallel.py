@@ -1,0 +1,84 @@
+"""Multi-GPU sharding of candidate sets: one process per GPU (torchrun), static slices, no
+collective on the data path; one small all-gather of every rank's best rows per round
+(SURVEY.md section 8(e)).  The reference's counterpart is Pool.map over candidates
+(covest/grid.py:61-64, covest/covest.py:67-68).
+
+Works with CUDA tensors over NCCL and with CPU tensors over gloo (the CPU test-suite).
+"""
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def world():
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    try:
+        dist = _dist()
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def shard_strided(total, rank, world_size):
+    """(first, stride, count) of the rank's slice: indices rank, rank + W, ...  Striding spreads
+    the expensive region of a lattice (small q: many copy-number terms) over all ranks."""
+    count = (total - rank + world_size - 1) // world_size if total > rank else 0
+    return rank, world_size, count
+
+
+def shard_contiguous(total, rank, world_size):
+    """[lo, hi) of a balanced contiguous split."""
+    base, extra = divmod(total, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allgather_rows(rows):
+    """All ranks' (K, C) row blocks stacked in rank order: (W*K, C) tensor on the same device."""
+    import torch
+    dist = _dist()
+    if not isinstance(rows, torch.Tensor):
+        rows = torch.from_numpy(np.ascontiguousarray(rows))
+    rank, w = world()
+    if w == 1:
+        return rows
+    rows = rows.contiguous()
+    out = torch.empty((w * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out, rows)
+    return out
+
+
+def merge_topk(rows, k_best):
+    """The k_best best rows (column 0 = log-likelihood, larger is better) of a stacked block,
+    best first.  NaN and padding (-inf) sort last; ties keep gather order (lower rank, then lower
+    local position), so every rank selects the same rows."""
+    import torch
+    if not isinstance(rows, torch.Tensor):
+        rows = torch.from_numpy(np.ascontiguousarray(rows))
+    key = rows[:, 0]
+    key = torch.where(torch.isnan(key), torch.full_like(key, float('-inf')), key)
+    order = torch.sort(key, descending=True, stable=True).indices[:k_best]
+    return rows[order]
+
+
+def sharded_best_rows(evaluate_slice, total, k_best):
+    """Every rank evaluates its strided slice with `evaluate_slice(first, stride, count)` ->
+    (k_best, C) best-first rows, the blocks are all-gathered and merged.  Returns the global
+    k_best rows (identical on every rank)."""
+    rank, w = world()
+    first, stride, count = shard_strided(total, rank, w)
+    rows = evaluate_slice(first, stride, count)
+    return merge_topk(allgather_rows(rows), k_best)
+
+
+def split_starts(rows, rank=None, world_size=None):
+    """The refinement starts this rank owns: row i goes to rank i % W."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    return rows[rank::world_size]

@@ -88,6 +88,11 @@ CVB_API int cvb_probs_batch(cvb_ctx *ctx, int64_t n_points, const double *params
 CVB_API int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const double *params, int k_best,
              double *out_rows, void *stream);
 
+/* cvb_loglik_batch followed by cvb_topk in one call: the batch is staged once, out_ll may be NULL
+ * (only the best rows are wanted: what one round of covest/grid.py:56-69 consumes). */
+CVB_API int cvb_loglik_topk(cvb_ctx *ctx, int64_t n_points, const double *params, double *out_ll,
+                            int k_best, double *out_rows, void *stream);
+
 /* A Cartesian lattice of candidate points generated on the device (no host->device parameter
  * traffic): n_param axes, axis a has axis_len[a] values stored consecutively in axis_values
  * (host).  Point i of the call is lattice index first + i * stride, last axis fastest -- the

@@ -28,7 +28,7 @@ def build(force=False):
     C module into oracle/_ref/)."""
     if force or not os.path.exists(_LIB_PATH) or (
             os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, 'covest_oracle.c'))):
-        subprocess.check_call(['make', '-C', _HERE, 'libcovest_oracle.so'])
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []) + ["libcovest_oracle.so"])
     if os.path.exists('/root/reference/c_src/covest_poissonmodule.c'):
         subprocess.check_call(['make', '-C', _HERE, 'ref'])
 
