@@ -36,12 +36,17 @@ def _ptr(x):
     return ctypes.c_void_p(x.ctypes.data)
 
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle that names the default stream explicitly
+
+
 def _stream_ptr(stream):
+    """None -> NULL (the context's own stream).  A torch stream or a raw cudaStream_t value is
+    passed through; the default stream, whose raw value is 0, is named by cudaStreamLegacy so
+    that it is not mistaken for "no stream given"."""
     if stream is None:
         return None
-    if hasattr(stream, 'cuda_stream'):
-        return ctypes.c_void_p(stream.cuda_stream)
-    return ctypes.c_void_p(int(stream))
+    value = stream.cuda_stream if hasattr(stream, 'cuda_stream') else int(stream)
+    return ctypes.c_void_p(value if value else CUDA_STREAM_LEGACY)
 
 
 class LikelihoodContext:

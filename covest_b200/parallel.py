@@ -55,15 +55,21 @@ def allgather_rows(rows):
 
 def merge_topk(rows, k_best):
     """The k_best best rows (column 0 = log-likelihood, larger is better) of a stacked block,
-    best first.  NaN and padding (-inf) sort last; ties keep gather order (lower rank, then lower
-    local position), so every rank selects the same rows."""
+    best first.  NaN and padding (-inf) sort last.  Ties are broken by the parameter columns in
+    lexicographic order -- for a lattice with ascending axes that is the lattice index, i.e. the
+    tie-break of the single-GPU top-K -- so the result does not depend on the number of ranks."""
     import torch
     if not isinstance(rows, torch.Tensor):
         rows = torch.from_numpy(np.ascontiguousarray(rows))
-    key = rows[:, 0]
+    order = torch.arange(rows.shape[0], device=rows.device)
+    for col in range(rows.shape[1] - 1, 0, -1):  # least significant key first, stable sorts
+        vals = rows[order, col]
+        vals = torch.where(torch.isnan(vals), torch.full_like(vals, float('inf')), vals)
+        order = order[torch.sort(vals, stable=True).indices]
+    key = rows[order, 0]
     key = torch.where(torch.isnan(key), torch.full_like(key, float('-inf')), key)
-    order = torch.sort(key, descending=True, stable=True).indices[:k_best]
-    return rows[order]
+    order = order[torch.sort(key, descending=True, stable=True).indices]
+    return rows[order[:k_best]]
 
 
 def sharded_best_rows(evaluate_slice, total, k_best):

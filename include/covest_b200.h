@@ -15,7 +15,8 @@
  *   - buffer arguments documented "host or device" are inspected with cudaPointerGetAttributes:
  *     device pointers are used in place, host pointers are staged through context-owned device
  *     buffers (the copies are part of the call);
- *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).  Calls with
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream; name the default
+ *     stream with cudaStreamLegacy, (void*)1).  Calls with
  *     host buffers return after the results are in the host buffer; calls where all buffers are
  *     device pointers only enqueue work on the stream;
  *   - a context is bound to one device and is not re-entrant; distinct contexts are independent;

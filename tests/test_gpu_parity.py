@@ -162,10 +162,11 @@ def test_full_size_properties_cfg3():
         clipped[:, 1] = 0.5
         clipped[:, 4] = 0.0
         assert np.array_equal(ctx.loglik(outside), ctx.loglik(clipped))
-        # probabilities: total mass of a proper point is at most 1 and the likelihood follows
+        # probabilities are non-negative (their sum may exceed 1: the reference's denominator
+        # quirk for rates above 200 is reproduced) and the likelihood follows from them
         p, ll2 = ctx.probs(pts[:64], clip=True, with_loglik=True)
         assert np.array_equal(ll2, ll[:64])
-        assert np.all(p.sum(axis=1) < 1 + 1e-12)
+        assert np.all(p >= 0) and not np.any(np.isnan(p))
         h = np.array([v for v in case_hist(case).values()], dtype=float)
         with np.errstate(divide='ignore'):
             manual = np.array([np.sum(h[h > 0] * np.log(row[h > 0])) for row in p])
