@@ -234,6 +234,8 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         if ((e = upload(c, T.slot_mult, &t.slot_mult)) != cudaSuccess) break;
         if ((e = upload(c, T.slot_h, &t.slot_h)) != cudaSuccess) break;
         if ((e = upload(c, T.slot_bin, &t.slot_bin)) != cudaSuccess) break;
+        if ((e = upload(c, T.copy_log_h, &t.copy_log_h)) != cudaSuccess) break;
+        if ((e = upload(c, T.copy_log_l, &t.copy_log_l)) != cudaSuccess) break;
         if ((e = upload(c, T.seg_first, &t.seg_first)) != cudaSuccess) break;
         if ((e = upload(c, T.seg_len, &t.seg_len)) != cudaSuccess) break;
         if ((e = upload(c, T.blk_seg_begin, &t.blk_seg_begin)) != cudaSuccess) break;

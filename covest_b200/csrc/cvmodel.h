@@ -8,7 +8,7 @@
  *     tp(L, j) = (prod_{i<=j} L/i) / D(L)                               (covest_poissonmodule.c:7-35)
  *
  * Every (o, s) pair is one *term* with rate L = o*l_s and weight w = b(o)*a_os.  Its value at
- * bin j is w * L^j / j! / D(L) = exp(j*log L - lgamma(j+1) - log D(L) + log w).  The kernels
+ * bin j is w * L^j / j! / D(L) = exp(j*log L - lgamma(j+1) - lin) * w / Dred.  The kernels
  * evaluate that exponential once per (term, chain of bins) -- the *seed*, in double-double so
  * the large cancelling parts j*log L, lgamma(j+1) and L keep ~1e-15 absolute accuracy -- and
  * walk the following bins with the recurrence value(j+1) = value(j) * L / (j+1), which is the
@@ -31,9 +31,10 @@
 #define CV_MAX_ERR 64
 
 struct CvTerm {
-    double lam;    /* rate o*l_s */
+    double lam;    /* rate o*l_s (1 for a term that contributes nothing) */
     double lh, ll; /* log(lam) as double-double */
-    double ch, cl; /* log w - log D(lam) [the part not proportional to the bin], double-double */
+    double lin;    /* the part of log D(lam) that is linear: lam, or 200 n (exact in double) */
+    double f;      /* w / Dred with D(lam) = e^lin * Dred; 0 for a dead term, NaN propagates */
 };
 
 /* models.py:60-69 fit_to_bounds for one coordinate; NaN bound = open */
@@ -77,22 +78,24 @@ CV_HD double cv_class_mass(double comb_s, double lam)
     return cv_mul(comb_s, cv_one_minus_exp_neg(lam));
 }
 
-/* Everything of a term that does not depend on the bin.  `w` is b(o) * a_os. */
-CV_HD CvTerm cv_term_make(double lam, double w)
+/* Everything of a term that does not depend on the bin.
+ *   num / total = b(o) * n_os / sum_s n_os = the weight w of the term (models.py:229, :236)
+ *   (lgh, lgl)  = log(lam) as a double-double
+ * D(lam) is split as e^lin * Dred with lin exact, so that the scaled value of the term at bin j is
+ *   exp(j*log(lam) - lgamma(j+1) + 420 - lin) * f,   f = w / Dred
+ * -- one exp per seed and no logarithm per term. */
+CV_HD CvTerm cv_term_make(double lam, double num, double total, double lgh, double lgl)
 {
     CvTerm t;
-    if (lam != lam || w != w) {
-        t.lam = 1.0;
-        t.lh = t.ll = 0.0;
-        t.ch = NAN;
-        t.cl = 0.0;
+    t.lam = 1.0;
+    t.lh = t.ll = 0.0;
+    t.lin = 0.0;
+    if (lam != lam || num != num || total != total) {
+        t.f = NAN;
         return t;
     }
-    if (!(lam > 0.0) || !(w > 0.0)) { /* zero weight: contributes exactly 0 (a_os * tp = 0) */
-        t.lam = 1.0;
-        t.lh = t.ll = 0.0;
-        t.ch = CV_DEAD_TERM;
-        t.cl = 0.0;
+    if (!(lam > 0.0) || !(num > 0.0)) { /* zero weight: contributes exactly 0 (a_os * tp = 0) */
+        t.f = 0.0;
         return t;
     }
     /* c:25-28: staged reduction by 200 */
@@ -110,7 +113,7 @@ CV_HD CvTerm cv_term_make(double lam, double w)
             n -= 1.0;
         }
     }
-    double lin, dterm;
+    double dred;
     if (r > 1e-8 && r < 0x1p-11) {
         /* c:30 `expl(l) - 1` in x87 long double: e^r lies in [1, 2), where the 64-bit format has
          * a spacing of 2^-63, so the difference is e^r - 1 rounded to a multiple of 2^-63 -- a
@@ -122,40 +125,37 @@ CV_HD CvTerm cv_term_make(double lam, double w)
         double x1 = cv_mul(r, 0x1p63), x2 = cv_mul(tail, 0x1p63);
         double i1 = floor(x1), i2 = floor(x2);
         double units = cv_add(cv_add(i1, i2), rint(cv_add(cv_sub(x1, i1), cv_sub(x2, i2))));
-        lin = 200.0 * n;
-        dterm = log(cv_mul(units, 0x1p-63));
-    } else if (r > 1e-8) { /* c:29-31 */
-        lin = lam;                /* log D = lam + log(1 - e^-r) */
-        dterm = log(-expm1(-r));
-    } else {
-        lin = 200.0 * n;          /* log D = 200 n + log(lam) */
-        dterm = log(lam);
+        t.lin = 200.0 * n;
+        dred = cv_mul(units, 0x1p-63);
+    } else if (r > 1e-8) { /* c:29-31: D = e^(200 n) (e^r - 1) = e^lam (1 - e^-r) */
+        t.lin = lam;
+        dred = (r >= 38.0) ? 1.0 : -expm1(-r);
+    } else { /* c:19: the ORIGINAL rate is the denominator */
+        t.lin = 200.0 * n;
+        dred = lam;
     }
-    cv_dd lg = cv_log_dd(lam);
-    cv_dd c = cv_two_sum(-lin, log(w) - dterm);
     t.lam = lam;
-    t.lh = lg.hi;
-    t.ll = lg.lo;
-    t.ch = c.hi;
-    t.cl = c.lo;
+    t.lh = lgh;
+    t.ll = lgl;
+    t.f = cv_div(num, cv_mul(total, dred));
     return t;
 }
 
-/* Scaled value of a term at the head bin of a chain:
- *   exp(j0 * log(lam) + [CV_SCALE_LOG - lgamma(j0+1)] + [log w - log D])
- * (head_h, head_l) is the bracketed chain constant as a double-double. */
-CV_HD double cv_seed(double j0, double head_h, double head_l, double lh, double ll, double ch,
-                     double cl)
+/* Scaled value of a term at the head bin j0 of a row:
+ *   exp(j0 * log(lam) + [CV_SCALE_LOG - lgamma(j0+1)] - lin) * f
+ * (head_h, head_l) is the bracketed row constant as a double-double. */
+CV_HD double cv_seed(double j0, double head_h, double head_l, double lh, double ll, double lin,
+                     double f)
 {
     double p = cv_mul(j0, lh);
     double pe = cv_fma(j0, ll, cv_fma(j0, lh, -p));
     cv_dd s1 = cv_two_sum(p, head_h);
-    cv_dd s2 = cv_two_sum(s1.hi, ch);
-    double lo = cv_add(cv_add(cv_add(pe, head_l), cl), cv_add(s1.lo, s2.lo));
+    cv_dd s2 = cv_two_sum(s1.hi, -lin);
+    double lo = cv_add(cv_add(pe, head_l), cv_add(s1.lo, s2.lo));
     double eh = cv_add(s2.hi, lo);
     double el = cv_sub(lo, cv_sub(eh, s2.hi));
     double u = exp(eh);
-    return cv_fma(u, el, u);
+    return cv_mul(cv_fma(u, el, u), f);
 }
 
 /* models.py:103-107 for the last step: total mass, tail term */

@@ -28,12 +28,13 @@
 
 #define CV_W 16        /* bins per row (chain) */
 #define CV_RB 64       /* rows per block: 1024 bins */
-#define CV_TT 128      /* mixture terms per tile */
+#define CV_TT 64       /* mixture terms per tile */
 #define CV_SSTRIDE 65  /* padded row stride of the seed matrix (bank-conflict-free columns) */
-#define CV_NT 256      /* threads per CTA */
-#define CV_NWARP 8
+#define CV_NT 128      /* threads per CTA; four CTAs share an SM */
+#define CV_NWARP 4
 #define CV_SEGMAX 32   /* longest run of rows seeded from one exp() */
 #define CV_MAX_PARAMS 5
+#define CV_BW_CACHE 512 /* copy weights b(o), o < 512, are kept from the cut-off search */
 
 /* Histogram-side tables of a context, all indexed by row / slot (slot = row * 16 + i).  Device
  * memory in the product, host memory in the emulation.  Built by cv_build_tables (cvtables.h). */
@@ -46,6 +47,8 @@ struct CvTables {
     const double *slot_mult;   /* exp(-CV_SCALE_LOG) * j0! / (j0+i)!; 0 marks a slot not in hist */
     const double *slot_h;      /* count h_j */
     const int *slot_bin;       /* position of the bin in the caller's hist order, -1 = padding */
+    const double *copy_log_h;  /* log(o), o = 0..max_bin, as a double-double (entry 0 unused) */
+    const double *copy_log_l;
     const int *seg_first;      /* segments: runs of consecutive rows inside one block */
     const int *seg_len;
     const int *blk_seg_begin;  /* [n_blocks + 1] */
@@ -69,15 +72,18 @@ struct CvModelDesc {
 /* Working set of one point; shared memory on the device. */
 struct CvPointShared {
     double par[CV_MAX_PARAMS];
-    double ls[CV_MAX_ERR];
+    double ls[CV_MAX_ERR];                 /* l_s */
+    double lls_h[CV_MAX_ERR], lls_l[CV_MAX_ERR]; /* log(l_s), double-double */
     double two, many, base; /* (1-q1)*q2, (1-q1)*(1-q2)*q, 1-q */
     int o_end;              /* O_thr: copies 1 .. o_end-1 are evaluated */
     int pad_;
+    double bw[CV_BW_CACHE]; /* b(o) */
     double nmass[CV_TT];
-    double lam[CV_TT], lh[CV_TT], ll[CV_TT], ch[CV_TT], cl[CV_TT];
+    double lam[CV_TT], lh[CV_TT], ll[CV_TT], lin[CV_TT], f[CV_TT];
     double l2[CV_TT], l4[CV_TT], l8[CV_TT], pw16[CV_TT], ipw16[CV_TT];
     double PW[CV_TT * CV_W];
-    double SD[CV_TT * CV_SSTRIDE]; /* seeds; reused as the cross-warp reduction buffer */
+    double SD[CV_TT * CV_SSTRIDE]; /* seeds; reused as the cross-warp reduction buffer and, after
+                                      the last epilogue, for the final reduction */
 };
 
 struct CvPartial {
@@ -99,7 +105,13 @@ CV_HD void cv_phase_header(int tid, const CvModelDesc &m, const double *row, int
             e = cv_clip(e, m.lo[1], m.hi[1]);
         }
         double ck = cv_kmer_coverage(c, m.k, m.r);
-        sh.ls[tid] = cv_error_class_rate(ck, m.pow3[tid], e, m.k, tid);
+        double l = cv_error_class_rate(ck, m.pow3[tid], e, m.k, tid);
+        sh.ls[tid] = l;
+        cv_dd lg = {0.0, 0.0};
+        if (l > 0.0 && l - l == 0.0) /* positive and finite */
+            lg = cv_log_dd(l);
+        sh.lls_h[tid] = lg.hi;
+        sh.lls_l[tid] = lg.lo;
     }
     if (tid == CV_NT - 1) {
         for (int i = 0; i < m.n_param; i++)
@@ -127,11 +139,15 @@ CV_HD double cv_point_copy_weight(const CvModelDesc &m, const CvPointShared &sh,
 
 /* One pass of the cut-off search models.py:187-190 over copies first_o .. first_o + CV_NT - 1.
  * Returns the candidate this thread found (or INT_MAX); the caller min-reduces into sh.o_end. */
-CV_HD int cv_phase_cut_candidate(int tid, const CvModelDesc &m, const CvPointShared &sh,
-                                 int first_o)
+CV_HD int cv_phase_cut_candidate(int tid, const CvModelDesc &m, CvPointShared &sh, int first_o)
 {
     int o = first_o + tid;
-    if (o < m.max_bin && cv_point_copy_weight(m, sh, o) <= m.threshold)
+    if (o >= m.max_bin)
+        return 0x7fffffff;
+    double b = cv_point_copy_weight(m, sh, o);
+    if (o < CV_BW_CACHE)
+        sh.bw[o] = b;
+    if (b <= m.threshold)
         return o;
     return 0x7fffffff;
 }
@@ -154,22 +170,33 @@ CV_HD void cv_phase_terms(int tid, const CvModelDesc &m, int tile_o, int nterms,
     if (tid >= nterms)
         return;
     int S = m.n_err;
-    int g = tid / S;
+    int g = tid / S, s = tid - g * S;
     int o = tile_o + g;
     /* models.py:88 / :224: Python sum(), left to right starting from int 0 */
     double total = 0.0;
-    for (int s = 0; s < S; s++)
-        total = cv_add(total, sh.nmass[g * S + s]);
+    for (int i = 0; i < S; i++)
+        total = cv_add(total, sh.nmass[g * S + i]);
     if (total == 0.0)
         total = 1.0; /* utils.py:25-29 fix_zero */
-    double a = cv_div(sh.nmass[tid], total); /* models.py:90 / :229 */
-    double w = cv_mul(cv_point_copy_weight(m, sh, o), a);
-    CvTerm t = cv_term_make(sh.lam[tid], w);
+    double b = 1.0;
+    if (m.model_kind)
+        b = (o < CV_BW_CACHE) ? sh.bw[o] : cv_point_copy_weight(m, sh, o);
+    double lam = sh.lam[tid];
+    /* log(lam) = log(o) + log(l_s) + log(lam / (o*l_s)); the last part undoes the rounding of the
+     * product lam = RN(o*l_s) and is -(o*l_s - lam)/lam to first order (|.| <= 2^-53) */
+    double ls = sh.ls[s];
+    double resid = cv_fma((double)o, ls, -lam);
+    cv_dd lo_ = {m.tab.copy_log_h[o], m.tab.copy_log_l[o]};
+    cv_dd ll_ = {sh.lls_h[s], sh.lls_l[s]};
+    cv_dd lg = cv_dd_add(lo_, ll_);
+    if (resid != 0.0)
+        lg = cv_dd_add_d(lg, -cv_div(resid, lam));
+    CvTerm t = cv_term_make(lam, cv_mul(b, sh.nmass[tid]), total, lg.hi, lg.lo);
     sh.lam[tid] = t.lam;
     sh.lh[tid] = t.lh;
     sh.ll[tid] = t.ll;
-    sh.ch[tid] = t.ch;
-    sh.cl[tid] = t.cl;
+    sh.lin[tid] = t.lin;
+    sh.f[tid] = t.f;
     double l2 = cv_mul(t.lam, t.lam);
     double l4 = cv_mul(l2, l2);
     double l8 = cv_mul(l4, l4);
@@ -220,7 +247,7 @@ CV_HD void cv_phase_seeds(int tid, int nthreads, const CvModelDesc &m, int blk, 
         else if (off > 0.0)
             rs = (int)off;
         double seed = cv_seed(T.row_j0[grow + rs], T.row_head_h[grow + rs], T.row_head_l[grow + rs],
-                              sh.lh[t], sh.ll[t], sh.ch[t], sh.cl[t]);
+                              sh.lh[t], sh.ll[t], sh.lin[t], sh.f[t]);
         double *srow = sh.SD + t * CV_SSTRIDE + first;
         srow[rs] = seed;
         double v = seed;
@@ -239,8 +266,8 @@ CV_HD void cv_phase_seeds(int tid, int nthreads, const CvModelDesc &m, int blk, 
 }
 
 /* The accumulators of a thread: rows rg + 16a (a < 4), columns 8cg + b (b < 8) of the block, with
- * rg = lane >> 1, cg = lane & 1; warp w takes the terms t = w, w + 8, ... (split over terms, summed
- * in cv_phase_epilogue). */
+ * rg = lane >> 1, cg = lane & 1; warp w takes the terms t = w, w + CV_NWARP, ... (split over terms,
+ * summed in cv_phase_epilogue). */
 CV_HD void cv_phase_fma(int tid, int nterms, int nrows_blk, const CvPointShared &sh, double *acc)
 {
     int warp = tid >> 5, lane = tid & 31;
@@ -305,8 +332,8 @@ CV_HD void cv_partial_merge(CvPartial &p, const CvPartial &q)
     p.sum_l = cv_add(p.sum_l, q.sum_l);
 }
 
-/* models.py:100-107 per bin.  Thread tid finishes the slots e = tid + 256 n (n < 4) of the
- * [a][b][lane] order of cv_phase_spill. */
+/* models.py:100-107 per bin.  Thread tid finishes the slots e = tid + CV_NT n of the [a][b][lane]
+ * order of cv_phase_spill. */
 CV_HD void cv_phase_epilogue(int tid, const CvModelDesc &m, int blk, const CvPointShared &sh,
                              CvPartial &part, double *out_probs)
 {
@@ -345,4 +372,27 @@ CV_HD double cv_point_finish(const CvModelDesc &m, const CvPartial &part)
     if (part.sum_h - part.sum_h == 0.0) /* finite */
         sum = cv_add(part.sum_h, part.sum_l);
     return cv_finish_loglik(sum, mass, m.tail);
+}
+
+/* Final reduction, in a fixed order: every thread publishes its partial, warp 0 folds
+ * CV_NT / 32 partials per lane; the caller finishes with 32 values (lane order). */
+CV_HD void cv_phase_publish(int tid, CvPointShared &sh, const CvPartial &part)
+{
+    double *red = sh.SD; /* free after the last epilogue (the caller synchronises) */
+    red[tid] = part.sum_h;
+    red[CV_NT + tid] = part.sum_l;
+    red[2 * CV_NT + tid] = part.mass_h;
+    red[3 * CV_NT + tid] = part.mass_l;
+}
+
+CV_HD CvPartial cv_phase_fold(int lane, const CvPointShared &sh)
+{
+    const double *red = sh.SD;
+    CvPartial acc = {red[lane], red[CV_NT + lane], red[2 * CV_NT + lane], red[3 * CV_NT + lane]};
+    for (int w = 1; w < CV_NWARP; w++) {
+        int i = lane + 32 * w;
+        CvPartial q = {red[i], red[CV_NT + i], red[2 * CV_NT + i], red[3 * CV_NT + i]};
+        cv_partial_merge(acc, q);
+    }
+    return acc;
 }

@@ -19,6 +19,7 @@
 
 struct CvHostTables {
     std::vector<double> row_j0, row_head_h, row_head_l, row_up, row_dn, slot_mult, slot_h;
+    std::vector<double> copy_log_h, copy_log_l;
     std::vector<int> slot_bin, seg_first, seg_len, blk_seg_begin;
     int n_rows = 0, n_blocks = 0, max_bin = 0;
 };
@@ -112,6 +113,14 @@ static inline std::string cv_build_tables(int n_bins, const int *bin_j, const do
             T.slot_bin[slot] = keys[b].second;
         }
     }
+    /* log(o) for every copy number the cut-off can reach (models.py:186: o < max(hist)) */
+    T.copy_log_h.assign((size_t)T.max_bin + 2, 0.0);
+    T.copy_log_l.assign((size_t)T.max_bin + 2, 0.0);
+    for (int o = 2; o <= T.max_bin + 1; o++) {
+        cv_dd lg = cv_log_dd((double)o);
+        T.copy_log_h[o] = lg.hi;
+        T.copy_log_l[o] = lg.lo;
+    }
     /* segments */
     T.blk_seg_begin.assign(T.n_blocks + 1, 0);
     for (int blk = 0; blk < T.n_blocks; blk++) {
@@ -142,6 +151,8 @@ static inline CvTables cv_tables_view(const CvHostTables &T)
     v.slot_mult = T.slot_mult.data();
     v.slot_h = T.slot_h.data();
     v.slot_bin = T.slot_bin.data();
+    v.copy_log_h = T.copy_log_h.data();
+    v.copy_log_l = T.copy_log_l.data();
     v.seg_first = T.seg_first.data();
     v.seg_len = T.seg_len.data();
     v.blk_seg_begin = T.blk_seg_begin.data();

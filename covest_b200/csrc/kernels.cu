@@ -1,7 +1,8 @@
 /*
  * kernels.cu -- hand-written sm_100a kernels of the CovEst likelihood path.
  *
- *   cv_loglik_kernel   K1/K2: one CTA per parameter point (persistent CTAs drawing point indices
+ *   cv_loglik_kernel   K1/K2: one 128-thread CTA per parameter point, four CTAs per SM (persistent
+ *                      CTAs drawing point indices
  *                      from a device counter), phases of cvpoint.h separated by __syncthreads().
  *                      FP64 throughout; the inner loop is one DFMA per (mixture term, bin).
  *   cv_topk_select     K3: deterministic top-K of the log-likelihoods.
@@ -28,6 +29,8 @@ __device__ __forceinline__ void cv_lattice_point(const CvLattice &lat, long long
     }
 }
 
+#define CV_CTAS_PER_SM 4
+
 __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, int delta)
 {
     CvPartial q;
@@ -38,7 +41,7 @@ __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, in
     return q;
 }
 
-__global__ void __launch_bounds__(CV_NT, 2)
+__global__ void __launch_bounds__(CV_NT, CV_CTAS_PER_SM)
 cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                  const double *__restrict__ params, long long n_points, int clip,
                  double *__restrict__ out_ll, double *__restrict__ out_probs,
@@ -47,7 +50,6 @@ cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char cv_smem_raw[];
     CvPointShared &sh = *reinterpret_cast<CvPointShared *>(cv_smem_raw);
     __shared__ long long s_point;
-    __shared__ CvPartial s_part[CV_NWARP];
     __shared__ double s_row[CV_MAX_PARAMS];
 
     const int tid = threadIdx.x;
@@ -115,20 +117,19 @@ cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ 
             cv_phase_epilogue(tid, m, blk, sh, part, probs_row);
             __syncthreads();
         }
-        /* block reduction of the partial sums, in a fixed order */
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            CvPartial q = cv_partial_shfl_down(part, d);
-            cv_partial_merge(part, q);
-        }
-        if ((tid & 31) == 0)
-            s_part[tid >> 5] = part;
+        /* block reduction of the partial sums, in a fixed order: warp 0 folds the published
+         * partials, then a shuffle tree */
+        cv_phase_publish(tid, sh, part);
         __syncthreads();
-        if (tid == 0) {
-            CvPartial total = s_part[0];
-            for (int w = 1; w < CV_NWARP; w++)
-                cv_partial_merge(total, s_part[w]);
-            out_ll[point] = cv_point_finish(m, total);
+        if (tid < 32) {
+            CvPartial total = cv_phase_fold(tid, sh);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                CvPartial q = cv_partial_shfl_down(total, d);
+                cv_partial_merge(total, q);
+            }
+            if (tid == 0)
+                out_ll[point] = cv_point_finish(m, total);
         }
     }
 }
@@ -149,7 +150,7 @@ cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const d
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess)
         return e;
-    long long want = 2LL * n_sm; /* two resident CTAs per SM */
+    long long want = (long long)CV_CTAS_PER_SM * n_sm; /* resident CTAs */
     int grid = (int)(n_points < want ? n_points : want);
     cv_loglik_kernel<<<grid, CV_NT, cv_loglik_smem_bytes(), stream>>>(m, lat, params, n_points, clip,
                                                                       out_ll, out_probs, counter);

@@ -56,7 +56,14 @@ static void emulate_point(const CvModelDesc &m, const double *row, int clip, dou
             cv_phase_epilogue(tid, m, blk, sh, part[tid], out_probs);
     }
     for (int tid = 0; tid < CV_NT; tid++)
-        cv_partial_merge(total, part[tid]);
+        cv_phase_publish(tid, sh, part[tid]);
+    for (int lane = 0; lane < 32; lane++) {
+        CvPartial q = cv_phase_fold(lane, sh);
+        if (lane == 0)
+            total = q;
+        else
+            cv_partial_merge(total, q);
+    }
     *out_ll = cv_point_finish(m, total);
 }
 
