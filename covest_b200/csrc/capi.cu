@@ -21,6 +21,7 @@
 struct cvb_ctx {
     int device = 0;
     int n_sm = 0;
+    int smem_max = 0; /* opt-in dynamic shared memory per CTA */
     CvModelDesc desc;
     std::vector<void *> owned; /* device allocations that live as long as the context */
     cudaStream_t stream = nullptr;
@@ -217,6 +218,7 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
             break;
         c->n_sm = prop.multiProcessorCount;
+        c->smem_max = (int)prop.sharedMemPerBlockOptin;
         if (prop.major < 10) {
             rc = fail(nullptr, CVB_ECUDA,
                       std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
@@ -296,7 +298,8 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
     bool timed = ctx->timing && ctx->timed_chunks < CVB_MAX_TIMED_CHUNKS;
     if (timed)
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks], s), "cudaEventRecord");
-    CU(cv_launch_loglik(ctx->desc, lat, d_params, n, clip, d_ll, d_probs, ctx->d_counter, ctx->n_sm, s),
+    CU(cv_launch_loglik(ctx->desc, lat, d_params, n, clip, d_ll, d_probs, ctx->d_counter, ctx->n_sm,
+                        ctx->smem_max, s),
        "cv_loglik_kernel launch");
     if (timed) {
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks + 1], s), "cudaEventRecord");

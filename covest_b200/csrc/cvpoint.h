@@ -1,25 +1,28 @@
 /*
  * cvpoint.h -- the per-point evaluation of the CovEst mixture likelihood, written as a sequence
- * of *phases*.  Inside the sm_100a kernel (loglik_kernel.cu) every thread of a CTA calls each
- * phase with its own `tid` and the phases are separated by __syncthreads(); the test-only host
- * emulation (tests/host_math/emulate.cpp) calls the same functions in a serial loop over `tid`,
- * phase by phase, which is the same computation.  No phase uses warp intrinsics.
- *
- * One CTA evaluates one parameter point at a time:
+ * of warp-wide *phases*.  Inside the sm_100a kernel (kernels.cu) ONE WARP evaluates one parameter
+ * point at a time: its 32 lanes call each phase with their own `lane`, the phases are separated by
+ * __syncwarp(), and nothing is shared between the warps of a CTA except read-only row tables.  The
+ * test-only host emulation (tests/host_math/emulate.cpp) calls the same functions in a serial loop
+ * over `lane`, phase by phase, which is the same computation.  No phase uses warp intrinsics.
  *
  *   header      clip the parameters (models.py:60-69), error-class rates l_s (models.py:71-79),
- *               copy-number weights (models.py:193-208) and the cut-off O_thr (models.py:185-191)
- *   per tile of up to CV_TT mixture terms (o, s):
+ *               the constants of the copy-number weights (models.py:193-208)
+ *   per pass of 32 copy numbers o: the weights b(o), one per lane, and the cut-off O_thr
+ *               (models.py:185-191) -- the weights stay in registers and reach the terms by shuffle
+ *   per group of up to 32 mixture terms (o, s)  [64 when there are more than 32 error classes]:
  *     mass      n_os = comb[s] * (1.0 - exp(-o*l_s))                      (models.py:87, :221)
  *     terms     a_os = n_os / sum_s n_os, w = b(o) * a_os, log-domain constants of the term
- *     powers    PW[t][i] = lam_t^i, i = 0..15
- *     seeds     SD[t][row] = scaled value of term t at the head bin of every 16-bin row of the
- *               current block of rows: one exp() at the row holding the mode of the term, then
+ *     per half-tile of 16 terms:
+ *       powers  PW[t][i] = lam_t^i, i = 0..15
+ *       seeds   SD[row][t] = scaled value of term t at the head bin of every 16-bin row of the
+ *               current block of 64 rows: one exp() at the row holding the mode of the term, then
  *               the reference's own product recurrence (covest_poissonmodule.c:22-24) walked
  *               outwards 16 bins at a time
- *     fma       ACC[row][i] += SD[t][row] * PW[t][i]     -- one FP64 FMA per (term, bin)
- *   spill       per-warp partial ACCs to shared memory
- *   epilogue    p_j = ACC * slot_mult, mass += p_j, sum += h_j * log p_j  (models.py:100-107)
+ *       fma     ACC[row][i] += SD[row][t] * PW[t][i]   -- one FP64 FMA per (term, bin); a lane
+ *               owns 8 rows x 4 columns of the 64 x 16 block (32 accumulators in registers)
+ *   epilogue    p_j = ACC * slot_mult, mass += p_j, sum += h_j * log p_j  (models.py:100-107),
+ *               straight from the accumulator registers
  *
  * Reference lines are relative to /root/reference.
  */
@@ -28,13 +31,13 @@
 
 #define CV_W 16        /* bins per row (chain) */
 #define CV_RB 64       /* rows per block: 1024 bins */
-#define CV_TT 64       /* mixture terms per tile */
-#define CV_SSTRIDE 65  /* padded row stride of the seed matrix (bank-conflict-free columns) */
-#define CV_NT 128      /* threads per CTA; four CTAs share an SM */
-#define CV_NWARP 4
+#define CV_HT 16       /* mixture terms per half-tile (powers / seeds / fma) */
+#define CV_CT 32       /* mixture terms per constant tile (terms phase: one per lane) */
+#define CV_SDS 18      /* row stride of the seed matrix SD[row][term]: 144 B, so that the 16-byte
+                          chunks of 8 consecutive rows fall into 8 different bank groups */
 #define CV_SEGMAX 32   /* longest run of rows seeded from one exp() */
 #define CV_MAX_PARAMS 5
-#define CV_BW_CACHE 512 /* copy weights b(o), o < 512, are kept from the cut-off search */
+#define CV_WARPS_MAX 16 /* warps (= points in flight) per CTA; one CTA per SM */
 
 /* Histogram-side tables of a context, all indexed by row / slot (slot = row * 16 + i).  Device
  * memory in the product, host memory in the emulation.  Built by cv_build_tables (cvtables.h). */
@@ -69,177 +72,238 @@ struct CvModelDesc {
     CvTables tab;
 };
 
-/* Working set of one point; shared memory on the device. */
-struct CvPointShared {
+/* Fixed-size part of the working set of one warp (= one point in flight); shared memory on the
+ * device.  Compile-time offsets keep the hot phases free of address arithmetic. */
+struct CvWarpFixed {
+    double SD[CV_RB * CV_SDS];  /* seeds of the current half-tile, [row][term] */
+    double PW[CV_HT * CV_W];    /* powers of the current half-tile, [term][i] */
+    double lam[CV_CT], lh[CV_CT], ll[CV_CT], lin[CV_CT], f[CV_CT]; /* constants of a tile of terms */
+    double pw16[CV_HT], ipw16[CV_HT];                              /* lam^16 and its inverse */
     double par[CV_MAX_PARAMS];
-    double ls[CV_MAX_ERR];                 /* l_s */
-    double lls_h[CV_MAX_ERR], lls_l[CV_MAX_ERR]; /* log(l_s), double-double */
     double two, many, base; /* (1-q1)*q2, (1-q1)*(1-q2)*q, 1-q */
-    int o_end;              /* O_thr: copies 1 .. o_end-1 are evaluated */
-    int pad_;
-    double bw[CV_BW_CACHE]; /* b(o) */
-    double nmass[CV_TT];
-    double lam[CV_TT], lh[CV_TT], ll[CV_TT], lin[CV_TT], f[CV_TT];
-    double l2[CV_TT], l4[CV_TT], l8[CV_TT], pw16[CV_TT], ipw16[CV_TT];
-    double PW[CV_TT * CV_W];
-    double SD[CV_TT * CV_SSTRIDE]; /* seeds; reused as the cross-warp reduction buffer and, after
-                                      the last epilogue, for the final reduction */
 };
+
+/* The working set of a warp: the fixed part, the arrays whose length depends on the number of
+ * error classes, and the row tables every warp of the CTA reads. */
+struct CvWarpMem {
+    CvWarpFixed *fx;
+    double *ls;            /* [S] l_s */
+    double *lls_h, *lls_l; /* [S] log(l_s), double-double */
+    double *nmass;         /* [group terms] n_os */
+    double *glam;          /* [group terms] o * l_s */
+    const double *row_up;  /* CvTables.row_up / row_dn (staged in shared memory when they fit) */
+    const double *row_dn;
+};
+
+/* terms of the largest group: whole copies, at most 32 terms unless one copy alone has more */
+CV_HD int cv_copies_per_group(int n_err) { return n_err >= CV_CT ? 1 : CV_CT / n_err; }
+CV_HD int cv_group_terms_max(int n_err) { return n_err > CV_CT ? 2 * CV_CT : CV_CT; }
+/* doubles of the variable part of a warp's working set */
+CV_HD int cv_warp_var_doubles(int n_err) { return 3 * n_err + 2 * cv_group_terms_max(n_err); }
+
+CV_HD void cv_warp_mem_carve(CvWarpMem &M, CvWarpFixed *fx, double *var, int n_err)
+{
+    int gm = cv_group_terms_max(n_err);
+    M.fx = fx;
+    M.ls = var;
+    M.lls_h = var + n_err;
+    M.lls_l = var + 2 * n_err;
+    M.nmass = var + 3 * n_err;
+    M.glam = M.nmass + gm;
+}
 
 struct CvPartial {
     double sum_h, sum_l;   /* sum_j h_j log p_j, compensated */
     double mass_h, mass_l; /* sum_j p_j, compensated */
 };
 
-/* copies per tile */
-CV_HD int cv_copies_per_tile(int n_err) { return CV_TT / n_err; }
-
 /* ---- header ------------------------------------------------------------------------------- */
-CV_HD void cv_phase_header(int tid, const CvModelDesc &m, const double *row, int clip,
-                           CvPointShared &sh)
+/* `row` holds the raw parameters of the point (every lane has them). */
+CV_HD void cv_w_header(int lane, const CvModelDesc &m, const double *row, int clip, CvWarpMem &M)
 {
-    if (tid < m.n_err) {
-        double c = row[0], e = row[1];
-        if (clip) {
-            c = cv_clip(c, m.lo[0], m.hi[0]);
-            e = cv_clip(e, m.lo[1], m.hi[1]);
-        }
-        double ck = cv_kmer_coverage(c, m.k, m.r);
-        double l = cv_error_class_rate(ck, m.pow3[tid], e, m.k, tid);
-        sh.ls[tid] = l;
+    CvWarpFixed &F = *M.fx;
+    double c = row[0], e = row[1];
+    if (clip) {
+        c = cv_clip(c, m.lo[0], m.hi[0]);
+        e = cv_clip(e, m.lo[1], m.hi[1]);
+    }
+    double ck = cv_kmer_coverage(c, m.k, m.r);
+    for (int s = lane; s < m.n_err; s += 32) {
+        double l = cv_error_class_rate(ck, m.pow3[s], e, m.k, s);
+        M.ls[s] = l;
         cv_dd lg = {0.0, 0.0};
         if (l > 0.0 && l - l == 0.0) /* positive and finite */
             lg = cv_log_dd(l);
-        sh.lls_h[tid] = lg.hi;
-        sh.lls_l[tid] = lg.lo;
+        M.lls_h[s] = lg.hi;
+        M.lls_l[s] = lg.lo;
     }
-    if (tid == CV_NT - 1) {
-        for (int i = 0; i < m.n_param; i++)
-            sh.par[i] = clip ? cv_clip(row[i], m.lo[i], m.hi[i]) : row[i];
+    if (lane == 31) {
+        double par[CV_MAX_PARAMS];
+#pragma unroll
+        for (int i = 0; i < CV_MAX_PARAMS; i++) {
+            par[i] = 0.0;
+            if (i < m.n_param)
+                par[i] = clip ? cv_clip(row[i], m.lo[i], m.hi[i]) : row[i];
+            F.par[i] = par[i];
+        }
         if (m.model_kind) {
-            double q1 = sh.par[2], q2 = sh.par[3], q = sh.par[4];
-            sh.two = cv_mul(cv_sub(1.0, q1), q2);                          /* models.py:195 */
-            sh.many = cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), q); /* models.py:196 */
-            sh.base = cv_sub(1.0, q);
-            sh.o_end = m.max_bin; /* models.py:191 */
+            double q1 = par[2], q2 = par[3], q = par[4];
+            F.two = cv_mul(cv_sub(1.0, q1), q2);                          /* models.py:195 */
+            F.many = cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), q); /* models.py:196 */
+            F.base = cv_sub(1.0, q);
         } else {
-            sh.two = sh.many = sh.base = 0.0;
-            sh.o_end = 2; /* the basic model is the single copy o = 1 with weight 1 */
+            F.two = F.many = F.base = 0.0;
         }
     }
 }
 
-/* b(o), models.py:198-206 */
-CV_HD double cv_point_copy_weight(const CvModelDesc &m, const CvPointShared &sh, int o)
+/* One lane's share of a pass of the cut-off search models.py:187-190 over copies
+ * first_o .. first_o + 31: lane i looks at o = first_o + i.  Returns true when the evaluated
+ * copies end BEFORE o (the caller takes the lowest such lane); *b is b(o), models.py:198-206.
+ * The basic model is the single copy o = 1 with weight 1. */
+CV_HD bool cv_w_copy_pass(int lane, const CvModelDesc &m, const CvWarpMem &M, int first_o, double *b)
 {
-    if (!m.model_kind)
-        return 1.0;
-    return cv_copy_weight(o, sh.par[2], sh.two, sh.many, sh.base);
+    int o = first_o + lane;
+    if (!m.model_kind) {
+        *b = 1.0;
+        return o >= 2;
+    }
+    if (o >= m.max_bin) { /* models.py:191: no cut found, O_thr = max(hist) */
+        *b = 0.0;
+        return true;
+    }
+    const CvWarpFixed &F = *M.fx;
+    double w = cv_copy_weight(o, F.par[2], F.two, F.many, F.base);
+    *b = w;
+    return w <= m.threshold;
 }
 
-/* One pass of the cut-off search models.py:187-190 over copies first_o .. first_o + CV_NT - 1.
- * Returns the candidate this thread found (or INT_MAX); the caller min-reduces into sh.o_end. */
-CV_HD int cv_phase_cut_candidate(int tid, const CvModelDesc &m, CvPointShared &sh, int first_o)
+/* ---- per group ---------------------------------------------------------------------------- */
+/* models.py:87 / :221.  Term t of the group is copy o = group_o + t / S, error class s = t % S. */
+CV_HD void cv_w_mass(int lane, const CvModelDesc &m, int group_o, int nterms, CvWarpMem &M)
 {
-    int o = first_o + tid;
-    if (o >= m.max_bin)
-        return 0x7fffffff;
-    double b = cv_point_copy_weight(m, sh, o);
-    if (o < CV_BW_CACHE)
-        sh.bw[o] = b;
-    if (b <= m.threshold)
-        return o;
-    return 0x7fffffff;
-}
-
-/* ---- per tile ----------------------------------------------------------------------------- */
-/* models.py:87 / :221.  Term t of the tile is copy o = tile_o + t / S, error class s = t % S. */
-CV_HD void cv_phase_mass(int tid, const CvModelDesc &m, int tile_o, int nterms, CvPointShared &sh)
-{
-    if (tid >= nterms)
-        return;
     int S = m.n_err;
-    int o = tile_o + tid / S, s = tid % S;
-    double lam = cv_mul((double)o, sh.ls[s]); /* o * l_s, models.py:238 */
-    sh.lam[tid] = lam;
-    sh.nmass[tid] = cv_class_mass(m.comb[s], lam);
-}
-
-CV_HD void cv_phase_terms(int tid, const CvModelDesc &m, int tile_o, int nterms, CvPointShared &sh)
-{
-    if (tid >= nterms)
-        return;
-    int S = m.n_err;
-    int g = tid / S, s = tid - g * S;
-    int o = tile_o + g;
-    /* models.py:88 / :224: Python sum(), left to right starting from int 0 */
-    double total = 0.0;
-    for (int i = 0; i < S; i++)
-        total = cv_add(total, sh.nmass[g * S + i]);
-    if (total == 0.0)
-        total = 1.0; /* utils.py:25-29 fix_zero */
-    double b = 1.0;
-    if (m.model_kind)
-        b = (o < CV_BW_CACHE) ? sh.bw[o] : cv_point_copy_weight(m, sh, o);
-    double lam = sh.lam[tid];
-    /* log(lam) = log(o) + log(l_s) + log(lam / (o*l_s)); the last part undoes the rounding of the
-     * product lam = RN(o*l_s) and is -(o*l_s - lam)/lam to first order (|.| <= 2^-53) */
-    double ls = sh.ls[s];
-    double resid = cv_fma((double)o, ls, -lam);
-    cv_dd lo_ = {m.tab.copy_log_h[o], m.tab.copy_log_l[o]};
-    cv_dd ll_ = {sh.lls_h[s], sh.lls_l[s]};
-    cv_dd lg = cv_dd_add(lo_, ll_);
-    if (resid != 0.0)
-        lg = cv_dd_add_d(lg, -cv_div(resid, lam));
-    CvTerm t = cv_term_make(lam, cv_mul(b, sh.nmass[tid]), total, lg.hi, lg.lo);
-    sh.lam[tid] = t.lam;
-    sh.lh[tid] = t.lh;
-    sh.ll[tid] = t.ll;
-    sh.lin[tid] = t.lin;
-    sh.f[tid] = t.f;
-    double l2 = cv_mul(t.lam, t.lam);
-    double l4 = cv_mul(l2, l2);
-    double l8 = cv_mul(l4, l4);
-    double l16 = cv_mul(l8, l8);
-    sh.l2[tid] = l2;
-    sh.l4[tid] = l4;
-    sh.l8[tid] = l8;
-    sh.pw16[tid] = l16;
-    sh.ipw16[tid] = cv_div(1.0, l16);
-}
-
-/* PW[t][i] = lam_t^i, i < 16, from the squarings: every element is at most three products */
-CV_HD void cv_phase_powers(int tid, int nthreads, int nterms, CvPointShared &sh)
-{
-    for (int e = tid; e < nterms * CV_W; e += nthreads) {
-        int t = e >> 4, i = e & 15;
-        double v = (i & 1) ? sh.lam[t] : 1.0;
-        if (i & 2)
-            v = cv_mul(v, sh.l2[t]);
-        if (i & 4)
-            v = cv_mul(v, sh.l4[t]);
-        if (i & 8)
-            v = cv_mul(v, sh.l8[t]);
-        sh.PW[e] = v;
+    for (int t = lane; t < nterms; t += 32) {
+        int g = t / S, s = t - g * S;
+        double lam = cv_mul((double)(group_o + g), M.ls[s]); /* o * l_s, models.py:238 */
+        M.glam[t] = lam;
+        M.nmass[t] = cv_class_mass(m.comb[s], lam);
     }
 }
 
-/* Seeds of every (term, row) of block `blk`.  A work item is (term, segment); it takes one exp()
- * at the row of the segment that holds the mode of the term (j ~ lam) and walks outwards, where
- * the term only decreases, so that a value that underflowed never has to grow back. */
-CV_HD void cv_phase_seeds(int tid, int nthreads, const CvModelDesc &m, int blk, int nterms,
-                          CvPointShared &sh)
+/* Constants of the term t = sub + lane of the group (a dead term when t >= nterms); `b` is the
+ * weight b(o) of the copy this lane's term belongs to. */
+CV_HD void cv_w_terms(int lane, const CvModelDesc &m, int group_o, int nterms, int sub, double b,
+                      CvWarpMem &M)
 {
+    CvWarpFixed &F = *M.fx;
+    int t = sub + lane;
+    if (t >= nterms) { /* padding of the last tile: contributes exactly 0 */
+        F.lam[lane] = 1.0;
+        F.lh[lane] = 0.0;
+        F.ll[lane] = 0.0;
+        F.lin[lane] = 0.0;
+        F.f[lane] = 0.0;
+        return;
+    }
+    int S = m.n_err;
+    int g = t / S, s = t - g * S;
+    int o = group_o + g;
+    /* models.py:88 / :224: Python sum(), left to right starting from int 0 */
+    double total = 0.0;
+    for (int i = 0; i < S; i++)
+        total = cv_add(total, M.nmass[g * S + i]);
+    if (total == 0.0)
+        total = 1.0; /* utils.py:25-29 fix_zero */
+    double lam = M.glam[t];
+    /* log(lam) = log(o) + log(l_s) + log(lam / (o*l_s)); the last part undoes the rounding of the
+     * product lam = RN(o*l_s) and is -(o*l_s - lam)/lam to first order (|.| <= 2^-53) */
+    double ls = M.ls[s];
+    double resid = cv_fma((double)o, ls, -lam);
+    cv_dd lo_ = {m.tab.copy_log_h[o], m.tab.copy_log_l[o]};
+    cv_dd ll_ = {M.lls_h[s], M.lls_l[s]};
+    cv_dd lg = cv_dd_add(lo_, ll_);
+    if (resid != 0.0)
+        lg = cv_dd_add_d(lg, -cv_div(resid, lam));
+    CvTerm tm = cv_term_make(lam, cv_mul(b, M.nmass[t]), total, lg.hi, lg.lo);
+    F.lam[lane] = tm.lam;
+    F.lh[lane] = tm.lh;
+    F.ll[lane] = tm.ll;
+    F.lin[lane] = tm.lin;
+    F.f[lane] = tm.f;
+}
+
+/* two adjacent doubles, one 16-byte access on the device */
+struct cv_pair {
+    double x, y;
+};
+CV_HD cv_pair cv_ld2(const double *p)
+{
+#if defined(__CUDA_ARCH__)
+    double2 v = *reinterpret_cast<const double2 *>(p);
+    cv_pair r = {v.x, v.y};
+    return r;
+#else
+    cv_pair r = {p[0], p[1]};
+    return r;
+#endif
+}
+CV_HD void cv_st2(double *p, double x, double y)
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+#else
+    p[0] = x;
+    p[1] = y;
+#endif
+}
+
+/* ---- per half-tile ------------------------------------------------------------------------ */
+/* PW[t][i] = lam_t^i, i < 16: lanes 2t and 2t+1 take the lower and the upper eight; every element
+ * is at most three products of the squarings (the lower eight are multiplied by an exact 1.0 so
+ * that the warp does not diverge).  Also lam^16 (kept by lane 2t) and 1 / lam^16 (lane 2t+1). */
+CV_HD void cv_w_powers(int lane, int half, CvWarpMem &M)
+{
+    CvWarpFixed &F = *M.fx;
+    int t = lane >> 1, up = lane & 1;
+    double lam = F.lam[half * CV_HT + t];
+    double l2 = cv_mul(lam, lam);
+    double l4 = cv_mul(l2, l2);
+    double l8 = cv_mul(l4, l4);
+    double l3 = cv_mul(l2, lam);
+    double l5 = cv_mul(l4, lam);
+    double l6 = cv_mul(l4, l2);
+    double l7 = cv_mul(l4, l3);
+    double l16 = cv_mul(l8, l8);
+    double inv16 = cv_div(1.0, l16);
+    double base = up ? l8 : 1.0;
+    double *pw = F.PW + t * CV_W + up * 8;
+    cv_st2(pw + 0, base, cv_mul(base, lam));
+    cv_st2(pw + 2, cv_mul(base, l2), cv_mul(base, l3));
+    cv_st2(pw + 4, cv_mul(base, l4), cv_mul(base, l5));
+    cv_st2(pw + 6, cv_mul(base, l6), cv_mul(base, l7));
+    if (up)
+        F.ipw16[t] = inv16;
+    else
+        F.pw16[t] = l16;
+}
+
+/* Seeds of every (term, row) of block `blk`.  A work item is (term, segment); it takes one exp()
+ * at the row of the segment that holds the mode of the term (j ~ lam) and walks outwards -- first
+ * up, then down, in ONE loop so that lanes with different mode rows do not diverge -- where the
+ * term only decreases, so that a value that underflowed never has to grow back. */
+CV_HD void cv_w_seeds(int lane, const CvModelDesc &m, int blk, int half, CvWarpMem &M)
+{
+    CvWarpFixed &F = *M.fx;
     const CvTables &T = m.tab;
     int sb = T.blk_seg_begin[blk];
-    int nseg = T.blk_seg_begin[blk + 1] - sb;
-    int items = nterms * nseg;
-    for (int it = tid; it < items; it += nthreads) {
-        int t = it % nterms;
-        int sg = sb + it / nterms;
+    int items = (T.blk_seg_begin[blk + 1] - sb) * CV_HT;
+    for (int it = lane; it < items; it += 32) {
+        int t = it & (CV_HT - 1), sg = sb + (it >> 4);
+        int ct = half * CV_HT + t;
         int first = T.seg_first[sg], len = T.seg_len[sg];
         int grow = blk * CV_RB + first;
-        double lam = sh.lam[t];
+        double lam = F.lam[ct];
         double off = (lam - T.row_j0[grow]) * (1.0 / CV_W);
         int rs = 0;
         if (off >= (double)(len - 1))
@@ -247,66 +311,53 @@ CV_HD void cv_phase_seeds(int tid, int nthreads, const CvModelDesc &m, int blk, 
         else if (off > 0.0)
             rs = (int)off;
         double seed = cv_seed(T.row_j0[grow + rs], T.row_head_h[grow + rs], T.row_head_l[grow + rs],
-                              sh.lh[t], sh.ll[t], sh.lin[t], sh.f[t]);
-        double *srow = sh.SD + t * CV_SSTRIDE + first;
-        srow[rs] = seed;
+                              F.lh[ct], F.ll[ct], F.lin[ct], F.f[ct]);
+        double *col = F.SD + first * CV_SDS + t;
+        col[rs * CV_SDS] = seed;
+        const int nup = len - 1 - rs;
+        const double step_up = F.pw16[t], step_dn = F.ipw16[t];
+        const double *tab_up = M.row_up + grow, *tab_dn = M.row_dn + grow;
         double v = seed;
-        double step = sh.pw16[t];
-        for (int r = rs + 1; r < len; r++) {
-            v = cv_mul(cv_mul(v, step), T.row_up[grow + r]);
-            srow[r] = v;
-        }
-        v = seed;
-        step = sh.ipw16[t];
-        for (int r = rs - 1; r >= 0; r--) {
-            v = cv_mul(cv_mul(v, step), T.row_dn[grow + r]);
-            srow[r] = v;
-        }
-    }
-}
-
-/* The accumulators of a thread: rows rg + 16a (a < 4), columns 8cg + b (b < 8) of the block, with
- * rg = lane >> 1, cg = lane & 1; warp w takes the terms t = w, w + CV_NWARP, ... (split over terms,
- * summed in cv_phase_epilogue). */
-CV_HD void cv_phase_fma(int tid, int nterms, int nrows_blk, const CvPointShared &sh, double *acc)
-{
-    int warp = tid >> 5, lane = tid & 31;
-    int rg = lane >> 1, cg = lane & 1;
-    bool live0 = rg < nrows_blk, live1 = rg + 16 < nrows_blk, live2 = rg + 32 < nrows_blk,
-         live3 = rg + 48 < nrows_blk;
-    for (int t = warp; t < nterms; t += CV_NWARP) {
-        const double *srow = sh.SD + t * CV_SSTRIDE + rg;
-        const double *pw = sh.PW + t * CV_W + cg * 8;
-        double b[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            b[i] = pw[i];
-        double a0 = live0 ? srow[0] : 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            acc[i] = cv_fma(a0, b[i], acc[i]);
-        if (nrows_blk > 16) {
-            double a1 = live1 ? srow[16] : 0.0;
-            double a2 = live2 ? srow[32] : 0.0;
-            double a3 = live3 ? srow[48] : 0.0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                acc[8 + i] = cv_fma(a1, b[i], acc[8 + i]);
-                acc[16 + i] = cv_fma(a2, b[i], acc[16 + i]);
-                acc[24 + i] = cv_fma(a3, b[i], acc[24 + i]);
-            }
+        for (int k = 1; k < len; k++) {
+            bool goes_up = k <= nup;
+            int r = goes_up ? rs + k : rs + nup - k;
+            /* G(j0 +- 16) = G(j0) * [lam^+-16 * factorial ratio]; the bracket does not depend on
+             * the running value, which keeps the chain one multiplication deep per row */
+            double ratio = goes_up ? tab_up[r] : tab_dn[r];
+            double c = cv_mul(goes_up ? step_up : step_dn, ratio);
+            if (k == nup + 1)
+                v = seed;
+            v = cv_mul(v, c);
+            col[r * CV_SDS] = v;
         }
     }
 }
 
-/* reduction buffer: red[warp][a][b][lane] */
-CV_HD void cv_phase_spill(int tid, CvPointShared &sh, const double *acc)
+/* The accumulators of a lane: rows rg + 8a (a < 8), columns 4cg + c (c < 4) of the block, with
+ * rg = lane >> 2, cg = lane & 3; acc[4a + c].  NA = number of live 8-row groups of the block. */
+template <int NA>
+CV_HD void cv_w_fma(int lane, const CvWarpFixed &F, double *acc)
 {
-    int warp = tid >> 5, lane = tid & 31;
-    double *red = sh.SD + warp * (CV_RB * CV_W);
+    int rg = lane >> 2, cg = lane & 3;
+    const double *sd = F.SD + rg * CV_SDS;
+    const double *pw = F.PW + cg * 4;
+#pragma unroll 2
+    for (int t = 0; t < CV_HT; t += 2) {
+        cv_pair b0l = cv_ld2(pw + t * CV_W), b0h = cv_ld2(pw + t * CV_W + 2);
+        cv_pair b1l = cv_ld2(pw + (t + 1) * CV_W), b1h = cv_ld2(pw + (t + 1) * CV_W + 2);
 #pragma unroll
-    for (int e = 0; e < 32; e++)
-        red[e * 32 + lane] = acc[e];
+        for (int a = 0; a < NA; a++) {
+            cv_pair s = cv_ld2(sd + a * 8 * CV_SDS + t); /* terms t and t+1 of row rg + 8a */
+            acc[4 * a + 0] = cv_fma(s.x, b0l.x, acc[4 * a + 0]);
+            acc[4 * a + 1] = cv_fma(s.x, b0l.y, acc[4 * a + 1]);
+            acc[4 * a + 2] = cv_fma(s.x, b0h.x, acc[4 * a + 2]);
+            acc[4 * a + 3] = cv_fma(s.x, b0h.y, acc[4 * a + 3]);
+            acc[4 * a + 0] = cv_fma(s.y, b1l.x, acc[4 * a + 0]);
+            acc[4 * a + 1] = cv_fma(s.y, b1l.y, acc[4 * a + 1]);
+            acc[4 * a + 2] = cv_fma(s.y, b1h.x, acc[4 * a + 2]);
+            acc[4 * a + 3] = cv_fma(s.y, b1h.y, acc[4 * a + 3]);
+        }
+    }
 }
 
 CV_HD void cv_partial_add_mass(CvPartial &p, double x)
@@ -332,32 +383,32 @@ CV_HD void cv_partial_merge(CvPartial &p, const CvPartial &q)
     p.sum_l = cv_add(p.sum_l, q.sum_l);
 }
 
-/* models.py:100-107 per bin.  Thread tid finishes the slots e = tid + CV_NT n of the [a][b][lane]
- * order of cv_phase_spill. */
-CV_HD void cv_phase_epilogue(int tid, const CvModelDesc &m, int blk, const CvPointShared &sh,
-                             CvPartial &part, double *out_probs)
+/* models.py:100-107 per bin, for the 8 NA x 4 slots of this lane. */
+template <int NA>
+CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, const double *acc, CvPartial &part,
+                         double *out_probs)
 {
     const CvTables &T = m.tab;
-    for (int n = 0; n < (CV_RB * CV_W) / CV_NT; n++) {
-        int e = tid + n * CV_NT;
-        double v = 0.0;
+    int rg = lane >> 2, cg = lane & 3;
 #pragma unroll
-        for (int w = 0; w < CV_NWARP; w++)
-            v = cv_add(v, sh.SD[w * (CV_RB * CV_W) + e]);
-        int lane = e & 31, b = (e >> 5) & 7, a = e >> 8;
-        int row = (lane >> 1) + 16 * a, col = 8 * (lane & 1) + b;
-        int slot = (blk * CV_RB + row) * CV_W + col;
-        double mult = T.slot_mult[slot];
-        if (mult == 0.0)
-            continue; /* a bin that is not in hist */
-        double p = cv_mul(v, mult);
-        if (out_probs)
-            out_probs[T.slot_bin[slot]] = p;
-        cv_partial_add_mass(part, p);
-        double h = T.slot_h[slot];
-        if (h != 0.0) { /* models.py:106 `if h` */
-            double lg = (p <= 0.0) ? -INFINITY : log(p); /* utils.py:32-35 safe_log */
-            cv_partial_add_sum(part, cv_mul(h, lg));
+    for (int a = 0; a < NA; a++) {
+        int slot = (blk * CV_RB + rg + 8 * a) * CV_W + 4 * cg;
+        cv_pair m01 = cv_ld2(T.slot_mult + slot), m23 = cv_ld2(T.slot_mult + slot + 2);
+        cv_pair h01 = cv_ld2(T.slot_h + slot), h23 = cv_ld2(T.slot_h + slot + 2);
+        double mult[4] = {m01.x, m01.y, m23.x, m23.y};
+        double cnt[4] = {h01.x, h01.y, h23.x, h23.y};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (mult[c] == 0.0)
+                continue; /* a bin that is not in hist */
+            double p = cv_mul(acc[4 * a + c], mult[c]);
+            if (out_probs)
+                out_probs[T.slot_bin[slot + c]] = p;
+            cv_partial_add_mass(part, p);
+            if (cnt[c] != 0.0) { /* models.py:106 `if h` */
+                double lg = (p <= 0.0) ? -INFINITY : log(p); /* utils.py:32-35 safe_log */
+                cv_partial_add_sum(part, cv_mul(cnt[c], lg));
+            }
         }
     }
 }
@@ -374,25 +425,9 @@ CV_HD double cv_point_finish(const CvModelDesc &m, const CvPartial &part)
     return cv_finish_loglik(sum, mass, m.tail);
 }
 
-/* Final reduction, in a fixed order: every thread publishes its partial, warp 0 folds
- * CV_NT / 32 partials per lane; the caller finishes with 32 values (lane order). */
-CV_HD void cv_phase_publish(int tid, CvPointShared &sh, const CvPartial &part)
+/* number of live 8-row groups of a block, rounded up to the instantiated 1, 2, 4, 8 */
+CV_HD int cv_row_groups(int nrows_blk)
 {
-    double *red = sh.SD; /* free after the last epilogue (the caller synchronises) */
-    red[tid] = part.sum_h;
-    red[CV_NT + tid] = part.sum_l;
-    red[2 * CV_NT + tid] = part.mass_h;
-    red[3 * CV_NT + tid] = part.mass_l;
-}
-
-CV_HD CvPartial cv_phase_fold(int lane, const CvPointShared &sh)
-{
-    const double *red = sh.SD;
-    CvPartial acc = {red[lane], red[CV_NT + lane], red[2 * CV_NT + lane], red[3 * CV_NT + lane]};
-    for (int w = 1; w < CV_NWARP; w++) {
-        int i = lane + 32 * w;
-        CvPartial q = {red[i], red[CV_NT + i], red[2 * CV_NT + i], red[3 * CV_NT + i]};
-        cv_partial_merge(acc, q);
-    }
-    return acc;
+    int na = (nrows_blk + 7) >> 3;
+    return na <= 1 ? 1 : na <= 2 ? 2 : na <= 4 ? 4 : 8;
 }

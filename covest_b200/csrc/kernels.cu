@@ -1,10 +1,11 @@
 /*
  * kernels.cu -- hand-written sm_100a kernels of the CovEst likelihood path.
  *
- *   cv_loglik_kernel   K1/K2: one 128-thread CTA per parameter point, four CTAs per SM (persistent
- *                      CTAs drawing point indices
- *                      from a device counter), phases of cvpoint.h separated by __syncthreads().
- *                      FP64 throughout; the inner loop is one DFMA per (mixture term, bin).
+ *   cv_loglik_kernel   K1/K2: one WARP per parameter point, up to 16 warps in the one CTA of an SM
+ *                      (persistent warps drawing point indices from a device counter), phases of
+ *                      cvpoint.h separated by __syncwarp() -- no CTA-wide barrier after the row
+ *                      tables are staged.  FP64 throughout; the inner loop is one DFMA per
+ *                      (mixture term, bin) with operands read from shared memory as 16-byte pairs.
  *   cv_topk_select     K3: deterministic top-K of the log-likelihoods.
  *   cv_gather_rows     (ll, params...) rows of the selected points.
  *   cv_peak_probe      register-resident DFMA / DMMA chains: the measured FP64 roofline.
@@ -29,8 +30,6 @@ __device__ __forceinline__ void cv_lattice_point(const CvLattice &lat, long long
     }
 }
 
-#define CV_CTAS_PER_SM 4
-
 __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, int delta)
 {
     CvPartial q;
@@ -41,108 +40,170 @@ __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, in
     return q;
 }
 
-__global__ void __launch_bounds__(CV_NT, CV_CTAS_PER_SM)
+/* shared memory of a CTA: [row_up | row_dn] (rows_staged doubles each, 0 when they do not fit),
+ * then per warp a CvWarpFixed followed by its variable part */
+__host__ __device__ __forceinline__ size_t cv_warp_bytes(int n_err)
+{
+    size_t b = sizeof(CvWarpFixed) + (size_t)cv_warp_var_doubles(n_err) * sizeof(double);
+    return (b + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(32 * CV_WARPS_MAX, 1)
 cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                  const double *__restrict__ params, long long n_points, int clip,
                  double *__restrict__ out_ll, double *__restrict__ out_probs,
-                 unsigned long long *counter)
+                 unsigned long long *counter, int rows_staged)
 {
     extern __shared__ __align__(16) unsigned char cv_smem_raw[];
-    CvPointShared &sh = *reinterpret_cast<CvPointShared *>(cv_smem_raw);
-    __shared__ long long s_point;
-    __shared__ double s_row[CV_MAX_PARAMS];
-
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = m.n_err;
-    const int cpt = cv_copies_per_tile(S);
+
+    CvWarpMem M;
+    {
+        double *tab = reinterpret_cast<double *>(cv_smem_raw);
+        unsigned char *wbase = cv_smem_raw + (size_t)2 * rows_staged * sizeof(double) +
+                               (size_t)warp * cv_warp_bytes(S);
+        CvWarpFixed *fx = reinterpret_cast<CvWarpFixed *>(wbase);
+        cv_warp_mem_carve(M, fx, reinterpret_cast<double *>(wbase + sizeof(CvWarpFixed)), S);
+        if (rows_staged) {
+            for (int i = threadIdx.x; i < rows_staged; i += blockDim.x) {
+                tab[i] = m.tab.row_up[i];
+                tab[rows_staged + i] = m.tab.row_dn[i];
+            }
+            M.row_up = tab;
+            M.row_dn = tab + rows_staged;
+        } else {
+            M.row_up = m.tab.row_up;
+            M.row_dn = m.tab.row_dn;
+        }
+    }
+    __syncthreads(); /* the only CTA-wide barrier: from here on every warp is on its own */
+
+    const int cpg = cv_copies_per_group(S);
 
     for (;;) {
-        if (tid == 0)
-            s_point = (long long)atomicAdd(counter, 1ULL);
-        __syncthreads();
-        const long long point = s_point;
+        long long point = 0;
+        if (lane == 0)
+            point = (long long)atomicAdd(counter, 1ULL);
+        point = __shfl_sync(CV_FULL_MASK, point, 0);
         if (point >= n_points)
             break;
-        const double *row;
+        double row[CV_MAX_PARAMS];
         if (lat.enabled) {
-            if (tid == 0)
-                cv_lattice_point(lat, point, s_row);
-            __syncthreads();
-            row = s_row;
+            cv_lattice_point(lat, point, row);
         } else {
-            row = params + point * m.n_param;
+#pragma unroll
+            for (int i = 0; i < CV_MAX_PARAMS; i++)
+                row[i] = i < m.n_param ? params[point * m.n_param + i] : 0.0;
         }
-        cv_phase_header(tid, m, row, clip, sh);
-        __syncthreads();
-        if (m.model_kind) { /* models.py:185-191 */
-            for (int first = 1; first < m.max_bin; first += CV_NT) {
-                int cand = cv_phase_cut_candidate(tid, m, sh, first);
-                if (cand != 0x7fffffff)
-                    atomicMin(&sh.o_end, cand);
-                __syncthreads();
-                int o_end_now = sh.o_end;
-                __syncthreads();
-                if (o_end_now < first + CV_NT)
-                    break;
-            }
-        }
-        const int o_end = sh.o_end;
-        const bool single_tile = (o_end - 1) <= cpt;
+        __syncwarp(); /* the previous point's readers of the working set are done */
+        cv_w_header(lane, m, row, clip, M);
+        __syncwarp();
+
         CvPartial part = {0.0, 0.0, 0.0, 0.0};
         double *probs_row = out_probs ? out_probs + point * (long long)m.n_bins : nullptr;
 
         for (int blk = 0; blk < m.n_blocks; blk++) {
-            const int nrows_blk = min(CV_RB, m.n_rows - blk * CV_RB);
+            const int na = cv_row_groups(min(CV_RB, m.n_rows - blk * CV_RB));
             double acc[32];
 #pragma unroll
             for (int i = 0; i < 32; i++)
                 acc[i] = 0.0;
-            for (int tile_o = 1; tile_o < o_end; tile_o += cpt) {
-                const int ncop = min(cpt, o_end - tile_o);
-                const int nterms = ncop * S;
-                if (!(single_tile && blk > 0)) { /* the term constants of a lone tile are kept */
-                    cv_phase_mass(tid, m, tile_o, nterms, sh);
-                    __syncthreads();
-                    cv_phase_terms(tid, m, tile_o, nterms, sh);
-                    __syncthreads();
-                    cv_phase_powers(tid, CV_NT, nterms, sh);
+            /* passes of 32 copy numbers: lane i holds b(first + i); the copies before the first
+             * lane that reports the cut-off are evaluated (models.py:185-191) */
+            for (int first = 1;; first += 32) {
+                double b;
+                bool stop = cv_w_copy_pass(lane, m, M, first, &b);
+                const unsigned stop_mask = __ballot_sync(CV_FULL_MASK, stop);
+                const int nlive = stop_mask ? __ffs(stop_mask) - 1 : 32;
+                for (int g = 0; g < nlive; g += cpg) {
+                    const int ncop = min(cpg, nlive - g);
+                    const int nterms = ncop * S;
+                    cv_w_mass(lane, m, first + g, nterms, M);
+                    __syncwarp();
+                    for (int sub = 0; sub < nterms; sub += CV_CT) {
+                        int src = g + (sub + lane) / S; /* the lane that holds this term's b(o) */
+                        double bt = __shfl_sync(CV_FULL_MASK, b, src < 31 ? src : 31);
+                        cv_w_terms(lane, m, first + g, nterms, sub, bt, M);
+                        __syncwarp();
+                        const int nhalf = (min(CV_CT, nterms - sub) + CV_HT - 1) / CV_HT;
+                        for (int half = 0; half < nhalf; half++) {
+                            cv_w_powers(lane, half, M);
+                            __syncwarp();
+                            cv_w_seeds(lane, m, blk, half, M);
+                            __syncwarp();
+                            switch (na) {
+                            case 1: cv_w_fma<1>(lane, *M.fx, acc); break;
+                            case 2: cv_w_fma<2>(lane, *M.fx, acc); break;
+                            case 4: cv_w_fma<4>(lane, *M.fx, acc); break;
+                            default: cv_w_fma<8>(lane, *M.fx, acc); break;
+                            }
+                            __syncwarp();
+                        }
+                    }
                 }
-                cv_phase_seeds(tid, CV_NT, m, blk, nterms, sh);
-                __syncthreads();
-                cv_phase_fma(tid, nterms, nrows_blk, sh, acc);
-                __syncthreads();
+                if (stop_mask)
+                    break;
             }
-            cv_phase_spill(tid, sh, acc);
-            __syncthreads();
-            cv_phase_epilogue(tid, m, blk, sh, part, probs_row);
-            __syncthreads();
+            switch (na) {
+            case 1: cv_w_epilogue<1>(lane, m, blk, acc, part, probs_row); break;
+            case 2: cv_w_epilogue<2>(lane, m, blk, acc, part, probs_row); break;
+            case 4: cv_w_epilogue<4>(lane, m, blk, acc, part, probs_row); break;
+            default: cv_w_epilogue<8>(lane, m, blk, acc, part, probs_row); break;
+            }
         }
-        /* block reduction of the partial sums, in a fixed order: warp 0 folds the published
-         * partials, then a shuffle tree */
-        cv_phase_publish(tid, sh, part);
-        __syncthreads();
-        if (tid < 32) {
-            CvPartial total = cv_phase_fold(tid, sh);
+        /* warp reduction of the partial sums in a fixed order */
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                CvPartial q = cv_partial_shfl_down(total, d);
-                cv_partial_merge(total, q);
-            }
-            if (tid == 0)
-                out_ll[point] = cv_point_finish(m, total);
+        for (int d = 16; d >= 1; d >>= 1) {
+            CvPartial q = cv_partial_shfl_down(part, d);
+            cv_partial_merge(part, q);
         }
+        if (lane == 0)
+            out_ll[point] = cv_point_finish(m, part);
     }
 }
 
-int cv_loglik_smem_bytes() { return (int)sizeof(CvPointShared); }
+/* warps per CTA and staged rows that fit the shared memory of an SM */
+static void cv_loglik_config(const CvModelDesc &m, int smem_max, int *n_warps, int *rows_staged,
+                             size_t *smem_bytes)
+{
+    const size_t wb = cv_warp_bytes(m.n_err);
+    int rows = m.n_blocks * CV_RB;
+    size_t tab = (size_t)2 * rows * sizeof(double);
+    if (tab + 4 * wb > (size_t)smem_max) { /* huge histograms: row tables stay in global memory */
+        rows = 0;
+        tab = 0;
+    }
+    long long w = ((long long)smem_max - (long long)tab) / (long long)wb;
+    if (w > CV_WARPS_MAX)
+        w = CV_WARPS_MAX;
+    if (w < 1)
+        w = 1;
+    *n_warps = (int)w;
+    *rows_staged = rows;
+    *smem_bytes = tab + (size_t)w * wb;
+}
+
+int cv_loglik_smem_bytes(const CvModelDesc &m, int smem_max)
+{
+    int w, r;
+    size_t b;
+    cv_loglik_config(m, smem_max, &w, &r, &b);
+    return (int)b;
+}
 
 cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const double *params,
                              long long n_points, int clip, double *out_ll, double *out_probs,
-                             unsigned long long *counter, int n_sm, cudaStream_t stream)
+                             unsigned long long *counter, int n_sm, int smem_max, cudaStream_t stream)
 {
+    int n_warps, rows_staged;
+    size_t smem;
+    cv_loglik_config(m, smem_max, &n_warps, &rows_staged, &smem);
+    if (smem > (size_t)smem_max)
+        return cudaErrorInvalidConfiguration;
     /* per device, and cheap: set on every launch */
     cudaError_t e = cudaFuncSetAttribute(cv_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         cv_loglik_smem_bytes());
+                                         (int)smem);
     if (e != cudaSuccess)
         return e;
     if (n_points <= 0)
@@ -150,10 +211,16 @@ cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const d
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess)
         return e;
-    long long want = (long long)CV_CTAS_PER_SM * n_sm; /* resident CTAs */
-    int grid = (int)(n_points < want ? n_points : want);
-    cv_loglik_kernel<<<grid, CV_NT, cv_loglik_smem_bytes(), stream>>>(m, lat, params, n_points, clip,
-                                                                      out_ll, out_probs, counter);
+    /* one persistent CTA per SM; a small batch is spread over the SMs first (fewer warps per CTA) */
+    if (n_points < (long long)n_sm * n_warps) {
+        int w = (int)((n_points + n_sm - 1) / n_sm);
+        smem -= (size_t)(n_warps - w) * cv_warp_bytes(m.n_err);
+        n_warps = w;
+    }
+    long long ctas = (n_points + n_warps - 1) / n_warps;
+    int grid = (int)(ctas < n_sm ? ctas : n_sm);
+    cv_loglik_kernel<<<grid, 32 * n_warps, smem, stream>>>(m, lat, params, n_points, clip, out_ll,
+                                                           out_probs, counter, rows_staged);
     return cudaGetLastError();
 }
 

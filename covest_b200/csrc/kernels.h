@@ -20,10 +20,11 @@ struct CvLattice {
 
 /* K1/K2: log-likelihood (and optionally the per-bin probabilities) of n_points points.
  * `params` (device, row-major n_points x n_param) is ignored when lat.enabled.
- * `counter` is a device word the persistent CTAs draw point indices from; zeroed here. */
+ * `counter` is a device word the persistent warps draw point indices from; zeroed here.
+ * `smem_max` is cudaDevAttrMaxSharedMemoryPerBlockOptin of the device. */
 cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const double *params,
                              long long n_points, int clip, double *out_ll, double *out_probs,
-                             unsigned long long *counter, int n_sm, cudaStream_t stream);
+                             unsigned long long *counter, int n_sm, int smem_max, cudaStream_t stream);
 
 /* K3: rows of the K largest log-likelihoods (ties: lower index first; NaN never selected before
  * a number).  out_idx/out_ll: device, K entries, descending (missing entries: -inf, -1).
@@ -42,4 +43,5 @@ cudaError_t cv_launch_gather_rows(const CvLattice &lat, const double *params, in
 cudaError_t cv_launch_peak_probe(int kind, int n_cta, int iters, double *sink, double *flop,
                                  cudaStream_t stream);
 
-int cv_loglik_smem_bytes();
+/* dynamic shared memory of a cv_loglik_kernel CTA given the opt-in limit of the device */
+int cv_loglik_smem_bytes(const CvModelDesc &m, int smem_max);

@@ -1,10 +1,11 @@
 /* Test-only host execution of the kernel's per-point phases (covest_b200/csrc/cvpoint.h).
  *
- * The sm_100a kernel runs every phase with 256 threads and a __syncthreads() between phases; here
- * the same phase functions are called in a serial loop over `tid`, phase by phase, which performs
- * the same arithmetic in the same order (the final cross-thread reduction is a plain loop).  This
- * lets the CPU test-suite check the *formulation* -- scaling, seeds, recurrences, tables -- against
- * the oracle without a GPU.  It is NOT a CPU fallback: nothing under covest_b200/ loads it.
+ * The sm_100a kernel runs every phase with the 32 lanes of one warp and a __syncwarp() between
+ * phases; here the same phase functions are called in a serial loop over `lane`, phase by phase,
+ * which performs the same arithmetic in the same order (ballot, shuffles and the final shuffle tree
+ * are plain loops over a 32-entry array).  This lets the CPU test-suite check the *formulation* --
+ * scaling, seeds, recurrences, tables -- against the oracle without a GPU.  It is NOT a CPU
+ * fallback: nothing under covest_b200/ loads it.
  *
  *   g++ -O2 -ffp-contract=off -fPIC -shared emulate.cpp -o libcv_emulate.so
  */
@@ -13,58 +14,96 @@
 
 #include "../../covest_b200/csrc/cvtables.h"
 
-static void emulate_point(const CvModelDesc &m, const double *row, int clip, double *out_ll,
+template <int NA>
+static void emu_fma(const CvWarpFixed &F, double *acc)
+{
+    for (int lane = 0; lane < 32; lane++)
+        cv_w_fma<NA>(lane, F, acc + 32 * lane);
+}
+
+template <int NA>
+static void emu_epilogue(const CvModelDesc &m, int blk, const double *acc, CvPartial *part,
+                         double *out_probs)
+{
+    for (int lane = 0; lane < 32; lane++)
+        cv_w_epilogue<NA>(lane, m, blk, acc + 32 * lane, part[lane], out_probs);
+}
+
+static void emulate_point(const CvModelDesc &m, const double *row_in, int clip, double *out_ll,
                           double *out_probs)
 {
-    static CvPointShared sh;
-    std::vector<double> acc((size_t)CV_NT * 32);
-    for (int tid = 0; tid < CV_NT; tid++)
-        cv_phase_header(tid, m, row, clip, sh);
-    if (m.model_kind) {
-        for (int first = 1; first < m.max_bin; first += CV_NT) {
-            int best = sh.o_end;
-            for (int tid = 0; tid < CV_NT; tid++)
-                best = std::min(best, cv_phase_cut_candidate(tid, m, sh, first));
-            sh.o_end = best;
-            if (sh.o_end < first + CV_NT)
+    static CvWarpFixed fx;
+    const int S = m.n_err;
+    std::vector<double> var(cv_warp_var_doubles(S));
+    CvWarpMem M;
+    cv_warp_mem_carve(M, &fx, var.data(), S);
+    M.row_up = m.tab.row_up;
+    M.row_dn = m.tab.row_dn;
+    double row[CV_MAX_PARAMS] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < m.n_param; i++)
+        row[i] = row_in[i];
+    for (int lane = 0; lane < 32; lane++)
+        cv_w_header(lane, m, row, clip, M);
+    const int cpg = cv_copies_per_group(S);
+    std::vector<double> acc(32 * 32);
+    CvPartial part[32];
+    for (int lane = 0; lane < 32; lane++)
+        part[lane] = CvPartial{0, 0, 0, 0};
+    for (int blk = 0; blk < m.n_blocks; blk++) {
+        const int na = cv_row_groups(std::min(CV_RB, m.n_rows - blk * CV_RB));
+        std::fill(acc.begin(), acc.end(), 0.0);
+        for (int first = 1;; first += 32) {
+            double b[32];
+            int nlive = 32;
+            bool any = false;
+            for (int lane = 31; lane >= 0; lane--)
+                if (cv_w_copy_pass(lane, m, M, first, &b[lane])) {
+                    nlive = lane;
+                    any = true;
+                }
+            for (int g = 0; g < nlive; g += cpg) {
+                const int ncop = std::min(cpg, nlive - g);
+                const int nterms = ncop * S;
+                for (int lane = 0; lane < 32; lane++)
+                    cv_w_mass(lane, m, first + g, nterms, M);
+                for (int sub = 0; sub < nterms; sub += CV_CT) {
+                    for (int lane = 0; lane < 32; lane++) {
+                        int src = g + (sub + lane) / S;
+                        cv_w_terms(lane, m, first + g, nterms, sub, b[src < 31 ? src : 31], M);
+                    }
+                    const int nhalf = (std::min(CV_CT, nterms - sub) + CV_HT - 1) / CV_HT;
+                    for (int half = 0; half < nhalf; half++) {
+                        for (int lane = 0; lane < 32; lane++)
+                            cv_w_powers(lane, half, M);
+                        for (int lane = 0; lane < 32; lane++)
+                            cv_w_seeds(lane, m, blk, half, M);
+                        switch (na) {
+                        case 1: emu_fma<1>(fx, acc.data()); break;
+                        case 2: emu_fma<2>(fx, acc.data()); break;
+                        case 4: emu_fma<4>(fx, acc.data()); break;
+                        default: emu_fma<8>(fx, acc.data()); break;
+                        }
+                    }
+                }
+            }
+            if (any)
                 break;
         }
-    }
-    int S = m.n_err, cpt = cv_copies_per_tile(S);
-    CvPartial total = {0, 0, 0, 0};
-    std::vector<CvPartial> part(CV_NT, CvPartial{0, 0, 0, 0});
-    for (int blk = 0; blk < m.n_blocks; blk++) {
-        int nrows_blk = std::min(CV_RB, m.n_rows - blk * CV_RB);
-        std::fill(acc.begin(), acc.end(), 0.0);
-        for (int tile_o = 1; tile_o < sh.o_end; tile_o += cpt) {
-            int ncop = std::min(cpt, sh.o_end - tile_o);
-            int nterms = ncop * S;
-            for (int tid = 0; tid < CV_NT; tid++)
-                cv_phase_mass(tid, m, tile_o, nterms, sh);
-            for (int tid = 0; tid < CV_NT; tid++)
-                cv_phase_terms(tid, m, tile_o, nterms, sh);
-            for (int tid = 0; tid < CV_NT; tid++)
-                cv_phase_powers(tid, CV_NT, nterms, sh);
-            for (int tid = 0; tid < CV_NT; tid++)
-                cv_phase_seeds(tid, CV_NT, m, blk, nterms, sh);
-            for (int tid = 0; tid < CV_NT; tid++)
-                cv_phase_fma(tid, nterms, nrows_blk, sh, &acc[(size_t)tid * 32]);
+        switch (na) {
+        case 1: emu_epilogue<1>(m, blk, acc.data(), part, out_probs); break;
+        case 2: emu_epilogue<2>(m, blk, acc.data(), part, out_probs); break;
+        case 4: emu_epilogue<4>(m, blk, acc.data(), part, out_probs); break;
+        default: emu_epilogue<8>(m, blk, acc.data(), part, out_probs); break;
         }
-        for (int tid = 0; tid < CV_NT; tid++)
-            cv_phase_spill(tid, sh, &acc[(size_t)tid * 32]);
-        for (int tid = 0; tid < CV_NT; tid++)
-            cv_phase_epilogue(tid, m, blk, sh, part[tid], out_probs);
     }
-    for (int tid = 0; tid < CV_NT; tid++)
-        cv_phase_publish(tid, sh, part[tid]);
-    for (int lane = 0; lane < 32; lane++) {
-        CvPartial q = cv_phase_fold(lane, sh);
-        if (lane == 0)
-            total = q;
-        else
-            cv_partial_merge(total, q);
+    /* __shfl_down_sync tree: a lane whose source is out of range receives its own value */
+    for (int d = 16; d >= 1; d >>= 1) {
+        CvPartial prev[32];
+        memcpy(prev, part, sizeof(prev));
+        for (int lane = 0; lane < 32; lane++)
+            cv_partial_merge(part[lane], prev[lane + d < 32 ? lane + d : lane]);
     }
-    *out_ll = cv_point_finish(m, total);
+    *out_ll = cv_point_finish(m, part[0]);
 }
 
 extern "C" int emu_loglik_batch(int model_kind, int k, int r, int n_err, int n_bins,
