@@ -91,8 +91,8 @@ struct CvWarpMem {
     double *lls_h, *lls_l; /* [S] log(l_s), double-double */
     double *nmass;         /* [group terms] n_os */
     double *glam;          /* [group terms] o * l_s */
-    const double *row_up;  /* CvTables.row_up / row_dn (staged in shared memory when they fit) */
-    const double *row_dn;
+    /* the row tables of CvTables every warp of the CTA reads (staged in shared memory) */
+    const double *row_j0, *row_head_h, *row_head_l, *row_up, *row_dn;
 };
 
 /* terms of the largest group: whole copies, at most 32 terms unless one copy alone has more */
@@ -288,47 +288,87 @@ CV_HD void cv_w_powers(int lane, int half, CvWarpMem &M)
         F.pw16[t] = l16;
 }
 
-/* Seeds of every (term, row) of block `blk`.  A work item is (term, segment); it takes one exp()
- * at the row of the segment that holds the mode of the term (j ~ lam) and walks outwards -- first
- * up, then down, in ONE loop so that lanes with different mode rows do not diverge -- where the
- * term only decreases, so that a value that underflowed never has to grow back. */
+/* Seeds of every (term, row) of block `blk`.  A work item is (term, segment): one exp() at one row
+ * of the segment, then the product recurrence walked over the other rows, one multiplication deep
+ * per row because the factor lam^+-16 * (factorial ratio) does not depend on the running value.
+ * Where the walk starts:
+ *   - mode of the term (j ~ lam) at or above the top row: at the top row, walking down;
+ *   - otherwise at the bottom row, walking up through the mode, when the value there is well inside
+ *     the double range (it always is unless the weight of the term is minute);
+ *   - otherwise at the row holding the mode, walking up and then down, so that a value that
+ *     underflowed never has to grow back.
+ * The first two cases share one loop with a per-lane direction, so lanes do not diverge. */
 CV_HD void cv_w_seeds(int lane, const CvModelDesc &m, int blk, int half, CvWarpMem &M)
 {
     CvWarpFixed &F = *M.fx;
     const CvTables &T = m.tab;
-    int sb = T.blk_seg_begin[blk];
-    int items = (T.blk_seg_begin[blk + 1] - sb) * CV_HT;
+    const int sb = T.blk_seg_begin[blk];
+    const int items = (T.blk_seg_begin[blk + 1] - sb) * CV_HT;
     for (int it = lane; it < items; it += 32) {
-        int t = it & (CV_HT - 1), sg = sb + (it >> 4);
-        int ct = half * CV_HT + t;
-        int first = T.seg_first[sg], len = T.seg_len[sg];
-        int grow = blk * CV_RB + first;
-        double lam = F.lam[ct];
-        double off = (lam - T.row_j0[grow]) * (1.0 / CV_W);
-        int rs = 0;
-        if (off >= (double)(len - 1))
-            rs = len - 1;
-        else if (off > 0.0)
-            rs = (int)off;
-        double seed = cv_seed(T.row_j0[grow + rs], T.row_head_h[grow + rs], T.row_head_l[grow + rs],
-                              F.lh[ct], F.ll[ct], F.lin[ct], F.f[ct]);
+        const int t = it & (CV_HT - 1), sg = sb + (it >> 4);
+        const int ct = half * CV_HT + t;
+        const int first = T.seg_first[sg], top = T.seg_len[sg] - 1;
+        const int grow = blk * CV_RB + first;
+        const double lam = F.lam[ct], lh = F.lh[ct], lin = F.lin[ct], f = F.f[ct];
+        const double j0 = M.row_j0[grow];
+        const double off = (lam - j0) * (1.0 / CV_W);
+        /* exponent of the scaled term at the bottom row, to a few ulps */
+        const double e0 = cv_sub(cv_fma(j0, lh, M.row_head_h[grow]), lin);
+        int rs;
+        if (off >= (double)top)
+            rs = top;
+        else if (e0 > -460.0 && !(f < 0x1p-200))
+            rs = 0;
+        else
+            rs = off > 0.0 ? (int)off : 0;
+        const double seed = cv_seed(M.row_j0[grow + rs], M.row_head_h[grow + rs], M.row_head_l[grow + rs],
+                                    lh, F.ll[ct], lin, f);
         double *col = F.SD + first * CV_SDS + t;
         col[rs * CV_SDS] = seed;
-        const int nup = len - 1 - rs;
-        const double step_up = F.pw16[t], step_dn = F.ipw16[t];
-        const double *tab_up = M.row_up + grow, *tab_dn = M.row_dn + grow;
-        double v = seed;
-        for (int k = 1; k < len; k++) {
-            bool goes_up = k <= nup;
-            int r = goes_up ? rs + k : rs + nup - k;
-            /* G(j0 +- 16) = G(j0) * [lam^+-16 * factorial ratio]; the bracket does not depend on
-             * the running value, which keeps the chain one multiplication deep per row */
-            double ratio = goes_up ? tab_up[r] : tab_dn[r];
-            double c = cv_mul(goes_up ? step_up : step_dn, ratio);
-            if (k == nup + 1)
-                v = seed;
-            v = cv_mul(v, c);
-            col[r * CV_SDS] = v;
+        const bool down = rs == top;
+        const double step_dn = F.ipw16[t];
+        {
+            const int n1 = down ? top : top - rs;
+            const int dt = down ? -1 : 1;
+            const double *tp = (down ? M.row_dn : M.row_up) + grow + rs + dt;
+            double *sp = col + (rs + dt) * CV_SDS;
+            const double step = down ? step_dn : F.pw16[t];
+            double v = seed;
+            int k = 0;
+            /* four rows at a time: the four table reads and factor products are issued together,
+             * only the running value is a dependent chain */
+            for (; k + 4 <= n1; k += 4) {
+                double r0 = tp[0], r1 = tp[dt], r2 = tp[2 * dt], r3 = tp[3 * dt];
+                double c0 = cv_mul(step, r0), c1 = cv_mul(step, r1), c2 = cv_mul(step, r2),
+                       c3 = cv_mul(step, r3);
+                double v0 = cv_mul(v, c0);
+                double v1 = cv_mul(v0, c1);
+                double v2 = cv_mul(v1, c2);
+                v = cv_mul(v2, c3);
+                sp[0] = v0;
+                sp[dt * CV_SDS] = v1;
+                sp[2 * dt * CV_SDS] = v2;
+                sp[3 * dt * CV_SDS] = v;
+                tp += 4 * dt;
+                sp += 4 * dt * CV_SDS;
+            }
+            for (; k < n1; k++) {
+                v = cv_mul(v, cv_mul(step, *tp));
+                *sp = v;
+                tp += dt;
+                sp += dt * CV_SDS;
+            }
+        }
+        if (!down) { /* the rows below an interior starting row */
+            const double *tp = M.row_dn + grow + rs - 1;
+            double *sp = col + (rs - 1) * CV_SDS;
+            double v = seed;
+            for (int k = 0; k < rs; k++) {
+                v = cv_mul(v, cv_mul(step_dn, *tp));
+                *sp = v;
+                tp -= 1;
+                sp -= CV_SDS;
+            }
         }
     }
 }
@@ -341,13 +381,17 @@ CV_HD void cv_w_fma(int lane, const CvWarpFixed &F, double *acc)
     int rg = lane >> 2, cg = lane & 3;
     const double *sd = F.SD + rg * CV_SDS;
     const double *pw = F.PW + cg * 4;
-#pragma unroll 2
+    cv_pair s = cv_ld2(sd); /* terms t and t+1 of row rg + 8a; always loaded one step ahead */
+#pragma unroll 1
     for (int t = 0; t < CV_HT; t += 2) {
         cv_pair b0l = cv_ld2(pw + t * CV_W), b0h = cv_ld2(pw + t * CV_W + 2);
         cv_pair b1l = cv_ld2(pw + (t + 1) * CV_W), b1h = cv_ld2(pw + (t + 1) * CV_W + 2);
 #pragma unroll
         for (int a = 0; a < NA; a++) {
-            cv_pair s = cv_ld2(sd + a * 8 * CV_SDS + t); /* terms t and t+1 of row rg + 8a */
+            /* after the last row group: the first row group of the next pair (the last pair
+             * wraps around to a harmless reload) */
+            cv_pair nx = (a + 1 < NA) ? cv_ld2(sd + (a + 1) * 8 * CV_SDS + t)
+                                      : cv_ld2(sd + ((t + 2) & (CV_HT - 1)));
             acc[4 * a + 0] = cv_fma(s.x, b0l.x, acc[4 * a + 0]);
             acc[4 * a + 1] = cv_fma(s.x, b0l.y, acc[4 * a + 1]);
             acc[4 * a + 2] = cv_fma(s.x, b0h.x, acc[4 * a + 2]);
@@ -356,7 +400,21 @@ CV_HD void cv_w_fma(int lane, const CvWarpFixed &F, double *acc)
             acc[4 * a + 1] = cv_fma(s.y, b1l.y, acc[4 * a + 1]);
             acc[4 * a + 2] = cv_fma(s.y, b1h.x, acc[4 * a + 2]);
             acc[4 * a + 3] = cv_fma(s.y, b1h.y, acc[4 * a + 3]);
+            s = nx;
         }
+    }
+}
+
+/* The accumulators of a lane go to the seed matrix (free after the last fma of a block) in slot
+ * order, slot = row * 16 + column. */
+CV_HD void cv_w_spill(int lane, CvWarpFixed &F, const double *acc)
+{
+    int rg = lane >> 2, cg = lane & 3;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        double *dst = F.SD + (rg + 8 * a) * CV_W + 4 * cg;
+        cv_st2(dst, acc[4 * a + 0], acc[4 * a + 1]);
+        cv_st2(dst + 2, acc[4 * a + 2], acc[4 * a + 3]);
     }
 }
 
@@ -383,32 +441,29 @@ CV_HD void cv_partial_merge(CvPartial &p, const CvPartial &q)
     p.sum_l = cv_add(p.sum_l, q.sum_l);
 }
 
-/* models.py:100-107 per bin, for the 8 NA x 4 slots of this lane. */
-template <int NA>
-CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, const double *acc, CvPartial &part,
-                         double *out_probs)
+/* models.py:100-107 per bin: lane l finishes the slots l, l + 32, ... of the block (a compact
+ * loop: the unrolled form of this, with its 32 logarithms, does not fit the instruction cache). */
+CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, int nrows_blk, const CvWarpFixed &F,
+                         CvPartial &part, double *out_probs)
 {
     const CvTables &T = m.tab;
-    int rg = lane >> 2, cg = lane & 3;
-#pragma unroll
-    for (int a = 0; a < NA; a++) {
-        int slot = (blk * CV_RB + rg + 8 * a) * CV_W + 4 * cg;
-        cv_pair m01 = cv_ld2(T.slot_mult + slot), m23 = cv_ld2(T.slot_mult + slot + 2);
-        cv_pair h01 = cv_ld2(T.slot_h + slot), h23 = cv_ld2(T.slot_h + slot + 2);
-        double mult[4] = {m01.x, m01.y, m23.x, m23.y};
-        double cnt[4] = {h01.x, h01.y, h23.x, h23.y};
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            if (mult[c] == 0.0)
-                continue; /* a bin that is not in hist */
-            double p = cv_mul(acc[4 * a + c], mult[c]);
-            if (out_probs)
-                out_probs[T.slot_bin[slot + c]] = p;
-            cv_partial_add_mass(part, p);
-            if (cnt[c] != 0.0) { /* models.py:106 `if h` */
-                double lg = (p <= 0.0) ? -INFINITY : log(p); /* utils.py:32-35 safe_log */
-                cv_partial_add_sum(part, cv_mul(cnt[c], lg));
-            }
+    const double *mult = T.slot_mult + blk * (CV_RB * CV_W);
+    const double *cnt = T.slot_h + blk * (CV_RB * CV_W);
+    const int *bin = T.slot_bin + blk * (CV_RB * CV_W);
+    const int nslots = nrows_blk * CV_W;
+#pragma unroll 2
+    for (int e = lane; e < nslots; e += 32) {
+        double mu = mult[e];
+        if (mu == 0.0)
+            continue; /* a bin that is not in hist */
+        double p = cv_mul(F.SD[e], mu);
+        if (out_probs)
+            out_probs[bin[e]] = p;
+        cv_partial_add_mass(part, p);
+        double h = cnt[e];
+        if (h != 0.0) { /* models.py:106 `if h` */
+            double lg = (p <= 0.0) ? -INFINITY : log(p); /* utils.py:32-35 safe_log */
+            cv_partial_add_sum(part, cv_mul(h, lg));
         }
     }
 }

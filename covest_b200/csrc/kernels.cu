@@ -40,8 +40,8 @@ __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, in
     return q;
 }
 
-/* shared memory of a CTA: [row_up | row_dn] (rows_staged doubles each, 0 when they do not fit),
- * then per warp a CvWarpFixed followed by its variable part */
+/* shared memory of a CTA: the five row tables (rows_staged doubles each), then per warp a
+ * CvWarpFixed followed by its variable part */
 __host__ __device__ __forceinline__ size_t cv_warp_bytes(int n_err)
 {
     size_t b = sizeof(CvWarpFixed) + (size_t)cv_warp_var_doubles(n_err) * sizeof(double);
@@ -61,21 +61,21 @@ cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ 
     CvWarpMem M;
     {
         double *tab = reinterpret_cast<double *>(cv_smem_raw);
-        unsigned char *wbase = cv_smem_raw + (size_t)2 * rows_staged * sizeof(double) +
+        unsigned char *wbase = cv_smem_raw + (size_t)5 * rows_staged * sizeof(double) +
                                (size_t)warp * cv_warp_bytes(S);
         CvWarpFixed *fx = reinterpret_cast<CvWarpFixed *>(wbase);
         cv_warp_mem_carve(M, fx, reinterpret_cast<double *>(wbase + sizeof(CvWarpFixed)), S);
-        if (rows_staged) {
-            for (int i = threadIdx.x; i < rows_staged; i += blockDim.x) {
-                tab[i] = m.tab.row_up[i];
-                tab[rows_staged + i] = m.tab.row_dn[i];
-            }
-            M.row_up = tab;
-            M.row_dn = tab + rows_staged;
-        } else {
-            M.row_up = m.tab.row_up;
-            M.row_dn = m.tab.row_dn;
-        }
+        const double *src[5] = {m.tab.row_j0, m.tab.row_head_h, m.tab.row_head_l, m.tab.row_up,
+                                m.tab.row_dn};
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+            for (int i = threadIdx.x; i < rows_staged; i += blockDim.x)
+                tab[k * rows_staged + i] = src[k][i];
+        M.row_j0 = tab;
+        M.row_head_h = tab + rows_staged;
+        M.row_head_l = tab + 2 * rows_staged;
+        M.row_up = tab + 3 * rows_staged;
+        M.row_dn = tab + 4 * rows_staged;
     }
     __syncthreads(); /* the only CTA-wide barrier: from here on every warp is on its own */
 
@@ -145,12 +145,10 @@ cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ 
                 if (stop_mask)
                     break;
             }
-            switch (na) {
-            case 1: cv_w_epilogue<1>(lane, m, blk, acc, part, probs_row); break;
-            case 2: cv_w_epilogue<2>(lane, m, blk, acc, part, probs_row); break;
-            case 4: cv_w_epilogue<4>(lane, m, blk, acc, part, probs_row); break;
-            default: cv_w_epilogue<8>(lane, m, blk, acc, part, probs_row); break;
-            }
+            cv_w_spill(lane, *M.fx, acc);
+            __syncwarp();
+            cv_w_epilogue(lane, m, blk, min(CV_RB, m.n_rows - blk * CV_RB), *M.fx, part, probs_row);
+            __syncwarp();
         }
         /* warp reduction of the partial sums in a fixed order */
 #pragma unroll
@@ -168,17 +166,13 @@ static void cv_loglik_config(const CvModelDesc &m, int smem_max, int *n_warps, i
                              size_t *smem_bytes)
 {
     const size_t wb = cv_warp_bytes(m.n_err);
-    int rows = m.n_blocks * CV_RB;
-    size_t tab = (size_t)2 * rows * sizeof(double);
-    if (tab + 4 * wb > (size_t)smem_max) { /* huge histograms: row tables stay in global memory */
-        rows = 0;
-        tab = 0;
-    }
+    const int rows = m.n_blocks * CV_RB;
+    const size_t tab = (size_t)5 * rows * sizeof(double);
     long long w = ((long long)smem_max - (long long)tab) / (long long)wb;
     if (w > CV_WARPS_MAX)
         w = CV_WARPS_MAX;
     if (w < 1)
-        w = 1;
+        w = 0; /* the row tables do not fit next to one warp: the caller reports it */
     *n_warps = (int)w;
     *rows_staged = rows;
     *smem_bytes = tab + (size_t)w * wb;
@@ -199,8 +193,8 @@ cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const d
     int n_warps, rows_staged;
     size_t smem;
     cv_loglik_config(m, smem_max, &n_warps, &rows_staged, &smem);
-    if (smem > (size_t)smem_max)
-        return cudaErrorInvalidConfiguration;
+    if (n_warps < 1)
+        return cudaErrorInvalidConfiguration; /* ctx_create refuses such histograms */
     /* per device, and cheap: set on every launch */
     cudaError_t e = cudaFuncSetAttribute(cv_loglik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);

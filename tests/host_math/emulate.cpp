@@ -21,14 +21,6 @@ static void emu_fma(const CvWarpFixed &F, double *acc)
         cv_w_fma<NA>(lane, F, acc + 32 * lane);
 }
 
-template <int NA>
-static void emu_epilogue(const CvModelDesc &m, int blk, const double *acc, CvPartial *part,
-                         double *out_probs)
-{
-    for (int lane = 0; lane < 32; lane++)
-        cv_w_epilogue<NA>(lane, m, blk, acc + 32 * lane, part[lane], out_probs);
-}
-
 static void emulate_point(const CvModelDesc &m, const double *row_in, int clip, double *out_ll,
                           double *out_probs)
 {
@@ -37,6 +29,9 @@ static void emulate_point(const CvModelDesc &m, const double *row_in, int clip, 
     std::vector<double> var(cv_warp_var_doubles(S));
     CvWarpMem M;
     cv_warp_mem_carve(M, &fx, var.data(), S);
+    M.row_j0 = m.tab.row_j0;
+    M.row_head_h = m.tab.row_head_h;
+    M.row_head_l = m.tab.row_head_l;
     M.row_up = m.tab.row_up;
     M.row_dn = m.tab.row_dn;
     double row[CV_MAX_PARAMS] = {0, 0, 0, 0, 0};
@@ -89,12 +84,11 @@ static void emulate_point(const CvModelDesc &m, const double *row_in, int clip, 
             if (any)
                 break;
         }
-        switch (na) {
-        case 1: emu_epilogue<1>(m, blk, acc.data(), part, out_probs); break;
-        case 2: emu_epilogue<2>(m, blk, acc.data(), part, out_probs); break;
-        case 4: emu_epilogue<4>(m, blk, acc.data(), part, out_probs); break;
-        default: emu_epilogue<8>(m, blk, acc.data(), part, out_probs); break;
-        }
+        for (int lane = 0; lane < 32; lane++)
+            cv_w_spill(lane, fx, acc.data() + 32 * lane);
+        for (int lane = 0; lane < 32; lane++)
+            cv_w_epilogue(lane, m, blk, std::min(CV_RB, m.n_rows - blk * CV_RB), fx, part[lane],
+                          out_probs);
     }
     /* __shfl_down_sync tree: a lane whose source is out of range receives its own value */
     for (int d = 16; d >= 1; d >>= 1) {
