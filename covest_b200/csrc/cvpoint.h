@@ -14,13 +14,14 @@
  *     mass      n_os = comb[s] * (1.0 - exp(-o*l_s))                      (models.py:87, :221)
  *     terms     a_os = n_os / sum_s n_os, w = b(o) * a_os, log-domain constants of the term
  *     per half-tile of 16 terms:
- *       powers  PW[t][i] = lam_t^i, i = 0..15
+ *       powers  PW[i][t] = lam_t^i, i = 0..15
  *       seeds   SD[row][t] = scaled value of term t at the head bin of every 16-bin row of the
  *               current block of 64 rows: one exp() at the row holding the mode of the term, then
  *               the reference's own product recurrence (covest_poissonmodule.c:22-24) walked
  *               outwards 16 bins at a time
- *       fma     ACC[row][i] += SD[row][t] * PW[t][i]   -- one FP64 FMA per (term, bin); a lane
- *               owns 8 rows x 4 columns of the 64 x 16 block (32 accumulators in registers)
+ *       fma     ACC[row][i] += SD[row][t] * PW[i][t]   -- one FP64 FMA per (term, bin), issued as
+ *               m8n8k4 FP64 tensor-core MMAs: the 64 x 16 block is 8 x 2 MMA tiles, a lane holds
+ *               two accumulators of each (32 in registers)
  *   epilogue    p_j = ACC * slot_mult, mass += p_j, sum += h_j * log p_j  (models.py:100-107),
  *               straight from the accumulator registers
  *
@@ -33,11 +34,14 @@
 #define CV_RB 64       /* rows per block: 1024 bins */
 #define CV_HT 16       /* mixture terms per half-tile (powers / seeds / fma) */
 #define CV_CT 32       /* mixture terms per constant tile (terms phase: one per lane) */
-#define CV_SDS 18      /* row stride of the seed matrix SD[row][term]: 144 B, so that the 16-byte
-                          chunks of 8 consecutive rows fall into 8 different bank groups */
+#define CV_SDS 24      /* row stride of the seed matrix SD[row][term] and of the power matrix
+                          PW[column][term]: 192 B, so that the 16-byte chunks an 8-lane quarter
+                          warp reads for an MMA fragment (2 rows x 4 term pairs) fall into 8
+                          different bank groups */
+#define CV_PWS 24
 #define CV_SEGMAX 32   /* longest run of rows seeded from one exp() */
 #define CV_MAX_PARAMS 5
-#define CV_WARPS_MAX 16 /* warps (= points in flight) per CTA; one CTA per SM */
+#define CV_WARPS_MAX 12 /* warps (= points in flight) per CTA; one CTA per SM */
 
 /* Histogram-side tables of a context, all indexed by row / slot (slot = row * 16 + i).  Device
  * memory in the product, host memory in the emulation.  Built by cv_build_tables (cvtables.h). */
@@ -76,7 +80,7 @@ struct CvModelDesc {
  * device.  Compile-time offsets keep the hot phases free of address arithmetic. */
 struct CvWarpFixed {
     double SD[CV_RB * CV_SDS];  /* seeds of the current half-tile, [row][term] */
-    double PW[CV_HT * CV_W];    /* powers of the current half-tile, [term][i] */
+    double PW[CV_W * CV_PWS];   /* powers of the current half-tile, [column i][term] */
     double lam[CV_CT], lh[CV_CT], ll[CV_CT], lin[CV_CT], f[CV_CT]; /* constants of a tile of terms */
     double pw16[CV_HT], ipw16[CV_HT];                              /* lam^16 and its inverse */
     double par[CV_MAX_PARAMS];
@@ -259,7 +263,7 @@ CV_HD void cv_st2(double *p, double x, double y)
 }
 
 /* ---- per half-tile ------------------------------------------------------------------------ */
-/* PW[t][i] = lam_t^i, i < 16: lanes 2t and 2t+1 take the lower and the upper eight; every element
+/* PW[i][t] = lam_t^i, i < 16: lanes 2t and 2t+1 take the lower and the upper eight; every element
  * is at most three products of the squarings (the lower eight are multiplied by an exact 1.0 so
  * that the warp does not diverge).  Also lam^16 (kept by lane 2t) and 1 / lam^16 (lane 2t+1). */
 CV_HD void cv_w_powers(int lane, int half, CvWarpMem &M)
@@ -277,11 +281,15 @@ CV_HD void cv_w_powers(int lane, int half, CvWarpMem &M)
     double l16 = cv_mul(l8, l8);
     double inv16 = cv_div(1.0, l16);
     double base = up ? l8 : 1.0;
-    double *pw = F.PW + t * CV_W + up * 8;
-    cv_st2(pw + 0, base, cv_mul(base, lam));
-    cv_st2(pw + 2, cv_mul(base, l2), cv_mul(base, l3));
-    cv_st2(pw + 4, cv_mul(base, l4), cv_mul(base, l5));
-    cv_st2(pw + 6, cv_mul(base, l6), cv_mul(base, l7));
+    double *pw = F.PW + up * 8 * CV_PWS + t; /* column 8 up + i of term t */
+    pw[0 * CV_PWS] = base;
+    pw[1 * CV_PWS] = cv_mul(base, lam);
+    pw[2 * CV_PWS] = cv_mul(base, l2);
+    pw[3 * CV_PWS] = cv_mul(base, l3);
+    pw[4 * CV_PWS] = cv_mul(base, l4);
+    pw[5 * CV_PWS] = cv_mul(base, l5);
+    pw[6 * CV_PWS] = cv_mul(base, l6);
+    pw[7 * CV_PWS] = cv_mul(base, l7);
     if (up)
         F.ipw16[t] = inv16;
     else
@@ -373,49 +381,74 @@ CV_HD void cv_w_seeds(int lane, const CvModelDesc &m, int blk, int half, CvWarpM
     }
 }
 
-/* The accumulators of a lane: rows rg + 8a (a < 8), columns 4cg + c (c < 4) of the block, with
- * rg = lane >> 2, cg = lane & 3; acc[4a + c].  NA = number of live 8-row groups of the block. */
+/* One m8n8k4 FP64 MMA: D = A (8 x 4, row) * B (4 x 8, col) + D.  Lane l holds A[l >> 2][l & 3],
+ * B[l & 3][l >> 2] and D[l >> 2][2 (l & 3) + {0, 1}]. */
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void cv_dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+#endif
+
+/* The accumulators of a lane: MMA tile (mt, nt), mt < 8 row tiles, nt < 2 column tiles, holds rows
+ * 8 mt + r and columns 8 nt + 2 q + {0, 1} with r = lane >> 2, q = lane & 3; acc[4 mt + 2 nt + {0, 1}].
+ * The 16 terms of the half-tile are contracted 4 at a time; lane q supplies the terms 2q and 2q+1 of
+ * each group of 8 (one 16-byte read) to two consecutive MMAs.  NA = number of live row tiles.
+ * On the host (test emulation) the same sums are formed with scalar FMAs in the same term order. */
 template <int NA>
 CV_HD void cv_w_fma(int lane, const CvWarpFixed &F, double *acc)
 {
-    int rg = lane >> 2, cg = lane & 3;
-    const double *sd = F.SD + rg * CV_SDS;
-    const double *pw = F.PW + cg * 4;
-    cv_pair s = cv_ld2(sd); /* terms t and t+1 of row rg + 8a; always loaded one step ahead */
-#pragma unroll 1
-    for (int t = 0; t < CV_HT; t += 2) {
-        cv_pair b0l = cv_ld2(pw + t * CV_W), b0h = cv_ld2(pw + t * CV_W + 2);
-        cv_pair b1l = cv_ld2(pw + (t + 1) * CV_W), b1h = cv_ld2(pw + (t + 1) * CV_W + 2);
+    const int r = lane >> 2, q = lane & 3;
+#if defined(__CUDA_ARCH__)
+    const double *sd = F.SD + r * CV_SDS + 2 * q;
+    const double *pw = F.PW + r * CV_PWS + 2 * q;
 #pragma unroll
-        for (int a = 0; a < NA; a++) {
-            /* after the last row group: the first row group of the next pair (the last pair
-             * wraps around to a harmless reload) */
-            cv_pair nx = (a + 1 < NA) ? cv_ld2(sd + (a + 1) * 8 * CV_SDS + t)
-                                      : cv_ld2(sd + ((t + 2) & (CV_HT - 1)));
-            acc[4 * a + 0] = cv_fma(s.x, b0l.x, acc[4 * a + 0]);
-            acc[4 * a + 1] = cv_fma(s.x, b0l.y, acc[4 * a + 1]);
-            acc[4 * a + 2] = cv_fma(s.x, b0h.x, acc[4 * a + 2]);
-            acc[4 * a + 3] = cv_fma(s.x, b0h.y, acc[4 * a + 3]);
-            acc[4 * a + 0] = cv_fma(s.y, b1l.x, acc[4 * a + 0]);
-            acc[4 * a + 1] = cv_fma(s.y, b1l.y, acc[4 * a + 1]);
-            acc[4 * a + 2] = cv_fma(s.y, b1h.x, acc[4 * a + 2]);
-            acc[4 * a + 3] = cv_fma(s.y, b1h.y, acc[4 * a + 3]);
-            s = nx;
+    for (int k0 = 0; k0 < CV_HT; k0 += 8) {
+        cv_pair b0 = cv_ld2(pw + k0), b1 = cv_ld2(pw + 8 * CV_PWS + k0);
+#pragma unroll
+        for (int mt = 0; mt < NA; mt++) {
+            cv_pair a = cv_ld2(sd + mt * 8 * CV_SDS + k0);
+            cv_dmma(acc[4 * mt + 0], acc[4 * mt + 1], a.x, b0.x);
+            cv_dmma(acc[4 * mt + 2], acc[4 * mt + 3], a.x, b1.x);
+            cv_dmma(acc[4 * mt + 0], acc[4 * mt + 1], a.y, b0.y);
+            cv_dmma(acc[4 * mt + 2], acc[4 * mt + 3], a.y, b1.y);
         }
     }
+#else
+    for (int k0 = 0; k0 < CV_HT; k0 += 8)
+        for (int mt = 0; mt < NA; mt++)
+            for (int par = 0; par < 2; par++)     /* the .x terms, then the .y terms */
+                for (int nt = 0; nt < 2; nt++)
+                    for (int c = 0; c < 2; c++) {
+                        const double *srow = F.SD + (8 * mt + r) * CV_SDS + k0 + par;
+                        const double *pcol = F.PW + (8 * nt + 2 * q + c) * CV_PWS + k0 + par;
+                        double v = acc[4 * mt + 2 * nt + c];
+                        for (int kk = 0; kk < 4; kk++)
+                            v = cv_fma(srow[2 * kk], pcol[2 * kk], v);
+                        acc[4 * mt + 2 * nt + c] = v;
+                    }
+#endif
 }
 
 /* The accumulators of a lane go to the seed matrix (free after the last fma of a block) in slot
- * order, slot = row * 16 + column. */
+ * order, slot = row * 16 + column; the 16-byte chunks of odd rows are swapped between the halves of
+ * the row so that a quarter warp (2 rows x 4 chunks) does not collide. */
+CV_HD int cv_spill_index(int slot)
+{
+    return slot ^ ((slot & CV_W) >> 1); /* column ^= 8 on odd rows */
+}
 CV_HD void cv_w_spill(int lane, CvWarpFixed &F, const double *acc)
 {
-    int rg = lane >> 2, cg = lane & 3;
+    const int r = lane >> 2, q = lane & 3;
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-        double *dst = F.SD + (rg + 8 * a) * CV_W + 4 * cg;
-        cv_st2(dst, acc[4 * a + 0], acc[4 * a + 1]);
-        cv_st2(dst + 2, acc[4 * a + 2], acc[4 * a + 3]);
-    }
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+            int slot = (8 * mt + r) * CV_W + 8 * nt + 2 * q;
+            cv_st2(F.SD + cv_spill_index(slot), acc[4 * mt + 2 * nt], acc[4 * mt + 2 * nt + 1]);
+        }
 }
 
 CV_HD void cv_partial_add_mass(CvPartial &p, double x)
@@ -456,7 +489,7 @@ CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, int nrows_blk,
         double mu = mult[e];
         if (mu == 0.0)
             continue; /* a bin that is not in hist */
-        double p = cv_mul(F.SD[e], mu);
+        double p = cv_mul(F.SD[cv_spill_index(e)], mu);
         if (out_probs)
             out_probs[bin[e]] = p;
         cv_partial_add_mass(part, p);
