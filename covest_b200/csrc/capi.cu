@@ -572,7 +572,7 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
 /* ---- roofline probe ----------------------------------------------------------------------- */
 extern "C" int cvb_fp64_peak(cvb_ctx *ctx, int kind, int reps, double *out_tflops)
 {
-    if (!ctx || !out_tflops || (kind != 0 && kind != 1))
+    if (!ctx || !out_tflops || (kind < 0 || kind > 2))
         return ctx ? fail(ctx, CVB_EINVAL, "bad arguments to cvb_fp64_peak") : CVB_EINVAL;
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     cudaEvent_t a, b;

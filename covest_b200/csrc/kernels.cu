@@ -14,6 +14,8 @@
  */
 #include "kernels.h"
 
+#include <cstdlib>
+
 #define CV_FULL_MASK 0xffffffffu
 
 __device__ __forceinline__ void cv_lattice_point(const CvLattice &lat, long long i, double *row)
@@ -171,6 +173,9 @@ static void cv_loglik_config(const CvModelDesc &m, int smem_max, int *n_warps, i
     long long w = ((long long)smem_max - (long long)tab) / (long long)wb;
     if (w > CV_WARPS_MAX)
         w = CV_WARPS_MAX;
+    if (const char *cap = getenv("COVEST_B200_WARPS")) /* development: occupancy experiments */
+        if (atoi(cap) >= 1 && atoi(cap) < w)
+            w = atoi(cap);
     if (w < 1)
         w = 0; /* the row tables do not fit next to one warp: the caller reports it */
     *n_warps = (int)w;
@@ -398,16 +403,59 @@ __global__ void __launch_bounds__(256) cv_peak_probe_dmma(int iters, double *sin
         sink[0] = s;
 }
 
+/* Even warps run the DMMA chain, odd warps the DFMA chain: do the two share execution units? */
+__global__ void __launch_bounds__(256) cv_peak_probe_mixed(int iters, double *sink)
+{
+    double s = 0.0;
+    if ((threadIdx.x >> 5) & 1) {
+        double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * blockIdx.x;
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            x[i] = 0.1 + 0.05 * i;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    x[j] = __fma_rn(x[j], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            s += x[i];
+    } else {
+        double a = 1e-3 * (threadIdx.x & 7), b = 1e-3 * (threadIdx.x & 3);
+        double c[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            c[i] = 0.0;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                cv_dmma_m8n8k4(c[2 * u], c[2 * u + 1], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            s += c[i];
+    }
+    if (s == 12345.678)
+        sink[0] = s;
+}
+
 cudaError_t cv_launch_peak_probe(int kind, int n_cta, int iters, double *sink, double *flop,
                                  cudaStream_t stream)
 {
     if (kind == 0) {
         cv_peak_probe_dfma<<<n_cta, 256, 0, stream>>>(iters, sink);
         *flop = 2.0 * 16.0 * 8.0 * (double)iters * 256.0 * (double)n_cta;
-    } else {
+    } else if (kind == 1) {
         cv_peak_probe_dmma<<<n_cta, 256, 0, stream>>>(iters, sink);
         /* one m8n8k4 = 8*8*4 FMA per warp */
         *flop = 2.0 * 256.0 * 8.0 * (double)iters * 8.0 * (double)n_cta;
+    } else {
+        /* four DFMA warps (16 x 8 FMA per thread and iteration) + four DMMA warps (8 MMAs) */
+        cv_peak_probe_mixed<<<n_cta, 256, 0, stream>>>(iters, sink);
+        *flop = (2.0 * 16.0 * 8.0 * 128.0 + 2.0 * 256.0 * 8.0 * 4.0) * (double)iters * (double)n_cta;
     }
     return cudaGetLastError();
 }

@@ -196,7 +196,8 @@ class LikelihoodContext:
 
     # -- measurement -----------------------------------------------------------------------
     def fp64_peak(self, kind=0, reps=5):
-        """Measured FP64 throughput (TFLOP/s) of register-resident DFMA (0) / DMMA (1) chains."""
+        """Measured FP64 throughput (TFLOP/s) of register-resident DFMA (0) / DMMA (1) chains, or of
+        both running side by side (2)."""
         out = ctypes.c_double()
         self._check(self._lib.cvb_fp64_peak(self._ctx, int(kind), int(reps), ctypes.byref(out)),
                     'cvb_fp64_peak')

@@ -105,7 +105,8 @@ CVB_API int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double
                      double *out_rows, void *stream);
 
 /* Measures the FP64 roofline denominator on the context's device: kind 0 = dependent-free DFMA
- * chains, kind 1 = DMMA m8n8k4 chains, both register resident.  *out_tflops = best of `reps`. */
+ * chains, kind 1 = DMMA m8n8k4 chains, kind 2 = both at once (half of the warps each), all register
+ * resident.  *out_tflops = best of `reps`. */
 CVB_API int cvb_fp64_peak(cvb_ctx *ctx, int kind, int reps, double *out_tflops);
 
 /* Device time (ms, CUDA events on the launch stream) of the dominant kernel of the most recent
