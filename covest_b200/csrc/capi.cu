@@ -191,7 +191,8 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
     m.n_err = max_error;
     m.n_param = model_kind ? 5 : 2;
     m.n_bins = n_bins;
-    m.n_rows = T.n_rows;
+    m.n_groups = T.n_groups;
+    m.na = T.na;
     m.n_blocks = T.n_blocks;
     m.max_bin = T.max_bin;
     m.tail = tail;
@@ -228,19 +229,19 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess)
             break;
         CvTables &t = m.tab;
-        if ((e = upload(c, T.row_j0, &t.row_j0)) != cudaSuccess) break;
-        if ((e = upload(c, T.row_head_h, &t.row_head_h)) != cudaSuccess) break;
-        if ((e = upload(c, T.row_head_l, &t.row_head_l)) != cudaSuccess) break;
-        if ((e = upload(c, T.row_up, &t.row_up)) != cudaSuccess) break;
-        if ((e = upload(c, T.row_dn, &t.row_dn)) != cudaSuccess) break;
+        if (cv_loglik_smem_bytes(m, c->smem_max) < 0) {
+            rc = fail(nullptr, CVB_EINVAL, "histogram too long: its group tables do not fit the shared memory of an SM");
+            break;
+        }
+        if ((e = upload(c, T.grp, &t.grp)) != cudaSuccess) break;
         if ((e = upload(c, T.slot_mult, &t.slot_mult)) != cudaSuccess) break;
         if ((e = upload(c, T.slot_h, &t.slot_h)) != cudaSuccess) break;
         if ((e = upload(c, T.slot_bin, &t.slot_bin)) != cudaSuccess) break;
         if ((e = upload(c, T.copy_log_h, &t.copy_log_h)) != cudaSuccess) break;
         if ((e = upload(c, T.copy_log_l, &t.copy_log_l)) != cudaSuccess) break;
-        if ((e = upload(c, T.seg_first, &t.seg_first)) != cudaSuccess) break;
-        if ((e = upload(c, T.seg_len, &t.seg_len)) != cudaSuccess) break;
-        if ((e = upload(c, T.blk_seg_begin, &t.blk_seg_begin)) != cudaSuccess) break;
+        if ((e = upload(c, T.run_first, &t.run_first)) != cudaSuccess) break;
+        if ((e = upload(c, T.run_len, &t.run_len)) != cudaSuccess) break;
+        if ((e = upload(c, T.blk_run_begin, &t.blk_run_begin)) != cudaSuccess) break;
         if ((e = cudaMalloc((void **)&c->d_counter, sizeof(unsigned long long))) != cudaSuccess) break;
         if ((e = cudaMalloc((void **)&c->d_sink, 64)) != cudaSuccess) break;
     } while (0);

@@ -2,63 +2,67 @@
  * cvpoint.h -- the per-point evaluation of the CovEst mixture likelihood, written as a sequence
  * of warp-wide *phases*.  Inside the sm_100a kernel (kernels.cu) ONE WARP evaluates one parameter
  * point at a time: its 32 lanes call each phase with their own `lane`, the phases are separated by
- * __syncwarp(), and nothing is shared between the warps of a CTA except read-only row tables.  The
- * test-only host emulation (tests/host_math/emulate.cpp) calls the same functions in a serial loop
- * over `lane`, phase by phase, which is the same computation.  No phase uses warp intrinsics.
+ * __syncwarp(), and nothing is shared between the warps of a CTA except read-only group tables.
+ * The test-only host emulation (tests/host_math/emulate.cpp) calls the same functions in a serial
+ * loop over `lane`, phase by phase, which is the same computation.
  *
  *   header      clip the parameters (models.py:60-69), error-class rates l_s (models.py:71-79),
  *               the constants of the copy-number weights (models.py:193-208)
  *   per pass of 32 copy numbers o: the weights b(o), one per lane, and the cut-off O_thr
  *               (models.py:185-191) -- the weights stay in registers and reach the terms by shuffle
- *   per group of up to 32 mixture terms (o, s)  [64 when there are more than 32 error classes]:
+ *   per tile of up to 32 mixture terms (o, s), ONE TERM PER LANE:
  *     mass      n_os = comb[s] * (1.0 - exp(-o*l_s))                      (models.py:87, :221)
- *     terms     a_os = n_os / sum_s n_os, w = b(o) * a_os, log-domain constants of the term
- *     per half-tile of 16 terms:
- *       powers  PW[i][t] = lam_t^i, i = 0..15
- *       seeds   SD[row][t] = scaled value of term t at the head bin of every 16-bin row of the
- *               current block of 64 rows: one exp() at the row holding the mode of the term, then
- *               the reference's own product recurrence (covest_poissonmodule.c:22-24) walked
- *               outwards 16 bins at a time
- *       fma     ACC[row][i] += SD[row][t] * PW[i][t]   -- one FP64 FMA per (term, bin), issued as
- *               m8n8k4 FP64 tensor-core MMAs: the 64 x 16 block is 8 x 2 MMA tiles, a lane holds
- *               two accumulators of each (32 in registers)
- *   epilogue    p_j = ACC * slot_mult, mass += p_j, sum += h_j * log p_j  (models.py:100-107),
- *               straight from the accumulator registers
+ *     prep      a_os = n_os / sum_s n_os, w = b(o) * a_os, the log-domain constants of the term;
+ *               its powers PW[i] = lam^i, i < 16; its *anchors*: the scaled value of the term at the
+ *               first bin of every group of NA rows (16 NA bins) of the current block -- one exp()
+ *               per run of up to four groups, at the anchor next to the mode of the term, then the
+ *               reference's own product recurrence (covest_poissonmodule.c:22-24) walked outwards
+ *               one group at a time
+ *     fused     lane (r, q) = (lane / 4, lane % 4) owns group r of the block: for each of the 4-term
+ *               slices of the tile it extends the anchor of term q of the slice over the NA rows of
+ *               its group with one multiplication per row -- which is exactly its A fragment of
+ *               an m8n8k4 FP64 tensor-core MMA -- and issues
+ *                   ACC[row][i] += A[row][t] * PW[i][t]      one FP64 FMA per (term, bin)
+ *               for the 8 NA x 16 block (NA x 2 MMA tiles, 4 NA accumulators per lane)
+ *   epilogue    p_j = ACC * slot_mult, mass += p_j, sum += h_j * log p_j  (models.py:100-107)
  *
  * Reference lines are relative to /root/reference.
  */
 #pragma once
 #include "cvmodel.h"
 
-#define CV_W 16        /* bins per row (chain) */
-#define CV_RB 64       /* rows per block: 1024 bins */
-#define CV_HT 16       /* mixture terms per half-tile (powers / seeds / fma) */
-#define CV_CT 32       /* mixture terms per constant tile (terms phase: one per lane) */
-#define CV_SDS 24      /* row stride of the seed matrix SD[row][term] and of the power matrix
-                          PW[column][term]: 192 B, so that the 16-byte chunks an 8-lane quarter
-                          warp reads for an MMA fragment (2 rows x 4 term pairs) fall into 8
-                          different bank groups */
-#define CV_PWS 24
-#define CV_SEGMAX 32   /* longest run of rows seeded from one exp() */
+#define CV_W 16        /* bins per row */
+#define CV_GB 8        /* groups per block (one per MMA row index) */
+#define CV_NA_MAX 8    /* rows per group: 1, 2, 4 (histograms of up to 8, 16, 32 rows) or 8 */
+#define CV_CT 32       /* mixture terms per tile: one per lane */
+#define CV_RUNMAX 4    /* longest run of groups anchored from one exp() */
 #define CV_MAX_PARAMS 5
 #define CV_WARPS_MAX 12 /* warps (= points in flight) per CTA; one CTA per SM */
 
-/* Histogram-side tables of a context, all indexed by row / slot (slot = row * 16 + i).  Device
- * memory in the product, host memory in the emulation.  Built by cv_build_tables (cvtables.h). */
+/* record of a group in CvTables::grp */
+#define CV_GD 16       /* doubles per record */
+#define CV_G_J0 0      /* first bin of the group */
+#define CV_G_HEAD 1    /* CV_SCALE_LOG - lgamma(j0 + 1), double-double (2) */
+#define CV_G_EHEAD 3   /* the same at the bin after the group, j0 + 16 NA (2) */
+#define CV_G_CINV 5    /* c^-16, c = geometric mean of the bins of the group: the chain normaliser */
+#define CV_G_C16 6     /* its inverse */
+#define CV_G_ENORM 7   /* takes the value at the bin after the group to the chain's scale */
+#define CV_G_UP 8      /* (4) factorial ratios of the sub-steps of an anchor step, walking up */
+#define CV_G_DN 12     /* (4) and walking down */
+
+/* Histogram-side tables of a context.  Device memory in the product, host memory in the
+ * emulation.  Built by cv_build_tables (cvtables.h).  slot = (group * NA + row) * 16 + column. */
 struct CvTables {
-    const double *row_j0;      /* head bin of the row */
-    const double *row_head_h;  /* CV_SCALE_LOG - lgamma(j0 + 1), double-double */
-    const double *row_head_l;
-    const double *row_up;      /* j0[r-1]! / j0[r]!   (row r continues row r-1) */
-    const double *row_dn;      /* j0[r+1]! / j0[r]!   (row r+1 continues row r) */
-    const double *slot_mult;   /* exp(-CV_SCALE_LOG) * j0! / (j0+i)!; 0 marks a slot not in hist */
+    const double *grp;         /* CV_GD doubles per group */
+    const double *slot_mult;   /* exp(-CV_SCALE_LOG) * (chain scale of the row) * j0! / (j0+i)!;
+                                  0 marks a slot that is not in hist */
     const double *slot_h;      /* count h_j */
     const int *slot_bin;       /* position of the bin in the caller's hist order, -1 = padding */
     const double *copy_log_h;  /* log(o), o = 0..max_bin, as a double-double (entry 0 unused) */
     const double *copy_log_l;
-    const int *seg_first;      /* segments: runs of consecutive rows inside one block */
-    const int *seg_len;
-    const int *blk_seg_begin;  /* [n_blocks + 1] */
+    const int *run_first;      /* runs: consecutive groups inside one block, at most CV_RUNMAX */
+    const int *run_len;
+    const int *blk_run_begin;  /* [n_blocks + 1] */
 };
 
 struct CvModelDesc {
@@ -66,7 +70,8 @@ struct CvModelDesc {
     int k, r;
     int n_err;      /* max_error (models.py:28-31) */
     int n_param;
-    int n_bins, n_rows, n_blocks;
+    int n_bins, n_groups, n_blocks;
+    int na;         /* rows per group */
     int max_bin;    /* max(hist), models.py:186 */
     double tail;
     double threshold; /* NaN = None */
@@ -77,26 +82,32 @@ struct CvModelDesc {
 };
 
 /* Fixed-size part of the working set of one warp (= one point in flight); shared memory on the
- * device.  Compile-time offsets keep the hot phases free of address arithmetic. */
+ * device.  PW and ANC hold one 16-byte chunk per (term, group index / column pair); the chunk of
+ * (t, g) sits at position (g + 2 t) & 7 of the 128 bytes of term t, so that the 8 lanes that read
+ * together (2 groups x 4 terms) touch 8 different bank groups. */
 struct CvWarpFixed {
-    double SD[CV_RB * CV_SDS];  /* seeds of the current half-tile, [row][term] */
-    double PW[CV_W * CV_PWS];   /* powers of the current half-tile, [column i][term] */
-    double lam[CV_CT], lh[CV_CT], ll[CV_CT], lin[CV_CT], f[CV_CT]; /* constants of a tile of terms */
-    double pw16[CV_HT], ipw16[CV_HT];                              /* lam^16 and its inverse */
+    union {
+        struct {
+            double PW[CV_CT * 16];  /* chunk (t, i), i < 8: {lam^i, lam^(8+i)} */
+            double ANC[CV_CT * 16]; /* chunk (t, g), g < 8: value of the term at the first bin of
+                                       group g, and at the bin after the group */
+        } t;
+        double spill[CV_GB * CV_NA_MAX * CV_W]; /* the accumulators on their way to the epilogue */
+    } u;
+    double PWR[CV_CT * 2]; /* {lam^16, lam^-16} */
     double par[CV_MAX_PARAMS];
     double two, many, base; /* (1-q1)*q2, (1-q1)*(1-q2)*q, 1-q */
 };
 
 /* The working set of a warp: the fixed part, the arrays whose length depends on the number of
- * error classes, and the row tables every warp of the CTA reads. */
+ * error classes, and the group tables every warp of the CTA reads. */
 struct CvWarpMem {
     CvWarpFixed *fx;
     double *ls;            /* [S] l_s */
     double *lls_h, *lls_l; /* [S] log(l_s), double-double */
     double *nmass;         /* [group terms] n_os */
     double *glam;          /* [group terms] o * l_s */
-    /* the row tables of CvTables every warp of the CTA reads (staged in shared memory) */
-    const double *row_j0, *row_head_h, *row_head_l, *row_up, *row_dn;
+    const double *grp;     /* CvTables::grp, staged in shared memory */
 };
 
 /* terms of the largest group: whole copies, at most 32 terms unless one copy alone has more */
@@ -117,7 +128,7 @@ CV_HD void cv_warp_mem_carve(CvWarpMem &M, CvWarpFixed *fx, double *var, int n_e
 }
 
 struct CvPartial {
-    double sum_h, sum_l;   /* sum_j h_j log p_j, compensated */
+    double sum;            /* sum_j h_j log p_j */
     double mass_h, mass_l; /* sum_j p_j, compensated */
 };
 
@@ -182,7 +193,7 @@ CV_HD bool cv_w_copy_pass(int lane, const CvModelDesc &m, const CvWarpMem &M, in
     return w <= m.threshold;
 }
 
-/* ---- per group ---------------------------------------------------------------------------- */
+/* ---- per group of copies ------------------------------------------------------------------ */
 /* models.py:87 / :221.  Term t of the group is copy o = group_o + t / S, error class s = t % S. */
 CV_HD void cv_w_mass(int lane, const CvModelDesc &m, int group_o, int nterms, CvWarpMem &M)
 {
@@ -197,18 +208,13 @@ CV_HD void cv_w_mass(int lane, const CvModelDesc &m, int group_o, int nterms, Cv
 
 /* Constants of the term t = sub + lane of the group (a dead term when t >= nterms); `b` is the
  * weight b(o) of the copy this lane's term belongs to. */
-CV_HD void cv_w_terms(int lane, const CvModelDesc &m, int group_o, int nterms, int sub, double b,
-                      CvWarpMem &M)
+CV_HD CvTerm cv_w_term(int lane, const CvModelDesc &m, int group_o, int nterms, int sub, double b,
+                       const CvWarpMem &M)
 {
-    CvWarpFixed &F = *M.fx;
     int t = sub + lane;
     if (t >= nterms) { /* padding of the last tile: contributes exactly 0 */
-        F.lam[lane] = 1.0;
-        F.lh[lane] = 0.0;
-        F.ll[lane] = 0.0;
-        F.lin[lane] = 0.0;
-        F.f[lane] = 0.0;
-        return;
+        CvTerm dead = {1.0, 0.0, 0.0, 0.0, 0.0};
+        return dead;
     }
     int S = m.n_err;
     int g = t / S, s = t - g * S;
@@ -229,12 +235,7 @@ CV_HD void cv_w_terms(int lane, const CvModelDesc &m, int group_o, int nterms, i
     cv_dd lg = cv_dd_add(lo_, ll_);
     if (resid != 0.0)
         lg = cv_dd_add_d(lg, -cv_div(resid, lam));
-    CvTerm tm = cv_term_make(lam, cv_mul(b, M.nmass[t]), total, lg.hi, lg.lo);
-    F.lam[lane] = tm.lam;
-    F.lh[lane] = tm.lh;
-    F.ll[lane] = tm.ll;
-    F.lin[lane] = tm.lin;
-    F.f[lane] = tm.f;
+    return cv_term_make(lam, cv_mul(b, M.nmass[t]), total, lg.hi, lg.lo);
 }
 
 /* two adjacent doubles, one 16-byte access on the device */
@@ -262,120 +263,109 @@ CV_HD void cv_st2(double *p, double x, double y)
 #endif
 }
 
-/* ---- per half-tile ------------------------------------------------------------------------ */
-/* PW[i][t] = lam_t^i, i < 16: lanes 2t and 2t+1 take the lower and the upper eight; every element
- * is at most three products of the squarings (the lower eight are multiplied by an exact 1.0 so
- * that the warp does not diverge).  Also lam^16 (kept by lane 2t) and 1 / lam^16 (lane 2t+1). */
-CV_HD void cv_w_powers(int lane, int half, CvWarpMem &M)
-{
-    CvWarpFixed &F = *M.fx;
-    int t = lane >> 1, up = lane & 1;
-    double lam = F.lam[half * CV_HT + t];
-    double l2 = cv_mul(lam, lam);
-    double l4 = cv_mul(l2, l2);
-    double l8 = cv_mul(l4, l4);
-    double l3 = cv_mul(l2, lam);
-    double l5 = cv_mul(l4, lam);
-    double l6 = cv_mul(l4, l2);
-    double l7 = cv_mul(l4, l3);
-    double l16 = cv_mul(l8, l8);
-    double inv16 = cv_div(1.0, l16);
-    double base = up ? l8 : 1.0;
-    double *pw = F.PW + up * 8 * CV_PWS + t; /* column 8 up + i of term t */
-    pw[0 * CV_PWS] = base;
-    pw[1 * CV_PWS] = cv_mul(base, lam);
-    pw[2 * CV_PWS] = cv_mul(base, l2);
-    pw[3 * CV_PWS] = cv_mul(base, l3);
-    pw[4 * CV_PWS] = cv_mul(base, l4);
-    pw[5 * CV_PWS] = cv_mul(base, l5);
-    pw[6 * CV_PWS] = cv_mul(base, l6);
-    pw[7 * CV_PWS] = cv_mul(base, l7);
-    if (up)
-        F.ipw16[t] = inv16;
-    else
-        F.pw16[t] = l16;
-}
+/* position (in doubles) of chunk (t, g) inside PW / ANC */
+CV_HD int cv_chunk(int t, int g) { return (t * 8 + ((g + 2 * t) & 7)) * 2; }
 
-/* Seeds of every (term, row) of block `blk`.  A work item is (term, segment): one exp() at one row
- * of the segment, then the product recurrence walked over the other rows, one multiplication deep
- * per row because the factor lam^+-16 * (factorial ratio) does not depend on the running value.
- * Where the walk starts:
- *   - mode of the term (j ~ lam) at or above the top row: at the top row, walking down;
- *   - otherwise at the bottom row, walking up through the mode, when the value there is well inside
- *     the double range (it always is unless the weight of the term is minute);
- *   - otherwise at the row holding the mode, walking up and then down, so that a value that
+/* ---- prep: powers and anchors of the lane's term ------------------------------------------- */
+/* An anchor step (16 NA bins) is taken as NSUB sub-steps of 32 bins (16 when NA = 1), each the
+ * product lam^32 * (factorial ratio): every factor stays far inside the double range for any rate
+ * the model can produce.
+ *
+ * Where the walk over the n + 1 anchors of a run starts:
+ *   - mode of the term (j ~ lam) at or above the last anchor: there, walking down;
+ *   - otherwise at the first anchor, walking up through the mode, when the value there is well
+ *     inside the double range (it always is unless the weight of the term is minute);
+ *   - otherwise at the anchor below the mode, walking up and then down, so that a value that
  *     underflowed never has to grow back.
  * The first two cases share one loop with a per-lane direction, so lanes do not diverge. */
-CV_HD void cv_w_seeds(int lane, const CvModelDesc &m, int blk, int half, CvWarpMem &M)
+template <int NA>
+CV_HD void cv_w_prep(int lane, const CvModelDesc &m, int blk, const CvTerm &tm, CvWarpMem &M)
 {
+    constexpr int NSUB = NA >= 2 ? NA / 2 : 1;
+    constexpr double INV_SPAN = 1.0 / (CV_W * NA);
     CvWarpFixed &F = *M.fx;
     const CvTables &T = m.tab;
-    const int sb = T.blk_seg_begin[blk];
-    const int items = (T.blk_seg_begin[blk + 1] - sb) * CV_HT;
-    for (int it = lane; it < items; it += 32) {
-        const int t = it & (CV_HT - 1), sg = sb + (it >> 4);
-        const int ct = half * CV_HT + t;
-        const int first = T.seg_first[sg], top = T.seg_len[sg] - 1;
-        const int grow = blk * CV_RB + first;
-        const double lam = F.lam[ct], lh = F.lh[ct], lin = F.lin[ct], f = F.f[ct];
-        const double j0 = M.row_j0[grow];
-        const double off = (lam - j0) * (1.0 / CV_W);
-        /* exponent of the scaled term at the bottom row, to a few ulps */
-        const double e0 = cv_sub(cv_fma(j0, lh, M.row_head_h[grow]), lin);
+    const double lam = tm.lam, lh = tm.lh, lin = tm.lin, f = tm.f;
+    const double l2 = cv_mul(lam, lam);
+    const double l3 = cv_mul(l2, lam);
+    const double l4 = cv_mul(l2, l2);
+    const double l5 = cv_mul(l4, lam);
+    const double l6 = cv_mul(l4, l2);
+    const double l7 = cv_mul(l4, l3);
+    const double l8 = cv_mul(l4, l4);
+    const double l16 = cv_mul(l8, l8);
+    const double inv16 = cv_div(1.0, l16);
+    {
+        double *pw = F.u.t.PW;
+        cv_st2(pw + cv_chunk(lane, 0), 1.0, l8);
+        cv_st2(pw + cv_chunk(lane, 1), lam, cv_mul(l8, lam));
+        cv_st2(pw + cv_chunk(lane, 2), l2, cv_mul(l8, l2));
+        cv_st2(pw + cv_chunk(lane, 3), l3, cv_mul(l8, l3));
+        cv_st2(pw + cv_chunk(lane, 4), l4, cv_mul(l8, l4));
+        cv_st2(pw + cv_chunk(lane, 5), l5, cv_mul(l8, l5));
+        cv_st2(pw + cv_chunk(lane, 6), l6, cv_mul(l8, l6));
+        cv_st2(pw + cv_chunk(lane, 7), l7, cv_mul(l8, l7));
+        cv_st2(F.PWR + 2 * lane, l16, inv16);
+    }
+    const double step_up = NA >= 2 ? cv_mul(l16, l16) : l16;
+    const double step_dn = NA >= 2 ? cv_mul(inv16, inv16) : inv16;
+    double *anc = F.u.t.ANC;
+    const int rb = T.blk_run_begin[blk], re = T.blk_run_begin[blk + 1];
+    for (int run = rb; run < re; run++) {
+        const int first = T.run_first[run], n = T.run_len[run];
+        const double *g0 = M.grp + (size_t)(blk * CV_GB + first) * CV_GD;
+        const double j0 = g0[CV_G_J0];
+        const double off = cv_mul(cv_sub(lam, j0), INV_SPAN);
+        /* exponent of the scaled term at the first anchor, to a few ulps */
+        const double e0 = cv_sub(cv_fma(j0, lh, g0[CV_G_HEAD]), lin);
         int rs;
-        if (off >= (double)top)
-            rs = top;
+        if (off >= (double)n)
+            rs = n;
         else if (e0 > -460.0 && !(f < 0x1p-200))
             rs = 0;
         else
             rs = off > 0.0 ? (int)off : 0;
-        const double seed = cv_seed(M.row_j0[grow + rs], M.row_head_h[grow + rs], M.row_head_l[grow + rs],
-                                    lh, F.ll[ct], lin, f);
-        double *col = F.SD + first * CV_SDS + t;
-        col[rs * CV_SDS] = seed;
-        const bool down = rs == top;
-        const double step_dn = F.ipw16[t];
+        const bool down = rs == n;
         {
-            const int n1 = down ? top : top - rs;
-            const int dt = down ? -1 : 1;
-            const double *tp = (down ? M.row_dn : M.row_up) + grow + rs + dt;
-            double *sp = col + (rs + dt) * CV_SDS;
-            const double step = down ? step_dn : F.pw16[t];
+            const double *ga = g0 + (down ? n - 1 : rs) * CV_GD;
+            const double ja = down ? cv_add(ga[CV_G_J0], (double)(CV_W * NA)) : ga[CV_G_J0];
+            const double hh = ga[down ? CV_G_EHEAD : CV_G_HEAD];
+            const double hl = ga[down ? CV_G_EHEAD + 1 : CV_G_HEAD + 1];
+            const double seed = cv_seed(ja, hh, hl, lh, tm.ll, lin, f);
+            if (rs < n)
+                anc[cv_chunk(lane, first + rs)] = seed;
+            if (rs > 0)
+                anc[cv_chunk(lane, first + rs - 1) + 1] = seed;
             double v = seed;
-            int k = 0;
-            /* four rows at a time: the four table reads and factor products are issued together,
-             * only the running value is a dependent chain */
-            for (; k + 4 <= n1; k += 4) {
-                double r0 = tp[0], r1 = tp[dt], r2 = tp[2 * dt], r3 = tp[3 * dt];
-                double c0 = cv_mul(step, r0), c1 = cv_mul(step, r1), c2 = cv_mul(step, r2),
-                       c3 = cv_mul(step, r3);
-                double v0 = cv_mul(v, c0);
-                double v1 = cv_mul(v0, c1);
-                double v2 = cv_mul(v1, c2);
-                v = cv_mul(v2, c3);
-                sp[0] = v0;
-                sp[dt * CV_SDS] = v1;
-                sp[2 * dt * CV_SDS] = v2;
-                sp[3 * dt * CV_SDS] = v;
-                tp += 4 * dt;
-                sp += 4 * dt * CV_SDS;
+            const int n1 = down ? n : n - rs;
+            const double step = down ? step_dn : step_up;
+            for (int k = 0; k < n1; k++) {
+                const int gi = down ? n - 1 - k : rs + k; /* the group the step crosses */
+                const double *fp = g0 + gi * CV_GD + (down ? CV_G_DN : CV_G_UP);
+                double c[NSUB];
+#pragma unroll
+                for (int u = 0; u < NSUB; u++)
+                    c[u] = cv_mul(step, fp[u]);
+#pragma unroll
+                for (int u = 0; u < NSUB; u++)
+                    v = cv_mul(v, c[u]);
+                const int a = down ? gi : gi + 1; /* the anchor reached */
+                if (a < n)
+                    anc[cv_chunk(lane, first + a)] = v;
+                if (a > 0)
+                    anc[cv_chunk(lane, first + a - 1) + 1] = v;
             }
-            for (; k < n1; k++) {
-                v = cv_mul(v, cv_mul(step, *tp));
-                *sp = v;
-                tp += dt;
-                sp += dt * CV_SDS;
-            }
-        }
-        if (!down) { /* the rows below an interior starting row */
-            const double *tp = M.row_dn + grow + rs - 1;
-            double *sp = col + (rs - 1) * CV_SDS;
-            double v = seed;
-            for (int k = 0; k < rs; k++) {
-                v = cv_mul(v, cv_mul(step_dn, *tp));
-                *sp = v;
-                tp -= 1;
-                sp -= CV_SDS;
+            if (!down) { /* the anchors below an interior starting anchor */
+                v = seed;
+                for (int a = rs - 1; a >= 0; a--) {
+                    const double *fp = g0 + a * CV_GD + CV_G_DN;
+#pragma unroll
+                    for (int u = 0; u < NSUB; u++)
+                        v = cv_mul(v, cv_mul(step_dn, fp[u]));
+                    anc[cv_chunk(lane, first + a)] = v;
+                    if (a > 0)
+                        anc[cv_chunk(lane, first + a - 1) + 1] = v;
+                }
             }
         }
     }
@@ -390,64 +380,121 @@ __device__ __forceinline__ void cv_dmma(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
+#define CV_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define CV_WARP_ANY(x) (x)
 #endif
 
-/* The accumulators of a lane: MMA tile (mt, nt), mt < 8 row tiles, nt < 2 column tiles, holds rows
- * 8 mt + r and columns 8 nt + 2 q + {0, 1} with r = lane >> 2, q = lane & 3; acc[4 mt + 2 nt + {0, 1}].
- * The 16 terms of the half-tile are contracted 4 at a time; lane q supplies the terms 2q and 2q+1 of
- * each group of 8 (one 16-byte read) to two consecutive MMAs.  NA = number of live row tiles.
- * On the host (test emulation) the same sums are formed with scalar FMAs in the same term order. */
+/* The constants of the lane's group (r = lane >> 2) for the fused phase; zeros past the last
+ * group of the block, which turns the lane's rows into exact zeros. */
+struct CvLaneGroup {
+    double cinv, c16, enorm;
+    int live;
+};
+CV_HD CvLaneGroup cv_lane_group(int lane, const CvModelDesc &m, int blk, const CvWarpMem &M)
+{
+    CvLaneGroup G = {0.0, 0.0, 0.0, 0};
+    int g = blk * CV_GB + (lane >> 2);
+    if (g < m.n_groups) {
+        const double *rec = M.grp + (size_t)g * CV_GD;
+        G.cinv = rec[CV_G_CINV];
+        G.c16 = rec[CV_G_C16];
+        G.enorm = rec[CV_G_ENORM];
+        G.live = 1;
+    }
+    return G;
+}
+
+/* The values of term t over the NA rows of the lane's group, on the chain's scale (row m is the
+ * true scaled value divided by a row constant that slot_mult carries): a[0] is the anchor, every
+ * further row one multiplication by E = (lam / c)^16.  A chain whose anchor underflowed although
+ * the values grow along the group is walked down from the far anchor instead. */
 template <int NA>
-CV_HD void cv_w_fma(int lane, const CvWarpFixed &F, double *acc)
+CV_HD void cv_row_chain(const CvWarpFixed &F, const CvLaneGroup &G, int r, int t, double *a)
+{
+    cv_pair av = cv_ld2(F.u.t.ANC + cv_chunk(t, r));
+    cv_pair pr = cv_ld2(F.PWR + 2 * t);
+    const double start = G.live ? av.x : 0.0;
+    const double end = G.live ? av.y : 0.0;
+    a[0] = start;
+    if (NA == 1)
+        return;
+    const double E = cv_mul(pr.x, G.cinv);
+#pragma unroll
+    for (int i = 1; i < NA; i++)
+        a[i] = cv_mul(a[i - 1], E);
+    const bool need_down = start < 0x1p-1000 && end > start;
+    if (CV_WARP_ANY(need_down)) {
+        const double Einv = cv_mul(pr.y, G.c16);
+        double d = cv_mul(end, G.enorm);
+#pragma unroll
+        for (int i = NA - 1; i >= 1; i--) {
+            d = cv_mul(d, Einv);
+            if (need_down)
+                a[i] = d;
+        }
+    }
+}
+
+/* The accumulators of a lane: MMA tile (mt, nt), mt < NA row tiles, nt < 2 column tiles, holds row
+ * mt of group r and columns 8 nt + 2 q + {0, 1} with r = lane >> 2, q = lane & 3;
+ * acc[4 mt + 2 nt + {0, 1}].  The terms of the tile are contracted 4 at a time (nkg slices); lane q
+ * supplies term q of each slice.  On the host (test emulation) the same sums are formed with scalar
+ * FMAs in the same term order. */
+template <int NA>
+CV_HD void cv_w_fused(int lane, const CvLaneGroup &G, int nkg, const CvWarpFixed &F, double *acc)
 {
     const int r = lane >> 2, q = lane & 3;
 #if defined(__CUDA_ARCH__)
-    const double *sd = F.SD + r * CV_SDS + 2 * q;
-    const double *pw = F.PW + r * CV_PWS + 2 * q;
-#pragma unroll
-    for (int k0 = 0; k0 < CV_HT; k0 += 8) {
-        cv_pair b0 = cv_ld2(pw + k0), b1 = cv_ld2(pw + 8 * CV_PWS + k0);
+#pragma unroll 2
+    for (int kg = 0; kg < nkg; kg++) {
+        const int t = 4 * kg + q;
+        double a[NA];
+        cv_row_chain<NA>(F, G, r, t, a);
+        cv_pair b = cv_ld2(F.u.t.PW + cv_chunk(t, r));
 #pragma unroll
         for (int mt = 0; mt < NA; mt++) {
-            cv_pair a = cv_ld2(sd + mt * 8 * CV_SDS + k0);
-            cv_dmma(acc[4 * mt + 0], acc[4 * mt + 1], a.x, b0.x);
-            cv_dmma(acc[4 * mt + 2], acc[4 * mt + 3], a.x, b1.x);
-            cv_dmma(acc[4 * mt + 0], acc[4 * mt + 1], a.y, b0.y);
-            cv_dmma(acc[4 * mt + 2], acc[4 * mt + 3], a.y, b1.y);
+            cv_dmma(acc[4 * mt + 0], acc[4 * mt + 1], a[mt], b.x);
+            cv_dmma(acc[4 * mt + 2], acc[4 * mt + 3], a[mt], b.y);
         }
     }
 #else
-    for (int k0 = 0; k0 < CV_HT; k0 += 8)
+    for (int kg = 0; kg < nkg; kg++) {
+        double a[4][NA];
+        for (int k = 0; k < 4; k++)
+            cv_row_chain<NA>(F, G, r, 4 * kg + k, a[k]);
         for (int mt = 0; mt < NA; mt++)
-            for (int par = 0; par < 2; par++)     /* the .x terms, then the .y terms */
-                for (int nt = 0; nt < 2; nt++)
-                    for (int c = 0; c < 2; c++) {
-                        const double *srow = F.SD + (8 * mt + r) * CV_SDS + k0 + par;
-                        const double *pcol = F.PW + (8 * nt + 2 * q + c) * CV_PWS + k0 + par;
-                        double v = acc[4 * mt + 2 * nt + c];
-                        for (int kk = 0; kk < 4; kk++)
-                            v = cv_fma(srow[2 * kk], pcol[2 * kk], v);
-                        acc[4 * mt + 2 * nt + c] = v;
+            for (int nt = 0; nt < 2; nt++)
+                for (int c = 0; c < 2; c++) {
+                    double v = acc[4 * mt + 2 * nt + c];
+                    for (int k = 0; k < 4; k++) {
+                        const double *ch = F.u.t.PW + cv_chunk(4 * kg + k, 2 * q + c);
+                        v = cv_fma(a[k][mt], ch[nt], v);
                     }
+                    acc[4 * mt + 2 * nt + c] = v;
+                }
+    }
 #endif
 }
 
-/* The accumulators of a lane go to the seed matrix (free after the last fma of a block) in slot
- * order, slot = row * 16 + column; the 16-byte chunks of odd rows are swapped between the halves of
- * the row so that a quarter warp (2 rows x 4 chunks) does not collide. */
+/* The accumulators of a lane go to the spill area in slot order, slot = row * 16 + column (row
+ * counted inside the block); the 16-byte chunks of odd groups are swapped between the halves of
+ * the row so that a quarter warp (2 groups x 4 chunks) does not collide. */
+template <int NA>
 CV_HD int cv_spill_index(int slot)
 {
-    return slot ^ ((slot & CV_W) >> 1); /* column ^= 8 on odd rows */
+    return slot ^ ((((slot >> 4) / NA) & 1) << 3); /* column ^= 8 in odd groups */
 }
+template <int NA>
 CV_HD void cv_w_spill(int lane, CvWarpFixed &F, const double *acc)
 {
     const int r = lane >> 2, q = lane & 3;
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
+    for (int mt = 0; mt < NA; mt++)
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) {
-            int slot = (8 * mt + r) * CV_W + 8 * nt + 2 * q;
-            cv_st2(F.SD + cv_spill_index(slot), acc[4 * mt + 2 * nt], acc[4 * mt + 2 * nt + 1]);
+            int slot = (NA * r + mt) * CV_W + 8 * nt + 2 * q;
+            cv_st2(F.u.spill + cv_spill_index<NA>(slot), acc[4 * mt + 2 * nt], acc[4 * mt + 2 * nt + 1]);
         }
 }
 
@@ -458,47 +505,69 @@ CV_HD void cv_partial_add_mass(CvPartial &p, double x)
     p.mass_l = cv_add(p.mass_l, s.lo);
 }
 
-CV_HD void cv_partial_add_sum(CvPartial &p, double x)
-{
-    cv_dd s = cv_two_sum(p.sum_h, x);
-    p.sum_h = s.hi;
-    if (s.lo == s.lo) /* an infinite term makes the error term NaN; the sum itself stays right */
-        p.sum_l = cv_add(p.sum_l, s.lo);
-}
-
 CV_HD void cv_partial_merge(CvPartial &p, const CvPartial &q)
 {
     cv_partial_add_mass(p, q.mass_h);
     p.mass_l = cv_add(p.mass_l, q.mass_l);
-    cv_partial_add_sum(p, q.sum_h);
-    p.sum_l = cv_add(p.sum_l, q.sum_l);
+    p.sum = cv_add(p.sum, q.sum);
 }
 
-/* models.py:100-107 per bin: lane l finishes the slots l, l + 32, ... of the block (a compact
- * loop: the unrolled form of this, with its 32 logarithms, does not fit the instruction cache). */
-CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, int nrows_blk, const CvWarpFixed &F,
+/* models.py:100-107 per bin: lane l finishes the slots l, l + 32, ... of the block, four at a time
+ * so that the logarithms overlap.  The weighted logarithms all have one sign (p_j <= 1 outside the
+ * reference's lam > 200 sawtooth), so their plain sum is good to ~1e-13; the mass needs the
+ * compensated sum only for the tail term and is skipped when there is no tail. */
+template <int NA>
+CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, int ngroups_blk, const CvWarpFixed &F,
                          CvPartial &part, double *out_probs)
 {
+    constexpr int U = 4;
     const CvTables &T = m.tab;
-    const double *mult = T.slot_mult + blk * (CV_RB * CV_W);
-    const double *cnt = T.slot_h + blk * (CV_RB * CV_W);
-    const int *bin = T.slot_bin + blk * (CV_RB * CV_W);
-    const int nslots = nrows_blk * CV_W;
-#pragma unroll 2
-    for (int e = lane; e < nslots; e += 32) {
-        double mu = mult[e];
-        if (mu == 0.0)
-            continue; /* a bin that is not in hist */
-        double p = cv_mul(F.SD[cv_spill_index(e)], mu);
-        if (out_probs)
-            out_probs[bin[e]] = p;
-        cv_partial_add_mass(part, p);
-        double h = cnt[e];
-        if (h != 0.0) { /* models.py:106 `if h` */
-            double lg = (p <= 0.0) ? -INFINITY : log(p); /* utils.py:32-35 safe_log */
-            cv_partial_add_sum(part, cv_mul(h, lg));
+    const size_t base = (size_t)blk * (CV_GB * NA * CV_W);
+    const double *mult = T.slot_mult + base;
+    const double *cnt = T.slot_h + base;
+    const int *bin = T.slot_bin + base;
+    const int nslots = ngroups_blk * NA * CV_W;
+    const bool want_mass = m.tail != 0.0;
+    double sum[U];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+        sum[u] = 0.0;
+    for (int base = 0; base < nslots; base += 32 * U) { /* warp-uniform trip count */
+        double p[U], h[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int e = base + lane + 32 * u;
+            double mu = 0.0;
+            h[u] = 0.0;
+            p[u] = 0.0;
+            if (e < nslots) {
+                mu = mult[e];
+                h[u] = cnt[e];
+                p[u] = cv_mul(F.u.spill[cv_spill_index<NA>(e)], mu);
+                if (out_probs && mu != 0.0)
+                    out_probs[bin[e]] = p[u];
+            }
+            if (mu == 0.0) { /* a bin that is not in hist (p may be NaN * 0) */
+                p[u] = 0.0;
+                h[u] = 0.0;
+            }
+        }
+        if (want_mass) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                cv_partial_add_mass(part, p[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool counted = h[u] != 0.0; /* models.py:106 `if h` */
+            if (CV_WARP_ANY(counted)) {
+                double lg = (p[u] <= 0.0) ? -INFINITY : log(p[u]); /* utils.py:32-35 safe_log */
+                if (counted)
+                    sum[u] = cv_add(sum[u], cv_mul(h[u], lg));
+            }
         }
     }
+    part.sum = cv_add(part.sum, cv_add(cv_add(sum[0], sum[1]), cv_add(sum[2], sum[3])));
 }
 
 /* models.py:103-107 */
@@ -507,15 +576,5 @@ CV_HD double cv_point_finish(const CvModelDesc &m, const CvPartial &part)
     double mass = cv_add(part.mass_h, part.mass_l);
     if (!(mass < 1.0))
         mass = 1.0; /* min(1, fsum(...)): keeps the 1 unless the sum is smaller (also for NaN) */
-    double sum = part.sum_h;
-    if (part.sum_h - part.sum_h == 0.0) /* finite */
-        sum = cv_add(part.sum_h, part.sum_l);
-    return cv_finish_loglik(sum, mass, m.tail);
-}
-
-/* number of live 8-row groups of a block, rounded up to the instantiated 1, 2, 4, 8 */
-CV_HD int cv_row_groups(int nrows_blk)
-{
-    int na = (nrows_blk + 7) >> 3;
-    return na <= 1 ? 1 : na <= 2 ? 2 : na <= 4 ? 4 : 8;
+    return cv_finish_loglik(part.sum, mass, m.tail);
 }

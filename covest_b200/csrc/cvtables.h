@@ -4,10 +4,11 @@
  * test-only emulation.
  *
  * The bins of `hist` (models.py:27; any set of non-negative keys, in the caller's dict order) are
- * covered by rows of 16 consecutive bins: the smallest uncovered key opens a row.  Slots of a row
- * whose bin is not a key of hist are padding (slot_mult = 0).  Rows are grouped in blocks of 64;
- * inside a block, runs of rows that follow each other without a gap form segments of at most
- * CV_SEGMAX rows -- the unit that is seeded by one exp() per mixture term.
+ * covered by *groups* of NA rows of 16 consecutive bins each: the smallest uncovered key opens a
+ * group.  NA is the smallest of 1, 2, 4 that covers the histogram with at most 8 groups, else 8
+ * (any number of groups, in blocks of 8).  Slots of a group whose bin is not a key of hist are
+ * padding (slot_mult = 0).  Inside a block, groups that follow each other without a gap form runs
+ * of at most CV_RUNMAX groups -- the unit that is anchored by one exp() per mixture term.
  */
 #pragma once
 #include <algorithm>
@@ -18,19 +19,19 @@
 #include "cvpoint.h"
 
 struct CvHostTables {
-    std::vector<double> row_j0, row_head_h, row_head_l, row_up, row_dn, slot_mult, slot_h;
+    std::vector<double> grp, slot_mult, slot_h;
     std::vector<double> copy_log_h, copy_log_l;
-    std::vector<int> slot_bin, seg_first, seg_len, blk_seg_begin;
-    int n_rows = 0, n_blocks = 0, max_bin = 0;
+    std::vector<int> slot_bin, run_first, run_len, blk_run_begin;
+    int n_groups = 0, n_blocks = 0, na = 0, max_bin = 0;
 };
 
-/* log(j!) as a double-double for every j that opens a row */
+/* log(j!) as a double-double for every j of the ascending list `at` */
 static inline void cv_log_factorials(const std::vector<long> &at, std::vector<cv_dd> &out)
 {
     out.resize(at.size());
     cv_dd acc = {0.0, 0.0};
     long j = 1; /* acc = log(j!) */
-    for (size_t i = 0; i < at.size(); i++) { /* `at` ascending */
+    for (size_t i = 0; i < at.size(); i++) {
         long want = at[i] < 1 ? 1 : at[i];
         while (j < want) {
             j++;
@@ -38,6 +39,15 @@ static inline void cv_log_factorials(const std::vector<long> &at, std::vector<cv
         }
         out[i] = acc;
     }
+}
+
+/* prod_{i=1..n} (j + i) */
+static inline long double cv_rising(long j, int n)
+{
+    long double run = 1.0L;
+    for (int i = 1; i <= n; i++)
+        run *= (long double)(j + i);
+    return run;
 }
 
 /* returns "" or an error message */
@@ -61,54 +71,94 @@ static inline std::string cv_build_tables(int n_bins, const int *bin_j, const do
     T.max_bin = (int)keys.back().first;
 
     std::vector<long> heads;
-    for (int b = 0; b < n_bins;) {
-        long j0 = keys[b].first;
-        heads.push_back(j0);
-        while (b < n_bins && keys[b].first < j0 + CV_W)
-            b++;
+    int na = 1;
+    for (;; na *= 2) {
+        heads.clear();
+        const long span = (long)CV_W * na;
+        for (int b = 0; b < n_bins;) {
+            long j0 = keys[b].first;
+            heads.push_back(j0);
+            while (b < n_bins && keys[b].first < j0 + span)
+                b++;
+        }
+        if (na == CV_NA_MAX || (int)heads.size() <= CV_GB)
+            break;
     }
-    T.n_rows = (int)heads.size();
-    T.n_blocks = (T.n_rows + CV_RB - 1) / CV_RB;
-    int padded = T.n_blocks * CV_RB;
-    T.row_j0.assign(padded, 0.0);
-    T.row_head_h.assign(padded, 0.0);
-    T.row_head_l.assign(padded, 0.0);
-    T.row_up.assign(padded, 0.0);
-    T.row_dn.assign(padded, 0.0);
-    T.slot_mult.assign((size_t)padded * CV_W, 0.0);
-    T.slot_h.assign((size_t)padded * CV_W, 0.0);
-    T.slot_bin.assign((size_t)padded * CV_W, -1);
+    const long span = (long)CV_W * na;
+    const int sub_bins = na == 1 ? CV_W : 2 * CV_W;
+    const int nsub = (int)(span / sub_bins);
+    T.na = na;
+    T.n_groups = (int)heads.size();
+    T.n_blocks = (T.n_groups + CV_GB - 1) / CV_GB;
+    const int padded = T.n_blocks * CV_GB;
+    const size_t nslots = (size_t)padded * na * CV_W;
+    T.grp.assign((size_t)padded * CV_GD, 0.0);
+    T.slot_mult.assign(nslots, 0.0);
+    T.slot_h.assign(nslots, 0.0);
+    T.slot_bin.assign(nslots, -1);
 
+    /* log-factorials at the first bin of every group and at the bin after it */
+    std::vector<long> at;
+    for (long j0 : heads) {
+        at.push_back(j0);
+        at.push_back(j0 + span);
+    }
+    std::sort(at.begin(), at.end());
+    at.erase(std::unique(at.begin(), at.end()), at.end());
     std::vector<cv_dd> logfact;
-    cv_log_factorials(heads, logfact);
+    cv_log_factorials(at, logfact);
+    auto head_at = [&](long j) {
+        size_t i = std::lower_bound(at.begin(), at.end(), j) - at.begin();
+        cv_dd neg = {-logfact[i].hi, -logfact[i].lo};
+        return cv_dd_add_d(neg, CV_SCALE_LOG);
+    };
+
     const long double unscale = expl(-(long double)CV_SCALE_LOG);
-    for (int r = 0; r < T.n_rows; r++) {
-        long j0 = heads[r];
-        T.row_j0[r] = (double)j0;
-        cv_dd head = cv_dd_add_d({-logfact[r].hi, -logfact[r].lo}, CV_SCALE_LOG);
-        T.row_head_h[r] = head.hi;
-        T.row_head_l[r] = head.lo;
-        long double run = 1.0L; /* (j0+i)! / j0! */
-        for (int i = 1; i <= CV_W; i++)
-            run *= (long double)(j0 + i);
-        if (r + 1 < T.n_rows && heads[r + 1] == j0 + CV_W) {
-            T.row_up[r + 1] = (double)(1.0L / run);
-            T.row_dn[r] = (double)run;
+    std::vector<long double> row_scale((size_t)T.n_groups * na, 1.0L); /* R'_m of DESIGN.md */
+    for (int g = 0; g < T.n_groups; g++) {
+        const long j0 = heads[g];
+        double *rec = T.grp.data() + (size_t)g * CV_GD;
+        rec[CV_G_J0] = (double)j0;
+        cv_dd h0 = head_at(j0), h1 = head_at(j0 + span);
+        rec[CV_G_HEAD] = h0.hi;
+        rec[CV_G_HEAD + 1] = h0.lo;
+        rec[CV_G_EHEAD] = h1.hi;
+        rec[CV_G_EHEAD + 1] = h1.lo;
+        /* c^16 with c the geometric mean of the bins j0+1 .. j0+span; the chain multiplies by the
+         * DOUBLE c^-16, so the row scales below are built from that double */
+        long double c16 = powl(cv_rising(j0, (int)span), 1.0L / (long double)na);
+        const double cinv = (double)(1.0L / c16);
+        rec[CV_G_CINV] = cinv;
+        rec[CV_G_C16] = (double)(1.0L / (long double)cinv);
+        long double scale = 1.0L;
+        for (int mrow = 1; mrow <= na; mrow++) {
+            scale = scale / (long double)cinv / cv_rising(j0 + (long)CV_W * (mrow - 1), CV_W);
+            if (mrow < na)
+                row_scale[(size_t)g * na + mrow] = scale;
+        }
+        rec[CV_G_ENORM] = (double)(1.0L / scale);
+        for (int u = 0; u < 4; u++) {
+            rec[CV_G_UP + u] = 1.0;
+            rec[CV_G_DN + u] = 1.0;
+            if (u < nsub) {
+                long double run = cv_rising(j0 + (long)sub_bins * u, sub_bins);
+                rec[CV_G_UP + u] = (double)(1.0L / run);
+                rec[CV_G_DN + u] = (double)run;
+            }
         }
     }
     /* slots */
     {
-        int r = 0;
+        int g = 0;
         for (int b = 0; b < n_bins; b++) {
             long j = keys[b].first;
-            while (j >= heads[r] + CV_W)
-                r++;
-            int i = (int)(j - heads[r]);
-            long double run = 1.0L;
-            for (int m = 1; m <= i; m++)
-                run *= (long double)(heads[r] + m);
-            size_t slot = (size_t)r * CV_W + i;
-            T.slot_mult[slot] = (double)(unscale / run);
+            while (j >= heads[g] + span)
+                g++;
+            int d = (int)(j - heads[g]);
+            int mrow = d / CV_W, i = d % CV_W;
+            long double run = cv_rising(heads[g] + (long)CV_W * mrow, i);
+            size_t slot = ((size_t)g * na + mrow) * CV_W + i;
+            T.slot_mult[slot] = (double)(unscale * row_scale[(size_t)g * na + mrow] / run);
             T.slot_h[slot] = bin_h ? bin_h[keys[b].second] : 0.0;
             T.slot_bin[slot] = keys[b].second;
         }
@@ -121,40 +171,38 @@ static inline std::string cv_build_tables(int n_bins, const int *bin_j, const do
         T.copy_log_h[o] = lg.hi;
         T.copy_log_l[o] = lg.lo;
     }
-    /* segments */
-    T.blk_seg_begin.assign(T.n_blocks + 1, 0);
+    /* runs */
+    T.blk_run_begin.assign(T.n_blocks + 1, 0);
+    T.run_first.clear();
+    T.run_len.clear();
     for (int blk = 0; blk < T.n_blocks; blk++) {
-        T.blk_seg_begin[blk] = (int)T.seg_first.size();
-        int lo = blk * CV_RB, hi = std::min(T.n_rows, lo + CV_RB);
-        int r = lo;
-        while (r < hi) {
-            int start = r;
-            r++;
-            while (r < hi && r - start < CV_SEGMAX && heads[r] == heads[r - 1] + CV_W)
-                r++;
-            T.seg_first.push_back(start - lo);
-            T.seg_len.push_back(r - start);
+        T.blk_run_begin[blk] = (int)T.run_first.size();
+        int lo = blk * CV_GB, hi = std::min(T.n_groups, lo + CV_GB);
+        int g = lo;
+        while (g < hi) {
+            int start = g;
+            g++;
+            while (g < hi && g - start < CV_RUNMAX && heads[g] == heads[g - 1] + span)
+                g++;
+            T.run_first.push_back(start - lo);
+            T.run_len.push_back(g - start);
         }
     }
-    T.blk_seg_begin[T.n_blocks] = (int)T.seg_first.size();
+    T.blk_run_begin[T.n_blocks] = (int)T.run_first.size();
     return "";
 }
 
 static inline CvTables cv_tables_view(const CvHostTables &T)
 {
     CvTables v;
-    v.row_j0 = T.row_j0.data();
-    v.row_head_h = T.row_head_h.data();
-    v.row_head_l = T.row_head_l.data();
-    v.row_up = T.row_up.data();
-    v.row_dn = T.row_dn.data();
+    v.grp = T.grp.data();
     v.slot_mult = T.slot_mult.data();
     v.slot_h = T.slot_h.data();
     v.slot_bin = T.slot_bin.data();
     v.copy_log_h = T.copy_log_h.data();
     v.copy_log_l = T.copy_log_l.data();
-    v.seg_first = T.seg_first.data();
-    v.seg_len = T.seg_len.data();
-    v.blk_seg_begin = T.blk_seg_begin.data();
+    v.run_first = T.run_first.data();
+    v.run_len = T.run_len.data();
+    v.blk_run_begin = T.blk_run_begin.data();
     return v;
 }

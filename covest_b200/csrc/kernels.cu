@@ -35,14 +35,13 @@ __device__ __forceinline__ void cv_lattice_point(const CvLattice &lat, long long
 __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, int delta)
 {
     CvPartial q;
-    q.sum_h = __shfl_down_sync(CV_FULL_MASK, p.sum_h, delta);
-    q.sum_l = __shfl_down_sync(CV_FULL_MASK, p.sum_l, delta);
+    q.sum = __shfl_down_sync(CV_FULL_MASK, p.sum, delta);
     q.mass_h = __shfl_down_sync(CV_FULL_MASK, p.mass_h, delta);
     q.mass_l = __shfl_down_sync(CV_FULL_MASK, p.mass_l, delta);
     return q;
 }
 
-/* shared memory of a CTA: the five row tables (rows_staged doubles each), then per warp a
+/* shared memory of a CTA: the group records (groups_staged * CV_GD doubles), then per warp a
  * CvWarpFixed followed by its variable part */
 __host__ __device__ __forceinline__ size_t cv_warp_bytes(int n_err)
 {
@@ -50,11 +49,58 @@ __host__ __device__ __forceinline__ size_t cv_warp_bytes(int n_err)
     return (b + 15) & ~(size_t)15;
 }
 
+/* All blocks of one point: for every block the tiles of mixture terms are prepared (one term per
+ * lane) and contracted into the lane's accumulators, then the block is finished bin by bin. */
+template <int NA>
+__device__ __forceinline__ void cv_point_blocks(int lane, const CvModelDesc &m, CvWarpMem &M,
+                                                CvPartial &part, double *probs_row)
+{
+    const int S = m.n_err;
+    const int cpg = cv_copies_per_group(S);
+    for (int blk = 0; blk < m.n_blocks; blk++) {
+        const CvLaneGroup G = cv_lane_group(lane, m, blk, M);
+        double acc[4 * NA];
+#pragma unroll
+        for (int i = 0; i < 4 * NA; i++)
+            acc[i] = 0.0;
+        /* passes of 32 copy numbers: lane i holds b(first + i); the copies before the first
+         * lane that reports the cut-off are evaluated (models.py:185-191) */
+        for (int first = 1;; first += 32) {
+            double b;
+            bool stop = cv_w_copy_pass(lane, m, M, first, &b);
+            const unsigned stop_mask = __ballot_sync(CV_FULL_MASK, stop);
+            const int nlive = stop_mask ? __ffs(stop_mask) - 1 : 32;
+            for (int g = 0; g < nlive; g += cpg) {
+                const int ncop = min(cpg, nlive - g);
+                const int nterms = ncop * S;
+                cv_w_mass(lane, m, first + g, nterms, M);
+                __syncwarp();
+                for (int sub = 0; sub < nterms; sub += CV_CT) {
+                    int src = g + (sub + lane) / S; /* the lane that holds this term's b(o) */
+                    double bt = __shfl_sync(CV_FULL_MASK, b, src < 31 ? src : 31);
+                    const CvTerm tm = cv_w_term(lane, m, first + g, nterms, sub, bt, M);
+                    cv_w_prep<NA>(lane, m, blk, tm, M);
+                    __syncwarp();
+                    const int nkg = (min(CV_CT, nterms - sub) + 3) >> 2;
+                    cv_w_fused<NA>(lane, G, nkg, *M.fx, acc);
+                    __syncwarp();
+                }
+            }
+            if (stop_mask)
+                break;
+        }
+        cv_w_spill<NA>(lane, *M.fx, acc);
+        __syncwarp();
+        cv_w_epilogue<NA>(lane, m, blk, min(CV_GB, m.n_groups - blk * CV_GB), *M.fx, part, probs_row);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(32 * CV_WARPS_MAX, 1)
 cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                  const double *__restrict__ params, long long n_points, int clip,
                  double *__restrict__ out_ll, double *__restrict__ out_probs,
-                 unsigned long long *counter, int rows_staged)
+                 unsigned long long *counter, int groups_staged)
 {
     extern __shared__ __align__(16) unsigned char cv_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -63,25 +109,15 @@ cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ 
     CvWarpMem M;
     {
         double *tab = reinterpret_cast<double *>(cv_smem_raw);
-        unsigned char *wbase = cv_smem_raw + (size_t)5 * rows_staged * sizeof(double) +
-                               (size_t)warp * cv_warp_bytes(S);
+        const int ntab = groups_staged * CV_GD;
+        unsigned char *wbase = cv_smem_raw + (size_t)ntab * sizeof(double) + (size_t)warp * cv_warp_bytes(S);
         CvWarpFixed *fx = reinterpret_cast<CvWarpFixed *>(wbase);
         cv_warp_mem_carve(M, fx, reinterpret_cast<double *>(wbase + sizeof(CvWarpFixed)), S);
-        const double *src[5] = {m.tab.row_j0, m.tab.row_head_h, m.tab.row_head_l, m.tab.row_up,
-                                m.tab.row_dn};
-#pragma unroll
-        for (int k = 0; k < 5; k++)
-            for (int i = threadIdx.x; i < rows_staged; i += blockDim.x)
-                tab[k * rows_staged + i] = src[k][i];
-        M.row_j0 = tab;
-        M.row_head_h = tab + rows_staged;
-        M.row_head_l = tab + 2 * rows_staged;
-        M.row_up = tab + 3 * rows_staged;
-        M.row_dn = tab + 4 * rows_staged;
+        for (int i = threadIdx.x; i < ntab; i += blockDim.x)
+            tab[i] = m.tab.grp[i];
+        M.grp = tab;
     }
     __syncthreads(); /* the only CTA-wide barrier: from here on every warp is on its own */
-
-    const int cpg = cv_copies_per_group(S);
 
     for (;;) {
         long long point = 0;
@@ -102,55 +138,13 @@ cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ 
         cv_w_header(lane, m, row, clip, M);
         __syncwarp();
 
-        CvPartial part = {0.0, 0.0, 0.0, 0.0};
+        CvPartial part = {0.0, 0.0, 0.0};
         double *probs_row = out_probs ? out_probs + point * (long long)m.n_bins : nullptr;
-
-        for (int blk = 0; blk < m.n_blocks; blk++) {
-            const int na = cv_row_groups(min(CV_RB, m.n_rows - blk * CV_RB));
-            double acc[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++)
-                acc[i] = 0.0;
-            /* passes of 32 copy numbers: lane i holds b(first + i); the copies before the first
-             * lane that reports the cut-off are evaluated (models.py:185-191) */
-            for (int first = 1;; first += 32) {
-                double b;
-                bool stop = cv_w_copy_pass(lane, m, M, first, &b);
-                const unsigned stop_mask = __ballot_sync(CV_FULL_MASK, stop);
-                const int nlive = stop_mask ? __ffs(stop_mask) - 1 : 32;
-                for (int g = 0; g < nlive; g += cpg) {
-                    const int ncop = min(cpg, nlive - g);
-                    const int nterms = ncop * S;
-                    cv_w_mass(lane, m, first + g, nterms, M);
-                    __syncwarp();
-                    for (int sub = 0; sub < nterms; sub += CV_CT) {
-                        int src = g + (sub + lane) / S; /* the lane that holds this term's b(o) */
-                        double bt = __shfl_sync(CV_FULL_MASK, b, src < 31 ? src : 31);
-                        cv_w_terms(lane, m, first + g, nterms, sub, bt, M);
-                        __syncwarp();
-                        const int nhalf = (min(CV_CT, nterms - sub) + CV_HT - 1) / CV_HT;
-                        for (int half = 0; half < nhalf; half++) {
-                            cv_w_powers(lane, half, M);
-                            __syncwarp();
-                            cv_w_seeds(lane, m, blk, half, M);
-                            __syncwarp();
-                            switch (na) {
-                            case 1: cv_w_fma<1>(lane, *M.fx, acc); break;
-                            case 2: cv_w_fma<2>(lane, *M.fx, acc); break;
-                            case 4: cv_w_fma<4>(lane, *M.fx, acc); break;
-                            default: cv_w_fma<8>(lane, *M.fx, acc); break;
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-                if (stop_mask)
-                    break;
-            }
-            cv_w_spill(lane, *M.fx, acc);
-            __syncwarp();
-            cv_w_epilogue(lane, m, blk, min(CV_RB, m.n_rows - blk * CV_RB), *M.fx, part, probs_row);
-            __syncwarp();
+        switch (m.na) {
+        case 1: cv_point_blocks<1>(lane, m, M, part, probs_row); break;
+        case 2: cv_point_blocks<2>(lane, m, M, part, probs_row); break;
+        case 4: cv_point_blocks<4>(lane, m, M, part, probs_row); break;
+        default: cv_point_blocks<8>(lane, m, M, part, probs_row); break;
         }
         /* warp reduction of the partial sums in a fixed order */
 #pragma unroll
@@ -163,13 +157,13 @@ cv_loglik_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ 
     }
 }
 
-/* warps per CTA and staged rows that fit the shared memory of an SM */
-static void cv_loglik_config(const CvModelDesc &m, int smem_max, int *n_warps, int *rows_staged,
+/* warps per CTA and staged groups that fit the shared memory of an SM */
+static void cv_loglik_config(const CvModelDesc &m, int smem_max, int *n_warps, int *groups_staged,
                              size_t *smem_bytes)
 {
     const size_t wb = cv_warp_bytes(m.n_err);
-    const int rows = m.n_blocks * CV_RB;
-    const size_t tab = (size_t)5 * rows * sizeof(double);
+    const int groups = m.n_blocks * CV_GB;
+    const size_t tab = (size_t)groups * CV_GD * sizeof(double);
     long long w = ((long long)smem_max - (long long)tab) / (long long)wb;
     if (w > CV_WARPS_MAX)
         w = CV_WARPS_MAX;
@@ -177,9 +171,9 @@ static void cv_loglik_config(const CvModelDesc &m, int smem_max, int *n_warps, i
         if (atoi(cap) >= 1 && atoi(cap) < w)
             w = atoi(cap);
     if (w < 1)
-        w = 0; /* the row tables do not fit next to one warp: the caller reports it */
+        w = 0; /* the group tables do not fit next to one warp: the caller reports it */
     *n_warps = (int)w;
-    *rows_staged = rows;
+    *groups_staged = groups;
     *smem_bytes = tab + (size_t)w * wb;
 }
 
@@ -188,16 +182,16 @@ int cv_loglik_smem_bytes(const CvModelDesc &m, int smem_max)
     int w, r;
     size_t b;
     cv_loglik_config(m, smem_max, &w, &r, &b);
-    return (int)b;
+    return w < 1 ? -1 : (int)b;
 }
 
 cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const double *params,
                              long long n_points, int clip, double *out_ll, double *out_probs,
                              unsigned long long *counter, int n_sm, int smem_max, cudaStream_t stream)
 {
-    int n_warps, rows_staged;
+    int n_warps, groups_staged;
     size_t smem;
-    cv_loglik_config(m, smem_max, &n_warps, &rows_staged, &smem);
+    cv_loglik_config(m, smem_max, &n_warps, &groups_staged, &smem);
     if (n_warps < 1)
         return cudaErrorInvalidConfiguration; /* ctx_create refuses such histograms */
     /* per device, and cheap: set on every launch */
@@ -219,7 +213,7 @@ cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const d
     long long ctas = (n_points + n_warps - 1) / n_warps;
     int grid = (int)(ctas < n_sm ? ctas : n_sm);
     cv_loglik_kernel<<<grid, 32 * n_warps, smem, stream>>>(m, lat, params, n_points, clip, out_ll,
-                                                           out_probs, counter, rows_staged);
+                                                           out_probs, counter, groups_staged);
     return cudaGetLastError();
 }
 

@@ -15,37 +15,16 @@
 #include "../../covest_b200/csrc/cvtables.h"
 
 template <int NA>
-static void emu_fma(const CvWarpFixed &F, double *acc)
+static void emulate_blocks(const CvModelDesc &m, CvWarpMem &M, CvPartial *part, double *out_probs)
 {
-    for (int lane = 0; lane < 32; lane++)
-        cv_w_fma<NA>(lane, F, acc + 32 * lane);
-}
-
-static void emulate_point(const CvModelDesc &m, const double *row_in, int clip, double *out_ll,
-                          double *out_probs)
-{
-    static CvWarpFixed fx;
+    CvWarpFixed &fx = *M.fx;
     const int S = m.n_err;
-    std::vector<double> var(cv_warp_var_doubles(S));
-    CvWarpMem M;
-    cv_warp_mem_carve(M, &fx, var.data(), S);
-    M.row_j0 = m.tab.row_j0;
-    M.row_head_h = m.tab.row_head_h;
-    M.row_head_l = m.tab.row_head_l;
-    M.row_up = m.tab.row_up;
-    M.row_dn = m.tab.row_dn;
-    double row[CV_MAX_PARAMS] = {0, 0, 0, 0, 0};
-    for (int i = 0; i < m.n_param; i++)
-        row[i] = row_in[i];
-    for (int lane = 0; lane < 32; lane++)
-        cv_w_header(lane, m, row, clip, M);
     const int cpg = cv_copies_per_group(S);
-    std::vector<double> acc(32 * 32);
-    CvPartial part[32];
-    for (int lane = 0; lane < 32; lane++)
-        part[lane] = CvPartial{0, 0, 0, 0};
+    std::vector<double> acc(32 * 4 * NA);
     for (int blk = 0; blk < m.n_blocks; blk++) {
-        const int na = cv_row_groups(std::min(CV_RB, m.n_rows - blk * CV_RB));
+        CvLaneGroup G[32];
+        for (int lane = 0; lane < 32; lane++)
+            G[lane] = cv_lane_group(lane, m, blk, M);
         std::fill(acc.begin(), acc.end(), 0.0);
         for (int first = 1;; first += 32) {
             double b[32];
@@ -64,31 +43,47 @@ static void emulate_point(const CvModelDesc &m, const double *row_in, int clip, 
                 for (int sub = 0; sub < nterms; sub += CV_CT) {
                     for (int lane = 0; lane < 32; lane++) {
                         int src = g + (sub + lane) / S;
-                        cv_w_terms(lane, m, first + g, nterms, sub, b[src < 31 ? src : 31], M);
+                        CvTerm tm = cv_w_term(lane, m, first + g, nterms, sub, b[src < 31 ? src : 31], M);
+                        cv_w_prep<NA>(lane, m, blk, tm, M);
                     }
-                    const int nhalf = (std::min(CV_CT, nterms - sub) + CV_HT - 1) / CV_HT;
-                    for (int half = 0; half < nhalf; half++) {
-                        for (int lane = 0; lane < 32; lane++)
-                            cv_w_powers(lane, half, M);
-                        for (int lane = 0; lane < 32; lane++)
-                            cv_w_seeds(lane, m, blk, half, M);
-                        switch (na) {
-                        case 1: emu_fma<1>(fx, acc.data()); break;
-                        case 2: emu_fma<2>(fx, acc.data()); break;
-                        case 4: emu_fma<4>(fx, acc.data()); break;
-                        default: emu_fma<8>(fx, acc.data()); break;
-                        }
-                    }
+                    const int nkg = (std::min(CV_CT, nterms - sub) + 3) >> 2;
+                    for (int lane = 0; lane < 32; lane++)
+                        cv_w_fused<NA>(lane, G[lane], nkg, fx, acc.data() + 4 * NA * lane);
                 }
             }
             if (any)
                 break;
         }
         for (int lane = 0; lane < 32; lane++)
-            cv_w_spill(lane, fx, acc.data() + 32 * lane);
+            cv_w_spill<NA>(lane, fx, acc.data() + 4 * NA * lane);
         for (int lane = 0; lane < 32; lane++)
-            cv_w_epilogue(lane, m, blk, std::min(CV_RB, m.n_rows - blk * CV_RB), fx, part[lane],
-                          out_probs);
+            cv_w_epilogue<NA>(lane, m, blk, std::min(CV_GB, m.n_groups - blk * CV_GB), fx, part[lane],
+                              out_probs);
+    }
+}
+
+static void emulate_point(const CvModelDesc &m, const double *row_in, int clip, double *out_ll,
+                          double *out_probs)
+{
+    static CvWarpFixed fx;
+    const int S = m.n_err;
+    std::vector<double> var(cv_warp_var_doubles(S));
+    CvWarpMem M;
+    cv_warp_mem_carve(M, &fx, var.data(), S);
+    M.grp = m.tab.grp;
+    double row[CV_MAX_PARAMS] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < m.n_param; i++)
+        row[i] = row_in[i];
+    for (int lane = 0; lane < 32; lane++)
+        cv_w_header(lane, m, row, clip, M);
+    CvPartial part[32];
+    for (int lane = 0; lane < 32; lane++)
+        part[lane] = CvPartial{0, 0, 0};
+    switch (m.na) {
+    case 1: emulate_blocks<1>(m, M, part, out_probs); break;
+    case 2: emulate_blocks<2>(m, M, part, out_probs); break;
+    case 4: emulate_blocks<4>(m, M, part, out_probs); break;
+    default: emulate_blocks<8>(m, M, part, out_probs); break;
     }
     /* __shfl_down_sync tree: a lane whose source is out of range receives its own value */
     for (int d = 16; d >= 1; d >>= 1) {
@@ -119,7 +114,8 @@ extern "C" int emu_loglik_batch(int model_kind, int k, int r, int n_err, int n_b
     m.n_err = n_err;
     m.n_param = model_kind ? 5 : 2;
     m.n_bins = n_bins;
-    m.n_rows = T.n_rows;
+    m.n_groups = T.n_groups;
+    m.na = T.na;
     m.n_blocks = T.n_blocks;
     m.max_bin = T.max_bin;
     m.tail = tail;
