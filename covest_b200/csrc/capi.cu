@@ -7,12 +7,14 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/covest_b200.h"
 #include "cvtables.h"
+#include "factored.h"
 #include "kernels.h"
 
 #define CVB_CHUNK_POINTS (1LL << 22) /* staging granularity for host-resident batches */
@@ -46,6 +48,14 @@ struct cvb_ctx {
     int timed_chunks = 0;
     int last_launches = 0;
     cudaStream_t timed_stream = nullptr;
+    /* the factored path of the repeats model (factored.h) */
+    CvFactorWork fw;
+    const double2 *d_slot_mh = nullptr;
+    int path_mode = 0;         /* 0 auto, 1 per-point kernel only, 2 factored whenever supported */
+    size_t w_limit = (size_t)2 << 30; /* doubles: 16 GiB of profiles per group range */
+    double min_group = 12.0;   /* auto: points per (c, e) group below which the per-point kernel runs */
+    long long min_points = 2048; /* auto: batches below this go straight to the per-point kernel */
+    int last_path = 0;         /* 1 per-point, 2 factored */
     std::string err;
 };
 
@@ -140,6 +150,7 @@ extern "C" void cvb_ctx_destroy(cvb_ctx *ctx)
             cudaFree(p);
     for (cudaEvent_t e : ctx->ev)
         cudaEventDestroy(e);
+    cvf_release(ctx->fw);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -242,6 +253,17 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         if ((e = upload(c, T.run_first, &t.run_first)) != cudaSuccess) break;
         if ((e = upload(c, T.run_len, &t.run_len)) != cudaSuccess) break;
         if ((e = upload(c, T.blk_run_begin, &t.blk_run_begin)) != cudaSuccess) break;
+        {
+            std::vector<double2> mh(T.slot_mult.size());
+            for (size_t i = 0; i < mh.size(); i++)
+                mh[i] = make_double2(T.slot_mult[i], T.slot_h[i]);
+            if ((e = upload(c, mh, &c->d_slot_mh)) != cudaSuccess) break;
+        }
+        if (const char *pm = getenv("COVEST_B200_PATH"))
+            c->path_mode = !strcmp(pm, "direct") ? 1 : !strcmp(pm, "factored") ? 2 : 0;
+        if (const char *wl = getenv("COVEST_B200_PROFILE_MIB"))
+            if (atoll(wl) > 0)
+                c->w_limit = (size_t)atoll(wl) * (1 << 20) / sizeof(double);
         if ((e = cudaMalloc((void **)&c->d_counter, sizeof(unsigned long long))) != cudaSuccess) break;
         if ((e = cudaMalloc((void **)&c->d_sink, 64)) != cudaSuccess) break;
     } while (0);
@@ -292,21 +314,36 @@ extern "C" int cvb_last_kernel_ms(cvb_ctx *ctx, double *out_ms, int *out_launche
     return CVB_OK;
 }
 
-/* one loglik launch, optionally bracketed by events */
+/* one evaluation of n points on the device, optionally bracketed by events: the factored path
+ * when the batch is large and groups well (never when per-bin probabilities are wanted), else the
+ * per-point kernel */
 static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_params, long long n,
                          int clip, double *d_ll, double *d_probs, cudaStream_t s)
 {
     bool timed = ctx->timing && ctx->timed_chunks < CVB_MAX_TIMED_CHUNKS;
     if (timed)
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks], s), "cudaEventRecord");
-    CU(cv_launch_loglik(ctx->desc, lat, d_params, n, clip, d_ll, d_probs, ctx->d_counter, ctx->n_sm,
-                        ctx->smem_max, s),
-       "cv_loglik_kernel launch");
+    int used = 0;
+    const bool try_factored = !d_probs && ctx->path_mode != 1 && cvf_supported(ctx->desc) &&
+                              (ctx->path_mode == 2 || n >= ctx->min_points);
+    if (try_factored) {
+        ctx->fw.timed = ctx->timing;
+        CU(cvf_eval(ctx->desc, lat, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->fw, ctx->n_sm,
+                    ctx->smem_max, ctx->w_limit, ctx->path_mode == 2 ? 0.0 : ctx->min_group, s, &used),
+           "factored evaluation");
+        ctx->last_launches += ctx->fw.launches;
+    }
+    if (!used) {
+        CU(cv_launch_loglik(ctx->desc, lat, d_params, n, clip, d_ll, d_probs, ctx->d_counter, ctx->n_sm,
+                            ctx->smem_max, s),
+           "cv_loglik_kernel launch");
+        ctx->last_launches++;
+    }
+    ctx->last_path = used ? 2 : 1;
     if (timed) {
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks + 1], s), "cudaEventRecord");
         ctx->timed_chunks++;
     }
-    ctx->last_launches++;
     return CVB_OK;
 }
 
@@ -567,6 +604,46 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     }
     if (need_sync)
         CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    return CVB_OK;
+}
+
+/* ---- path selection and facts about the last evaluation -------------------------------------- */
+extern "C" int cvb_set_path(cvb_ctx *ctx, int mode)
+{
+    if (!ctx)
+        return CVB_EINVAL;
+    if (mode < 0 || mode > 2)
+        return fail(ctx, CVB_EINVAL, "path mode must be 0 (auto), 1 (per-point) or 2 (factored)");
+    ctx->path_mode = mode;
+    return CVB_OK;
+}
+
+extern "C" int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out)
+{
+    if (!ctx || !out || n_out < 1)
+        return CVB_EINVAL;
+    CU(cudaSetDevice(ctx->device), "cudaSetDevice");
+    double v[CVB_PATH_INFO_LEN] = {0};
+    v[0] = ctx->last_path;
+    if (ctx->last_path == 2) {
+        const CvFactorWork &w = ctx->fw;
+        v[1] = (double)w.n_groups;
+        v[2] = (double)w.n_tiles;
+        v[3] = (double)w.n_items;
+        v[4] = (double)w.w_doubles;
+        if (w.timed && w.ev[0]) {
+            float ms = 0.f;
+            CU(cudaEventSynchronize(w.ev[3]), "cudaEventSynchronize");
+            CU(cudaEventElapsedTime(&ms, w.ev[0], w.ev[1]), "cudaEventElapsedTime");
+            v[5] = ms; /* keys, sort, group tables (includes one host synchronisation) */
+            CU(cudaEventElapsedTime(&ms, w.ev[1], w.ev[2]), "cudaEventElapsedTime");
+            v[6] = ms; /* profiles (and the tiles of all but the last group range) */
+            CU(cudaEventElapsedTime(&ms, w.ev[2], w.ev[3]), "cudaEventElapsedTime");
+            v[7] = ms; /* tiles of the last group range */
+        }
+    }
+    for (int i = 0; i < n_out && i < CVB_PATH_INFO_LEN; i++)
+        out[i] = v[i];
     return CVB_OK;
 }
 

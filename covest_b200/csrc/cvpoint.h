@@ -38,6 +38,7 @@
 #define CV_RUNMAX 4    /* longest run of groups anchored from one exp() */
 #define CV_MAX_PARAMS 5
 #define CV_WARPS_MAX 12 /* warps (= points in flight) per CTA; one CTA per SM */
+#define CV_COPY_PAD 40  /* copies past max(hist) that copy_log still covers */
 
 /* record of a group in CvTables::grp */
 #define CV_GD 16       /* doubles per record */
@@ -194,35 +195,42 @@ CV_HD bool cv_w_copy_pass(int lane, const CvModelDesc &m, const CvWarpMem &M, in
 }
 
 /* ---- per group of copies ------------------------------------------------------------------ */
-/* models.py:87 / :221.  Term t of the group is copy o = group_o + t / S, error class s = t % S. */
-CV_HD void cv_w_mass(int lane, const CvModelDesc &m, int group_o, int nterms, CvWarpMem &M)
+/* models.py:87 / :221.  Slot t of the group is copy o = group_o + t / sp, error class s = t % sp;
+ * sp >= S is the number of slots a copy takes (S in the per-point kernel, S rounded up to a
+ * multiple of 4 in the profile kernel, whose MMA slices must not mix copies); slots with s >= S
+ * are dead. */
+CV_HD void cv_w_mass(int lane, const CvModelDesc &m, int group_o, int nslots, int sp, CvWarpMem &M)
 {
     int S = m.n_err;
-    for (int t = lane; t < nterms; t += 32) {
-        int g = t / S, s = t - g * S;
+    for (int t = lane; t < nslots; t += 32) {
+        int g = t / sp, s = t - g * sp;
+        if (s >= S)
+            continue;
         double lam = cv_mul((double)(group_o + g), M.ls[s]); /* o * l_s, models.py:238 */
         M.glam[t] = lam;
         M.nmass[t] = cv_class_mass(m.comb[s], lam);
     }
 }
 
-/* Constants of the term t = sub + lane of the group (a dead term when t >= nterms); `b` is the
- * weight b(o) of the copy this lane's term belongs to. */
-CV_HD CvTerm cv_w_term(int lane, const CvModelDesc &m, int group_o, int nterms, int sub, double b,
-                       const CvWarpMem &M)
+/* Constants of the term in slot t = sub + lane of the group (a dead term when the slot is past
+ * the group or past the error classes of its copy); `b` is the weight b(o) of the copy this lane's
+ * term belongs to. */
+CV_HD CvTerm cv_w_term(int lane, const CvModelDesc &m, int group_o, int nslots, int sp, int sub,
+                       double b, const CvWarpMem &M)
 {
+    const CvTerm dead = {1.0, 0.0, 0.0, 0.0, 0.0}; /* contributes exactly 0 */
     int t = sub + lane;
-    if (t >= nterms) { /* padding of the last tile: contributes exactly 0 */
-        CvTerm dead = {1.0, 0.0, 0.0, 0.0, 0.0};
+    if (t >= nslots)
         return dead;
-    }
     int S = m.n_err;
-    int g = t / S, s = t - g * S;
+    int g = t / sp, s = t - g * sp;
+    if (s >= S)
+        return dead;
     int o = group_o + g;
     /* models.py:88 / :224: Python sum(), left to right starting from int 0 */
     double total = 0.0;
     for (int i = 0; i < S; i++)
-        total = cv_add(total, M.nmass[g * S + i]);
+        total = cv_add(total, M.nmass[g * sp + i]);
     if (total == 0.0)
         total = 1.0; /* utils.py:25-29 fix_zero */
     double lam = M.glam[t];
@@ -373,13 +381,17 @@ CV_HD void cv_w_prep(int lane, const CvModelDesc &m, int blk, const CvTerm &tm, 
 
 /* One m8n8k4 FP64 MMA: D = A (8 x 4, row) * B (4 x 8, col) + D.  Lane l holds A[l >> 2][l & 3],
  * B[l & 3][l >> 2] and D[l >> 2][2 (l & 3) + {0, 1}]. */
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 __device__ __forceinline__ void cv_dmma(double &d0, double &d1, double a, double b)
 {
+#if defined(__CUDA_ARCH__)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
+#endif
 }
+#endif
+#if defined(__CUDA_ARCH__)
 #define CV_WARP_ANY(x) __any_sync(0xffffffffu, (x))
 #else
 #define CV_WARP_ANY(x) (x)
@@ -439,15 +451,15 @@ CV_HD void cv_row_chain(const CvWarpFixed &F, const CvLaneGroup &G, int r, int t
 /* The accumulators of a lane: MMA tile (mt, nt), mt < NA row tiles, nt < 2 column tiles, holds row
  * mt of group r and columns 8 nt + 2 q + {0, 1} with r = lane >> 2, q = lane & 3;
  * acc[4 mt + 2 nt + {0, 1}].  The terms of the tile are contracted 4 at a time (nkg slices); lane q
- * supplies term q of each slice.  On the host (test emulation) the same sums are formed with scalar
+ * supplies term q of each slice; slices kg0 .. nkg - 1 are contracted.  On the host (test emulation) the same sums are formed with scalar
  * FMAs in the same term order. */
 template <int NA>
-CV_HD void cv_w_fused(int lane, const CvLaneGroup &G, int nkg, const CvWarpFixed &F, double *acc)
+CV_HD void cv_w_fused(int lane, const CvLaneGroup &G, int kg0, int nkg, const CvWarpFixed &F, double *acc)
 {
     const int r = lane >> 2, q = lane & 3;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
-    for (int kg = 0; kg < nkg; kg++) {
+    for (int kg = kg0; kg < nkg; kg++) {
         const int t = 4 * kg + q;
         double a[NA];
         cv_row_chain<NA>(F, G, r, t, a);
@@ -459,7 +471,7 @@ CV_HD void cv_w_fused(int lane, const CvLaneGroup &G, int nkg, const CvWarpFixed
         }
     }
 #else
-    for (int kg = 0; kg < nkg; kg++) {
+    for (int kg = kg0; kg < nkg; kg++) {
         double a[4][NA];
         for (int k = 0; k < 4; k++)
             cv_row_chain<NA>(F, G, r, 4 * kg + k, a[k]);

@@ -163,10 +163,11 @@ static inline std::string cv_build_tables(int n_bins, const int *bin_j, const do
             T.slot_bin[slot] = keys[b].second;
         }
     }
-    /* log(o) for every copy number the cut-off can reach (models.py:186: o < max(hist)) */
-    T.copy_log_h.assign((size_t)T.max_bin + 2, 0.0);
-    T.copy_log_l.assign((size_t)T.max_bin + 2, 0.0);
-    for (int o = 2; o <= T.max_bin + 1; o++) {
+    /* log(o) for every copy number the cut-off can reach (models.py:186: o < max(hist)), plus the
+     * few the profile kernel evaluates to fill its last slice of copies */
+    T.copy_log_h.assign((size_t)T.max_bin + 2 + CV_COPY_PAD, 0.0);
+    T.copy_log_l.assign((size_t)T.max_bin + 2 + CV_COPY_PAD, 0.0);
+    for (int o = 2; o <= T.max_bin + 1 + CV_COPY_PAD; o++) {
         cv_dd lg = cv_log_dd((double)o);
         T.copy_log_h[o] = lg.hi;
         T.copy_log_l[o] = lg.lo;

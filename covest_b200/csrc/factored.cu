@@ -1,0 +1,796 @@
+/*
+ * factored.cu -- batched evaluation of the repeats model as profiles x copy weights (factored.h).
+ *
+ *   cvf_point_keys      K0: per point clip, cut-off O_thr, sort key
+ *   cvf_heads / cvf_group_starts / cvf_group_counts / cvf_totals   group tables from the sorted keys
+ *   cvf_profile_kernel  K1: one warp per (group, 16 copy numbers): profiles over all bins
+ *   cvf_gemm_kernel     K2: one CTA per tile of 128 points: FP64 tensor-core GEMM + epilogue
+ *
+ * cub's device radix sort and prefix sums order the keys and lay out the group tables (plumbing);
+ * every likelihood flop is in the hand-written kernels of this file and of cvpoint.h.
+ *
+ * Reference lines are relative to /root/reference.
+ */
+#include "factored.h"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "kdevice.h"
+
+#define CVF_M 128       /* points per tile of K2 */
+#define CVF_NS 64       /* bins (slots) per N-step of K2 */
+#define CVF_KC 16       /* copy numbers per K-chunk */
+#define CVF_THREADS 256
+#define CVF_OBITS 20    /* bits of O_thr in the sort key */
+#define CVF_TILE_DOUBLES (CVF_KC * CVF_NS)
+
+/* device view of the plan of one batch */
+struct CvfPlan {
+    unsigned long long *keys, *keys_alt;
+    unsigned int *idx, *idx_alt; /* after the sort: point index by sorted position (in idx_sorted) */
+    const unsigned int *idx_sorted;
+    int *othr;       /* by ORIGINAL point index */
+    int *head, *gid; /* by sorted position */
+    int *g_start;    /* [n + 1] sorted position of the first point of a group */
+    int *tile_start; /* [n + 1] counts, then exclusive prefix */
+    int *item_start;
+    long long *w_off;
+    long long *header; /* n_groups, tiles, items, profile doubles */
+};
+
+/* slots a copy takes in a term tile of the profile kernel: S rounded up to a multiple of 4 */
+__host__ __device__ __forceinline__ int cvf_copy_slots(int n_err) { return (n_err + 3) & ~3; }
+/* copies per tile: the largest power of two that fits 32 lanes */
+__host__ __device__ __forceinline__ int cvf_copies_per_tile(int n_err)
+{
+    int c = 32 / cvf_copy_slots(n_err);
+    return c >= 8 ? 8 : c >= 4 ? 4 : c >= 2 ? 2 : 1;
+}
+
+bool cvf_supported(const CvModelDesc &m)
+{
+    return m.model_kind == 1 && m.n_err <= 32 && m.max_bin < (1 << CVF_OBITS) - CV_COPY_PAD;
+}
+
+__device__ __forceinline__ void cvf_raw_row(const CvModelDesc &m, const CvLattice &lat,
+                                            const double *__restrict__ params, long long i, double *row)
+{
+    if (lat.enabled) {
+        cv_lattice_point(lat, i, row);
+    } else {
+#pragma unroll
+        for (int a = 0; a < CV_MAX_PARAMS; a++)
+            row[a] = a < m.n_param ? params[i * m.n_param + a] : 0.0;
+    }
+}
+
+__device__ __forceinline__ double cvf_clipped(const CvModelDesc &m, const double *row, int clip, int a)
+{
+    return clip ? cv_clip(row[a], m.lo[a], m.hi[a]) : row[a];
+}
+
+/* models.py:185-191: the first o in [1, max(hist)) with b(o) <= threshold, else max(hist).  The
+ * geometric tail b(o) = many * base^(o-3) is searched from a closed-form estimate with the exact
+ * predicate; anything unusual (base outside (0, 1), non-positive threshold) is scanned. */
+__device__ int cvf_cutoff(const CvModelDesc &m, double q1, double two, double many, double base)
+{
+    const double thr = m.threshold;
+    const int top = m.max_bin;
+    if (!(thr == thr))
+        return top;
+    if (1 < top && q1 <= thr)
+        return 1;
+    if (2 < top && two <= thr)
+        return 2;
+    if (top <= 3)
+        return top;
+    if (many <= thr)
+        return 3;
+    if (!(many == many) || !(base == base))
+        return top; /* every comparison is false */
+    if (base > 0.0 && base < 1.0 && thr > 0.0 && many - many == 0.0) {
+        double est = 3.0 + log(thr / many) / log(base);
+        int o = est < (double)top ? (int)est - 1 : top - 1;
+        if (o < 3)
+            o = 3;
+        while (o < top && !(cv_copy_weight(o, q1, two, many, base) <= thr))
+            o++;
+        while (o > 3 && cv_copy_weight(o - 1, q1, two, many, base) <= thr)
+            o--;
+        return o < top ? o : top;
+    }
+    for (int o = 4; o < top; o++)
+        if (cv_copy_weight(o, q1, two, many, base) <= thr)
+            return o;
+    return top;
+}
+
+__device__ __forceinline__ unsigned int cvf_hash(double c, double e)
+{
+    unsigned long long x = (unsigned long long)__double_as_longlong(c) * 0x9E3779B97F4A7C15ULL;
+    x ^= (unsigned long long)__double_as_longlong(e) + 0xD6E8FEB86659FD93ULL + (x << 6) + (x >> 2);
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 29;
+    return (unsigned int)x;
+}
+
+/* K0 */
+__global__ void __launch_bounds__(256)
+cvf_point_keys(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
+               const double *__restrict__ params, long long n, int clip, CvfPlan pl)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    double row[CV_MAX_PARAMS];
+    cvf_raw_row(m, lat, params, i, row);
+    const double c = cvf_clipped(m, row, clip, 0), e = cvf_clipped(m, row, clip, 1);
+    const double q1 = cvf_clipped(m, row, clip, 2), q2 = cvf_clipped(m, row, clip, 3),
+                 q = cvf_clipped(m, row, clip, 4);
+    const double two = cv_mul(cv_sub(1.0, q1), q2);                          /* models.py:195 */
+    const double many = cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), q); /* models.py:196 */
+    const double base = cv_sub(1.0, q);
+    const int othr = cvf_cutoff(m, q1, two, many, base);
+    pl.othr[i] = othr;
+    pl.idx[i] = (unsigned int)i;
+    pl.keys[i] = ((unsigned long long)cvf_hash(c, e) << CVF_OBITS) | (unsigned long long)othr;
+}
+
+/* head[i] = 1 when sorted position i opens a group: its (c, e) differs from the position before */
+__global__ void __launch_bounds__(256)
+cvf_heads(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
+          const double *__restrict__ params, long long n, int clip, CvfPlan pl)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    int h = 1;
+    if (i > 0) {
+        double a[CV_MAX_PARAMS], b[CV_MAX_PARAMS];
+        cvf_raw_row(m, lat, params, pl.idx_sorted[i], a);
+        cvf_raw_row(m, lat, params, pl.idx_sorted[i - 1], b);
+        const long long c0 = __double_as_longlong(cvf_clipped(m, a, clip, 0));
+        const long long c1 = __double_as_longlong(cvf_clipped(m, b, clip, 0));
+        const long long e0 = __double_as_longlong(cvf_clipped(m, a, clip, 1));
+        const long long e1 = __double_as_longlong(cvf_clipped(m, b, clip, 1));
+        h = (c0 != c1) || (e0 != e1);
+    }
+    pl.head[i] = h;
+}
+
+__global__ void __launch_bounds__(256) cvf_group_starts(long long n, CvfPlan pl)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    if (pl.head[i])
+        pl.g_start[pl.gid[i] - 1] = (int)i;
+    if (i == n - 1) {
+        pl.header[0] = pl.gid[i];
+        pl.g_start[pl.gid[i]] = (int)n;
+    }
+}
+
+/* per group: tiles of K2, items of K1, doubles of its profiles; zeros past the last group so that
+ * the exclusive prefix sums end in the totals */
+__global__ void __launch_bounds__(256) cvf_group_counts(long long n, int slots_padded, CvfPlan pl)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n)
+        return;
+    const long long ng = pl.header[0];
+    int tiles = 0, items = 0;
+    long long w = 0;
+    if (g < ng) {
+        const int a = pl.g_start[g], b = pl.g_start[g + 1];
+        int omax = pl.othr[pl.idx_sorted[b - 1]] - 1; /* ascending O_thr inside a group */
+        if (omax < 0)
+            omax = 0;
+        tiles = (b - a + CVF_M - 1) / CVF_M;
+        items = (omax + CVF_KC - 1) / CVF_KC;
+        w = (long long)items * CVF_KC * slots_padded;
+    }
+    pl.tile_start[g] = tiles;
+    pl.item_start[g] = items;
+    pl.w_off[g] = w;
+}
+
+__global__ void cvf_totals(CvfPlan pl)
+{
+    const long long ng = pl.header[0];
+    pl.header[1] = pl.tile_start[ng];
+    pl.header[2] = pl.item_start[ng];
+    pl.header[3] = pl.w_off[ng];
+}
+
+/* largest g in [0, n) with start[g] <= x (start ascending, start[0] <= x) */
+__device__ __forceinline__ int cvf_find(const int *__restrict__ start, int n, int x)
+{
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (start[mid] <= x)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* K1: profiles                                                                                 */
+/* ------------------------------------------------------------------------------------------- */
+/* Position (in doubles) of (copy o, slot) inside the profiles of a group: tiles of 16 copies x 64
+ * slots, [K-chunk][N-step]; inside a tile the order in which a warp of K2 reads its B fragments:
+ * [N half wn][K slice ks][n-tile pair np][lane = (slot % 8) * 4 + (o - 1) % 4][n-tile parity]. */
+__host__ __device__ __forceinline__ long long cvf_w_index(int o, int slot, int nsteps)
+{
+    const int k = o - 1;
+    const int kchunk = k >> 4, ks = (k >> 2) & 3, q = k & 3;
+    const int nstep = slot >> 6, s64 = slot & 63;
+    const int wn = s64 >> 5, nt = (s64 >> 3) & 3, r = s64 & 7;
+    const int in_tile = ((((wn * 4 + ks) * 2 + (nt >> 1)) * 32 + r * 4 + q) * 2) + (nt & 1);
+    return ((long long)kchunk * nsteps + nstep) * CVF_TILE_DOUBLES + in_tile;
+}
+
+/* The accumulators of a lane after the slices of ONE copy are its share of the profile of that
+ * copy over block `blk`: rows mt of group r, columns 8 nt + 2 q + c.  The two column tiles of a
+ * row land next to each other (n-tile parity), so every store is 16 bytes. */
+template <int NA>
+__device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int nsteps,
+                                                  double *__restrict__ Wg, const double *acc)
+{
+    const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < NA; mt++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int slot = ((blk * CV_GB + r) * NA + mt) * CV_W + 2 * q + c; /* column tile 0 */
+            const long long at = cvf_w_index(o, slot, nsteps);
+            *reinterpret_cast<double2 *>(Wg + at) = make_double2(acc[4 * mt + c], acc[4 * mt + 2 + c]);
+        }
+}
+
+template <int NA>
+__device__ __forceinline__ void cvf_profile_item(int lane, const CvModelDesc &m, CvWarpMem &M,
+                                                 int o0, int omax4, int nsteps, double *__restrict__ Wg)
+{
+    const int sp = cvf_copy_slots(m.n_err);
+    const int cpt = cvf_copies_per_tile(m.n_err);
+    const int kpc = sp >> 2; /* MMA slices per copy */
+    for (int oa = o0; oa < o0 + CVF_KC && oa <= omax4; oa += cpt) {
+        cv_w_mass(lane, m, oa, cpt * sp, sp, M);
+        __syncwarp();
+        const CvTerm tm = cv_w_term(lane, m, oa, cpt * sp, sp, 0, 1.0, M);
+        for (int blk = 0; blk < m.n_blocks; blk++) {
+            const CvLaneGroup G = cv_lane_group(lane, m, blk, M);
+            cv_w_prep<NA>(lane, m, blk, tm, M);
+            __syncwarp();
+            for (int cc = 0; cc < cpt; cc++) {
+                double acc[4 * NA];
+#pragma unroll
+                for (int i = 0; i < 4 * NA; i++)
+                    acc[i] = 0.0;
+                cv_w_fused<NA>(lane, G, cc * kpc, (cc + 1) * kpc, *M.fx, acc);
+                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, Wg, acc);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * CV_WARPS_MAX, 1)
+cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
+                   const double *__restrict__ params, int clip, CvfPlan pl, int n_groups,
+                   int first_item, int n_items, double *__restrict__ W, long long w_base, int nsteps,
+                   unsigned long long *counter, int groups_staged)
+{
+    extern __shared__ __align__(16) unsigned char cv_smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int S = m.n_err;
+    CvWarpMem M;
+    {
+        double *tab = reinterpret_cast<double *>(cv_smem_raw);
+        const int ntab = groups_staged * CV_GD;
+        unsigned char *wbase = cv_smem_raw + (size_t)ntab * sizeof(double) + (size_t)warp * cv_warp_bytes(S);
+        CvWarpFixed *fx = reinterpret_cast<CvWarpFixed *>(wbase);
+        cv_warp_mem_carve(M, fx, reinterpret_cast<double *>(wbase + sizeof(CvWarpFixed)), S);
+        for (int i = threadIdx.x; i < ntab; i += blockDim.x)
+            tab[i] = m.tab.grp[i];
+        M.grp = tab;
+    }
+    __syncthreads();
+    for (;;) {
+        long long it = 0;
+        if (lane == 0)
+            it = (long long)atomicAdd(counter, 1ULL);
+        it = __shfl_sync(CV_FULL_MASK, it, 0);
+        if (it >= n_items)
+            break;
+        const int item = first_item + (int)it;
+        const int g = cvf_find(pl.item_start, n_groups, item);
+        const int kchunk = item - pl.item_start[g];
+        const int a = pl.g_start[g], b = pl.g_start[g + 1];
+        int omax = pl.othr[pl.idx_sorted[b - 1]] - 1;
+        const int omax4 = (omax + 3) & ~3;
+        double row[CV_MAX_PARAMS];
+        cvf_raw_row(m, lat, params, pl.idx_sorted[a], row);
+        __syncwarp();
+        cv_w_header(lane, m, row, clip, M);
+        __syncwarp();
+        double *Wg = W + (pl.w_off[g] - w_base);
+        const int o0 = kchunk * CVF_KC + 1;
+        switch (m.na) {
+        case 1: cvf_profile_item<1>(lane, m, M, o0, omax4, nsteps, Wg); break;
+        case 2: cvf_profile_item<2>(lane, m, M, o0, omax4, nsteps, Wg); break;
+        case 4: cvf_profile_item<4>(lane, m, M, o0, omax4, nsteps, Wg); break;
+        default: cvf_profile_item<8>(lane, m, M, o0, omax4, nsteps, Wg); break;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* K2: GEMM + epilogue                                                                          */
+/* ------------------------------------------------------------------------------------------- */
+struct CvfSmem {
+    double2 Bs[3][CVF_TILE_DOUBLES / 2];          /* profile tiles in flight, fragment order */
+    double2 As[2][CVF_M * CVF_KC / 2];            /* copy weights of the current chunk, fragment order */
+    double q1[CVF_M], two[CVF_M], many[CVF_M], base[CVF_M];
+    double red_sum[2][CVF_M];
+    double red_mh[2][CVF_M], red_ml[2][CVF_M];
+    int othr[CVF_M];
+    unsigned int pidx[CVF_M];
+    int tile;
+};
+
+__device__ __forceinline__ void cvf_cp_async16(void *dst_smem, const void *src)
+{
+    unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cvf_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cvf_cp_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+__device__ __forceinline__ void cvf_cp_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ void cvf_two_sum_acc(double &hi, double &lo, double x)
+{
+    cv_dd s = cv_two_sum(hi, x);
+    hi = s.hi;
+    lo = cv_add(lo, s.lo);
+}
+
+__global__ void __launch_bounds__(CVF_THREADS, 2)
+cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
+                const double *__restrict__ params, int clip, CvfPlan pl, int n_groups, int first_tile,
+                int n_tiles, const double *__restrict__ W, long long w_base,
+                const double2 *__restrict__ slot_mh, int nsteps, double *__restrict__ out_ll,
+                unsigned long long *counter)
+{
+    extern __shared__ __align__(16) unsigned char cvf_smem_raw[];
+    CvfSmem &S = *reinterpret_cast<CvfSmem *>(cvf_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int r = lane >> 2, q = lane & 3;
+    const int apos = r * 4 + (q ^ ((r >> 1) & 3)); /* swizzled position of the lane's A chunk */
+    /* generator role: point gp of the tile, copies 8 half + 1 .. 8 half + 8 of every chunk */
+    const int gp = (tid & 15) + 16 * (tid >> 5), half = (tid >> 4) & 1;
+    const int g_wm = gp >> 5, g_mt = (gp >> 3) & 3, g_r = gp & 7;
+    const bool want_mass = m.tail != 0.0;
+
+    for (;;) {
+        __syncthreads(); /* the previous tile's readers of shared memory are done */
+        if (tid == 0)
+            S.tile = (int)atomicAdd(counter, 1ULL);
+        __syncthreads();
+        if (S.tile >= n_tiles)
+            break;
+        const int tile = first_tile + S.tile;
+        const int g = cvf_find(pl.tile_start, n_groups, tile);
+        const int pfirst = pl.g_start[g] + (tile - pl.tile_start[g]) * CVF_M;
+        const int cnt = min(CVF_M, pl.g_start[g + 1] - pfirst);
+        if (tid < CVF_M) {
+            double q1 = 0.0, two = 0.0, many = 0.0, base = 0.0;
+            int othr = 0;
+            unsigned int pi = 0;
+            if (tid < cnt) {
+                pi = pl.idx_sorted[pfirst + tid];
+                double row[CV_MAX_PARAMS];
+                cvf_raw_row(m, lat, params, pi, row);
+                q1 = cvf_clipped(m, row, clip, 2);
+                const double q2 = cvf_clipped(m, row, clip, 3), qq = cvf_clipped(m, row, clip, 4);
+                two = cv_mul(cv_sub(1.0, q1), q2);
+                many = cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), qq);
+                base = cv_sub(1.0, qq);
+                othr = pl.othr[pi];
+            }
+            S.q1[tid] = q1;
+            S.two[tid] = two;
+            S.many[tid] = many;
+            S.base[tid] = base;
+            S.othr[tid] = othr;
+            S.pidx[tid] = pi;
+        }
+        __syncthreads();
+        int kmax = S.othr[cnt - 1] - 1; /* ascending inside the tile */
+        if (kmax < 0)
+            kmax = 0;
+        const int nkc = (kmax + CVF_KC - 1) / CVF_KC;
+        const double *Wg = W + (pl.w_off[g] - w_base);
+        const int total = nsteps * nkc;
+
+        /* generator constants of this thread's point */
+        const double g_q1 = S.q1[gp], g_two = S.two[gp], g_many = S.many[gp], g_base = S.base[gp];
+        const int g_othr = S.othr[gp];
+        const double b2 = cv_mul(g_base, g_base), b4 = cv_mul(b2, b2), b8 = cv_mul(b4, b4);
+        const double b16 = cv_mul(b8, b8);
+        /* b(o) of the first copy of the thread's half in chunk 0 (half 1: o = 9) resp. chunk 1 */
+        const double cur0 = half ? cv_mul(g_many, cv_mul(b4, b2)) : cv_mul(g_many, cv_mul(b8, cv_mul(b4, b2)));
+
+        auto issue = [&](int t) {
+            if (t < total) {
+                const int kc = t % nkc, ns = t / nkc;
+                const double2 *src = reinterpret_cast<const double2 *>(
+                    Wg + ((long long)kc * nsteps + ns) * CVF_TILE_DOUBLES);
+                double2 *dst = S.Bs[t % 3];
+                cvf_cp_async16(dst + tid, src + tid);
+                cvf_cp_async16(dst + tid + CVF_THREADS, src + tid + CVF_THREADS);
+            }
+            cvf_cp_commit();
+        };
+        issue(0);
+        issue(1);
+
+        double sum[4] = {0.0, 0.0, 0.0, 0.0};
+        double mass_h[4] = {0.0, 0.0, 0.0, 0.0}, mass_l[4] = {0.0, 0.0, 0.0, 0.0};
+        int t = 0;
+        for (int ns = 0; ns < nsteps; ns++) {
+            double acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                acc[i] = 0.0;
+            double cur = cur0;
+            for (int kc = 0; kc < nkc; kc++, t++) {
+                /* copy weights of the chunk: models.py:193-208 as a running product */
+                {
+                    double v[8];
+                    if (kc == 0 && half == 0) {
+                        v[0] = g_q1;
+                        v[1] = g_two;
+                        v[2] = g_many;
+#pragma unroll
+                        for (int i = 3; i < 8; i++)
+                            v[i] = cv_mul(v[i - 1], g_base);
+                    } else {
+                        v[0] = cur;
+#pragma unroll
+                        for (int i = 1; i < 8; i++)
+                            v[i] = cv_mul(v[i - 1], g_base);
+                        cur = cv_mul(cur, b16);
+                    }
+                    const int o_first = kc * CVF_KC + 8 * half + 1;
+                    double *as = reinterpret_cast<double *>(S.As[t & 1]);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int ks = 2 * half + (i >> 2), qq = i & 3;
+                        const int at = (((g_wm * 4 + ks) * 2 + (g_mt >> 1)) * 32 + g_r * 4 +
+                                        (qq ^ ((g_r >> 1) & 3))) * 2 + (g_mt & 1);
+                        as[at] = (o_first + i < g_othr) ? v[i] : 0.0; /* models.py:235: o < O_thr */
+                    }
+                }
+                cvf_cp_wait1();
+                __syncthreads(); /* weights written, profile tile t landed */
+                issue(t + 2);
+                const int nks = min(4, (kmax - kc * CVF_KC + 3) >> 2);
+                const double2 *as2 = S.As[t & 1];
+                const double2 *bs2 = S.Bs[t % 3];
+                for (int ks = 0; ks < nks; ks++) {
+                    const double2 a01 = as2[((wm * 4 + ks) * 2 + 0) * 32 + apos];
+                    const double2 a23 = as2[((wm * 4 + ks) * 2 + 1) * 32 + apos];
+                    const double2 b01 = bs2[((wn * 4 + ks) * 2 + 0) * 32 + lane];
+                    const double2 b23 = bs2[((wn * 4 + ks) * 2 + 1) * 32 + lane];
+                    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++)
+                            cv_dmma(acc[(mt * 4 + nt) * 2], acc[(mt * 4 + nt) * 2 + 1], a[mt], b[nt]);
+                }
+            }
+            /* epilogue of the N-step, models.py:100-107: the lane holds points 32 wm + 8 mt + r and
+             * slots 64 ns + 32 wn + 8 nt + 2 q + c */
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int slot = ns * CVF_NS + 32 * wn + 8 * nt + 2 * q + c;
+                    const double2 mh = __ldg(slot_mh + slot);
+                    const bool in_hist = mh.x != 0.0;
+                    const bool counted = mh.y != 0.0; /* models.py:106 `if h` */
+                    double p[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; mt++)
+                        p[mt] = in_hist ? cv_mul(acc[(mt * 4 + nt) * 2 + c], mh.x) : 0.0;
+                    if (want_mass) {
+#pragma unroll
+                        for (int mt = 0; mt < 4; mt++)
+                            cvf_two_sum_acc(mass_h[mt], mass_l[mt], p[mt]);
+                    }
+                    if (__any_sync(CV_FULL_MASK, counted)) {
+#pragma unroll
+                        for (int mt = 0; mt < 4; mt++) {
+                            double lg = (p[mt] <= 0.0) ? -INFINITY : log(p[mt]); /* utils.py:32-35 */
+                            if (counted)
+                                sum[mt] = cv_add(sum[mt], cv_mul(mh.y, lg));
+                        }
+                    }
+                }
+        }
+        cvf_cp_wait0();
+        /* the four lanes of a quad hold different slots of the same points */
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+#pragma unroll
+            for (int d = 1; d <= 2; d <<= 1) {
+                sum[mt] = cv_add(sum[mt], __shfl_xor_sync(CV_FULL_MASK, sum[mt], d));
+                if (want_mass) {
+                    double oh = __shfl_xor_sync(CV_FULL_MASK, mass_h[mt], d);
+                    double ol = __shfl_xor_sync(CV_FULL_MASK, mass_l[mt], d);
+                    cvf_two_sum_acc(mass_h[mt], mass_l[mt], oh);
+                    mass_l[mt] = cv_add(mass_l[mt], ol);
+                }
+            }
+            if (q == 0) {
+                const int pt = 32 * wm + 8 * mt + r;
+                S.red_sum[wn][pt] = sum[mt];
+                S.red_mh[wn][pt] = mass_h[mt];
+                S.red_ml[wn][pt] = mass_l[mt];
+            }
+        }
+        __syncthreads();
+        if (tid < cnt) {
+            CvPartial part;
+            part.sum = cv_add(S.red_sum[0][tid], S.red_sum[1][tid]);
+            part.mass_h = S.red_mh[0][tid];
+            part.mass_l = S.red_ml[0][tid];
+            cvf_two_sum_acc(part.mass_h, part.mass_l, S.red_mh[1][tid]);
+            part.mass_l = cv_add(part.mass_l, S.red_ml[1][tid]);
+            out_ll[S.pidx[tid]] = cv_point_finish(m, part);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* host side                                                                                    */
+/* ------------------------------------------------------------------------------------------- */
+void cvf_release(CvFactorWork &wk)
+{
+    if (wk.plan)
+        cudaFree(wk.plan);
+    if (wk.W)
+        cudaFree(wk.W);
+    if (wk.h_header)
+        cudaFreeHost(wk.h_header);
+    if (wk.d_counters)
+        cudaFree(wk.d_counters);
+    for (cudaEvent_t &e : wk.ev)
+        if (e) {
+            cudaEventDestroy(e);
+            e = nullptr;
+        }
+    wk.plan = nullptr;
+    wk.W = nullptr;
+    wk.h_header = nullptr;
+    wk.d_counters = nullptr;
+    wk.plan_cap = wk.w_cap = 0;
+}
+
+static size_t cvf_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+#define CVF_CK(call)              \
+    do {                          \
+        cudaError_t e_ = (call);  \
+        if (e_ != cudaSuccess)    \
+            return e_;            \
+    } while (0)
+
+cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
+                     int clip, double *out_ll, const double2 *slot_mh, CvFactorWork &wk, int n_sm,
+                     int smem_max, size_t w_limit, double min_group, cudaStream_t stream, int *used)
+{
+    *used = 0;
+    wk.launches = 0;
+    if (n <= 0 || n > 0x7fffffffLL || !cvf_supported(m))
+        return cudaSuccess;
+    const int slots_padded = m.n_blocks * CV_GB * m.na * CV_W;
+    const int nsteps = slots_padded / CVF_NS;
+
+    /* ---- carve the plan ---- */
+    size_t sort_tmp = 0, scan_tmp_i = 0, scan_tmp_l = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned long long *)nullptr,
+                                    (unsigned long long *)nullptr, (unsigned int *)nullptr,
+                                    (unsigned int *)nullptr, (int)n, 0, 32 + CVF_OBITS, stream);
+    cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_i, (int *)nullptr, (int *)nullptr, (int)n + 1, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_l, (long long *)nullptr, (long long *)nullptr,
+                                  (int)n + 1, stream);
+    const size_t tmp_bytes = std::max(sort_tmp, std::max(scan_tmp_i, scan_tmp_l)) + 256;
+    const size_t n1 = (size_t)n + 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off += cvf_align(bytes);
+        return at;
+    };
+    const size_t o_keys = take(n * 8), o_keys_alt = take(n * 8), o_idx = take(n * 4), o_idx_alt = take(n * 4);
+    const size_t o_othr = take(n * 4), o_head = take(n * 4), o_gid = take(n * 4);
+    const size_t o_gstart = take(n1 * 4), o_tile = take(n1 * 4), o_item = take(n1 * 4), o_woff = take(n1 * 8);
+    const size_t o_header = take(64), o_tmp = take(tmp_bytes);
+    if (off > wk.plan_cap) {
+        if (wk.plan)
+            cudaFree(wk.plan);
+        wk.plan = nullptr;
+        wk.plan_cap = 0;
+        CVF_CK(cudaMalloc(&wk.plan, off));
+        wk.plan_cap = off;
+    }
+    if (!wk.h_header)
+        CVF_CK(cudaMallocHost((void **)&wk.h_header, 64));
+    if (!wk.d_counters)
+        CVF_CK(cudaMalloc((void **)&wk.d_counters, 2 * sizeof(unsigned long long)));
+    if (wk.timed && !wk.ev[0])
+        for (cudaEvent_t &e : wk.ev)
+            CVF_CK(cudaEventCreate(&e));
+    unsigned char *base = (unsigned char *)wk.plan;
+    CvfPlan pl;
+    pl.keys = (unsigned long long *)(base + o_keys);
+    pl.keys_alt = (unsigned long long *)(base + o_keys_alt);
+    pl.idx = (unsigned int *)(base + o_idx);
+    pl.idx_alt = (unsigned int *)(base + o_idx_alt);
+    pl.idx_sorted = nullptr;
+    pl.othr = (int *)(base + o_othr);
+    pl.head = (int *)(base + o_head);
+    pl.gid = (int *)(base + o_gid);
+    pl.g_start = (int *)(base + o_gstart);
+    pl.tile_start = (int *)(base + o_tile);
+    pl.item_start = (int *)(base + o_item);
+    pl.w_off = (long long *)(base + o_woff);
+    pl.header = (long long *)(base + o_header);
+    void *tmp = base + o_tmp;
+
+    const int tb = 256;
+    const unsigned int nb = (unsigned int)((n + tb - 1) / tb), nb1 = (unsigned int)((n + 1 + tb - 1) / tb);
+    if (wk.timed)
+        CVF_CK(cudaEventRecord(wk.ev[0], stream));
+    cvf_point_keys<<<nb, tb, 0, stream>>>(m, lat, params, n, clip, pl);
+    CVF_CK(cudaGetLastError());
+    {
+        cub::DoubleBuffer<unsigned long long> dk(pl.keys, pl.keys_alt);
+        cub::DoubleBuffer<unsigned int> dv(pl.idx, pl.idx_alt);
+        size_t tb_ = tmp_bytes;
+        CVF_CK(cub::DeviceRadixSort::SortPairs(tmp, tb_, dk, dv, (int)n, 0, 32 + CVF_OBITS, stream));
+        pl.idx_sorted = dv.Current();
+    }
+    cvf_heads<<<nb, tb, 0, stream>>>(m, lat, params, n, clip, pl);
+    CVF_CK(cudaGetLastError());
+    {
+        size_t tb_ = tmp_bytes;
+        CVF_CK(cub::DeviceScan::InclusiveSum(tmp, tb_, pl.head, pl.gid, (int)n, stream));
+    }
+    cvf_group_starts<<<nb, tb, 0, stream>>>(n, pl);
+    CVF_CK(cudaGetLastError());
+    cvf_group_counts<<<nb1, tb, 0, stream>>>(n, slots_padded, pl);
+    CVF_CK(cudaGetLastError());
+    {
+        size_t tb_ = tmp_bytes;
+        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.tile_start, pl.tile_start, (int)n + 1, stream));
+        tb_ = tmp_bytes;
+        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.item_start, pl.item_start, (int)n + 1, stream));
+        tb_ = tmp_bytes;
+        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.w_off, pl.w_off, (int)n + 1, stream));
+    }
+    cvf_totals<<<1, 1, 0, stream>>>(pl);
+    CVF_CK(cudaGetLastError());
+    CVF_CK(cudaMemcpyAsync(wk.h_header, pl.header, 4 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    CVF_CK(cudaStreamSynchronize(stream));
+    wk.launches += 9;
+    const long long n_groups = wk.h_header[0], n_tiles = wk.h_header[1], n_items = wk.h_header[2];
+    const long long w_total = wk.h_header[3];
+    wk.n_groups = n_groups;
+    wk.n_tiles = n_tiles;
+    wk.n_items = n_items;
+    wk.w_doubles = w_total;
+    if (n_groups <= 0 || (double)n < min_group * (double)n_groups)
+        return cudaSuccess; /* too little sharing: the per-point kernel is the better tool */
+
+    /* ---- group ranges that fit the workspace ---- */
+    std::vector<int> cut; /* group boundaries */
+    cut.push_back(0);
+    std::vector<int> h_tile, h_item;
+    std::vector<long long> h_woff;
+    if ((size_t)w_total > w_limit) {
+        h_tile.resize(n_groups + 1);
+        h_item.resize(n_groups + 1);
+        h_woff.resize(n_groups + 1);
+        CVF_CK(cudaMemcpyAsync(h_tile.data(), pl.tile_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
+        CVF_CK(cudaMemcpyAsync(h_item.data(), pl.item_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
+        CVF_CK(cudaMemcpyAsync(h_woff.data(), pl.w_off, (n_groups + 1) * 8, cudaMemcpyDeviceToHost, stream));
+        CVF_CK(cudaStreamSynchronize(stream));
+        int g0 = 0;
+        while (g0 < n_groups) {
+            int g1 = g0 + 1;
+            while (g1 < n_groups && (size_t)(h_woff[g1 + 1] - h_woff[g0]) <= w_limit)
+                g1++;
+            cut.push_back(g1);
+            g0 = g1;
+        }
+    } else {
+        cut.push_back((int)n_groups);
+    }
+    size_t w_need = 0;
+    for (size_t i = 0; i + 1 < cut.size(); i++) {
+        long long a = h_woff.empty() ? 0 : h_woff[cut[i]];
+        long long b = h_woff.empty() ? w_total : h_woff[cut[i + 1]];
+        w_need = std::max(w_need, (size_t)(b - a));
+    }
+    if (w_need > wk.w_cap) {
+        if (wk.W)
+            cudaFree(wk.W);
+        wk.W = nullptr;
+        wk.w_cap = 0;
+        CVF_CK(cudaMalloc((void **)&wk.W, std::max(w_need, (size_t)1) * sizeof(double)));
+        wk.w_cap = w_need;
+    }
+
+    /* ---- K1 / K2 per range ---- */
+    const size_t wb = cv_warp_bytes(m.n_err);
+    const int groups_staged = m.n_blocks * CV_GB;
+    const size_t tab = (size_t)groups_staged * CV_GD * sizeof(double);
+    int k1_warps = (int)std::min<long long>(CV_WARPS_MAX, ((long long)smem_max - (long long)tab) / (long long)wb);
+    if (k1_warps < 1)
+        return cudaErrorInvalidConfiguration;
+    const size_t k1_smem = tab + (size_t)k1_warps * wb;
+    CVF_CK(cudaFuncSetAttribute(cvf_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
+    CVF_CK(cudaFuncSetAttribute(cvf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(CvfSmem)));
+    if (wk.timed)
+        CVF_CK(cudaEventRecord(wk.ev[1], stream));
+    for (size_t i = 0; i + 1 < cut.size(); i++) {
+        const int g0 = cut[i], g1 = cut[i + 1];
+        const int item0 = h_item.empty() ? 0 : h_item[g0], item1 = h_item.empty() ? (int)n_items : h_item[g1];
+        const int tile0 = h_tile.empty() ? 0 : h_tile[g0], tile1 = h_tile.empty() ? (int)n_tiles : h_tile[g1];
+        const long long w0 = h_woff.empty() ? 0 : h_woff[g0];
+        CVF_CK(cudaMemsetAsync(wk.d_counters, 0, 2 * sizeof(unsigned long long), stream));
+        if (item1 > item0) {
+            const int items = item1 - item0;
+            int grid = (items + k1_warps - 1) / k1_warps;
+            if (grid > n_sm)
+                grid = n_sm;
+            cvf_profile_kernel<<<grid, 32 * k1_warps, k1_smem, stream>>>(
+                m, lat, params, clip, pl, (int)n_groups, item0, items, wk.W, w0, nsteps, wk.d_counters,
+                groups_staged);
+            CVF_CK(cudaGetLastError());
+            wk.launches++;
+        }
+        if (wk.timed && i + 2 == cut.size())
+            CVF_CK(cudaEventRecord(wk.ev[2], stream));
+        if (tile1 > tile0) {
+            const int tiles = tile1 - tile0;
+            int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;
+            cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(
+                m, lat, params, clip, pl, (int)n_groups, tile0, tiles, wk.W, w0, slot_mh, nsteps, out_ll,
+                wk.d_counters + 1);
+            CVF_CK(cudaGetLastError());
+            wk.launches++;
+        }
+    }
+    if (wk.timed)
+        CVF_CK(cudaEventRecord(wk.ev[3], stream));
+    *used = 1;
+    return cudaSuccess;
+}

@@ -1,0 +1,52 @@
+/*
+ * factored.h -- the batched ("factored") evaluation of the repeats model: launch interface between
+ * the C ABI (capi.cu) and factored.cu.
+ *
+ * The reference evaluates p_j = sum_o b(o) * [sum_s a_os * tp(o*l_s, j)] (models.py:235-241).  The
+ * bracket -- the *profile* of copy number o -- depends on (coverage, error rate) only, the weight
+ * b(o) on (q1, q2, q) only (models.py:193-208).  A batch of parameter points (an initial grid, a
+ * grid-search round, the stencils of a multi-start refinement) holds few distinct (c, e) pairs and
+ * many (q1, q2, q) per pair, so the batch is evaluated as
+ *
+ *   K0  per point: clip (models.py:60-69), cut-off O_thr (models.py:185-191), a sort key
+ *       (hash of (c, e), O_thr); radix sort; groups = runs of equal (c, e), ascending O_thr inside
+ *   K1  per group and copy number o <= max O_thr of the group: the profile over all bins, with the
+ *       machinery of the per-point kernel (cvpoint.h), written to HBM in the fragment order K2 reads
+ *   K2  per tile of 128 points of one group: P[point][bin] = sum_o b_point(o) * profile[o][bin] as a
+ *       dense FP64 GEMM on the tensor cores (m8n8k4), b(o) generated on the fly in shared memory,
+ *       then the epilogue of models.py:100-107 straight from the accumulators
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+struct CvFactorWork {
+    void *plan = nullptr; /* sort keys, indices, group tables, cub scratch */
+    size_t plan_cap = 0;
+    double *W = nullptr;  /* profiles */
+    size_t w_cap = 0;     /* doubles */
+    long long *h_header = nullptr; /* pinned host: n_groups, tiles, items, profile doubles */
+    std::size_t h_arrays_cap = 0;
+    unsigned long long *d_counters = nullptr; /* two device words */
+    /* timing of the most recent evaluation (events recorded when `timed`) */
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    /* facts about the most recent evaluation */
+    long long n_groups = 0, n_tiles = 0, n_items = 0, w_doubles = 0;
+    int launches = 0;
+    double gemm_fma = 0.0; /* FMAs the tiles of K2 issue (128 rows x padded copies x padded slots) */
+};
+
+/* Can this context use the factored path at all (repeats model, few enough error classes)? */
+bool cvf_supported(const CvModelDesc &m);
+
+/* Evaluates n points.  *used = 0 when the batch does not group well enough (nothing written to
+ * out_ll; the caller runs the per-point kernel).  `slot_mh` = (slot_mult, slot_h) pairs, device.
+ * w_limit = largest profile workspace in doubles; larger batches run in several group ranges. */
+cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
+                     int clip, double *out_ll, const double2 *slot_mh, CvFactorWork &wk, int n_sm,
+                     int smem_max, size_t w_limit, double min_group, cudaStream_t stream, int *used);
+
+void cvf_release(CvFactorWork &wk);

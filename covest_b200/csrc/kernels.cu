@@ -16,21 +16,7 @@
 
 #include <cstdlib>
 
-#define CV_FULL_MASK 0xffffffffu
-
-__device__ __forceinline__ void cv_lattice_point(const CvLattice &lat, long long i, double *row)
-{
-    long long idx = lat.first + i * lat.stride;
-#pragma unroll
-    for (int a = CV_MAX_PARAMS - 1; a >= 0; a--) {
-        if (a < lat.n_axes) {
-            int n = lat.len[a];
-            long long q = idx / n;
-            row[a] = lat.axis[a][(int)(idx - q * n)];
-            idx = q;
-        }
-    }
-}
+#include "kdevice.h"
 
 __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, int delta)
 {
@@ -39,14 +25,6 @@ __device__ __forceinline__ CvPartial cv_partial_shfl_down(const CvPartial &p, in
     q.mass_h = __shfl_down_sync(CV_FULL_MASK, p.mass_h, delta);
     q.mass_l = __shfl_down_sync(CV_FULL_MASK, p.mass_l, delta);
     return q;
-}
-
-/* shared memory of a CTA: the group records (groups_staged * CV_GD doubles), then per warp a
- * CvWarpFixed followed by its variable part */
-__host__ __device__ __forceinline__ size_t cv_warp_bytes(int n_err)
-{
-    size_t b = sizeof(CvWarpFixed) + (size_t)cv_warp_var_doubles(n_err) * sizeof(double);
-    return (b + 15) & ~(size_t)15;
 }
 
 /* All blocks of one point: for every block the tiles of mixture terms are prepared (one term per
@@ -73,16 +51,16 @@ __device__ __forceinline__ void cv_point_blocks(int lane, const CvModelDesc &m, 
             for (int g = 0; g < nlive; g += cpg) {
                 const int ncop = min(cpg, nlive - g);
                 const int nterms = ncop * S;
-                cv_w_mass(lane, m, first + g, nterms, M);
+                cv_w_mass(lane, m, first + g, nterms, S, M);
                 __syncwarp();
                 for (int sub = 0; sub < nterms; sub += CV_CT) {
                     int src = g + (sub + lane) / S; /* the lane that holds this term's b(o) */
                     double bt = __shfl_sync(CV_FULL_MASK, b, src < 31 ? src : 31);
-                    const CvTerm tm = cv_w_term(lane, m, first + g, nterms, sub, bt, M);
+                    const CvTerm tm = cv_w_term(lane, m, first + g, nterms, S, sub, bt, M);
                     cv_w_prep<NA>(lane, m, blk, tm, M);
                     __syncwarp();
                     const int nkg = (min(CV_CT, nterms - sub) + 3) >> 2;
-                    cv_w_fused<NA>(lane, G, nkg, *M.fx, acc);
+                    cv_w_fused<NA>(lane, G, 0, nkg, *M.fx, acc);
                     __syncwarp();
                 }
             }

@@ -213,6 +213,22 @@ class LikelihoodContext:
                     'cvb_last_kernel_ms')
         return ms.value, n.value
 
+    PATH_AUTO, PATH_PER_POINT, PATH_FACTORED = 0, 1, 2
+
+    def set_path(self, mode):
+        """Evaluation path of the repeats model: PATH_AUTO, PATH_PER_POINT or PATH_FACTORED
+        (include/covest_b200.h, cvb_set_path)."""
+        self._check(self._lib.cvb_set_path(self._ctx, int(mode)), 'cvb_set_path')
+
+    def last_path_info(self):
+        """Facts about the most recent evaluation (cvb_last_path_info)."""
+        buf = (ctypes.c_double * 8)()
+        self._check(self._lib.cvb_last_path_info(self._ctx, buf, 8), 'cvb_last_path_info')
+        v = list(buf)
+        return {'path': {1: 'per-point', 2: 'factored'}.get(int(v[0]), 'none'), 'groups': int(v[1]),
+                'tiles': int(v[2]), 'items': int(v[3]), 'profile_doubles': int(v[4]),
+                'plan_ms': v[5], 'profile_ms': v[6], 'gemm_ms': v[7]}
+
     @property
     def sm_count(self):
         return self._lib.cvb_device_sm_count(self._ctx)

@@ -115,6 +115,24 @@ CVB_API int cvb_fp64_peak(cvb_ctx *ctx, int kind, int reps, double *out_tflops);
 CVB_API int cvb_set_timing(cvb_ctx *ctx, int enabled);
 CVB_API int cvb_last_kernel_ms(cvb_ctx *ctx, double *out_ms, int *out_launches);
 
+/* Evaluation path of the repeats model.  A batch is evaluated either point by point
+ * (cv_loglik_kernel: one warp per point, reference models.py:211-242 term by term) or *factored*:
+ * the per-copy-number bin profiles sum_s a_os * tp(o * l_s, j) -- the inner sum of models.py:236 --
+ * are computed once per distinct (coverage, error_rate) of the batch and contracted with the copy
+ * weights b(o) of every point (models.py:193-208) by an FP64 tensor-core GEMM.  mode 0 = automatic
+ * (factored for batches of >= 2048 points with >= 12 points per distinct (c, e)), 1 = per-point
+ * only, 2 = factored whenever the model supports it.  The environment variable
+ * COVEST_B200_PATH=direct|factored|auto sets the initial mode.  Per-bin probabilities
+ * (cvb_probs_batch) always use the per-point kernel. */
+CVB_API int cvb_set_path(cvb_ctx *ctx, int mode);
+
+/* Facts about the most recent evaluation: out[0] = path used (1 per-point, 2 factored); for the
+ * factored path out[1] = distinct (c, e) groups, out[2] = 128-point tiles, out[3] = profile items
+ * (16 copy numbers each), out[4] = doubles of profile workspace, out[5..7] = device ms of the
+ * planning kernels, the profile kernel and the GEMM kernel (after cvb_set_timing(ctx, 1)). */
+#define CVB_PATH_INFO_LEN 8
+CVB_API int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out);
+
 /* number of model parameters of the context (2 or 5), number of SMs of its device */
 CVB_API int cvb_n_param(const cvb_ctx *ctx);
 CVB_API int cvb_device_sm_count(const cvb_ctx *ctx);

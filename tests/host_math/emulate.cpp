@@ -39,16 +39,16 @@ static void emulate_blocks(const CvModelDesc &m, CvWarpMem &M, CvPartial *part, 
                 const int ncop = std::min(cpg, nlive - g);
                 const int nterms = ncop * S;
                 for (int lane = 0; lane < 32; lane++)
-                    cv_w_mass(lane, m, first + g, nterms, M);
+                    cv_w_mass(lane, m, first + g, nterms, S, M);
                 for (int sub = 0; sub < nterms; sub += CV_CT) {
                     for (int lane = 0; lane < 32; lane++) {
                         int src = g + (sub + lane) / S;
-                        CvTerm tm = cv_w_term(lane, m, first + g, nterms, sub, b[src < 31 ? src : 31], M);
+                        CvTerm tm = cv_w_term(lane, m, first + g, nterms, S, sub, b[src < 31 ? src : 31], M);
                         cv_w_prep<NA>(lane, m, blk, tm, M);
                     }
                     const int nkg = (std::min(CV_CT, nterms - sub) + 3) >> 2;
                     for (int lane = 0; lane < 32; lane++)
-                        cv_w_fused<NA>(lane, G[lane], nkg, fx, acc.data() + 4 * NA * lane);
+                        cv_w_fused<NA>(lane, G[lane], 0, nkg, fx, acc.data() + 4 * NA * lane);
                 }
             }
             if (any)

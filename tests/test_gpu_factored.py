@@ -1,0 +1,163 @@
+"""Parity of the factored evaluation path of the repeats model (profiles x copy weights on the FP64
+tensor cores, covest_b200/csrc/factored.cu) with the reference: golden vectors of the unmodified
+reference, the CPU oracle, and the per-point kernel on the same inputs.  Needs a B200."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import covest_oracle as orc
+from tests.helpers import (case_ctor_kwargs, case_hist, context_for, golden_case_names, load_case,
+                           rel_err_ll)
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9  # BASELINE.json north_star: per-point log-likelihood within 1e-9 relative
+PATH_RTOL = 1e-11  # the two device paths differ only in summation order
+
+
+def _model(case):
+    return orc.Model(case['model'], case['k'], case['r'], case_hist(case), case['tail'],
+                     **case_ctor_kwargs(case))
+
+
+def _repeats_cases():
+    return [n for n in golden_case_names() if load_case(n)['model'] == 'repeats']
+
+
+def _lattice(axes):
+    return np.ascontiguousarray(np.array(np.meshgrid(*axes, indexing='ij')).reshape(len(axes), -1).T)
+
+
+@pytest.mark.parametrize('name', _repeats_cases())
+def test_factored_matches_reference_golden(name):
+    case = load_case(name)
+    m = _model(case)
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_FACTORED)
+        got = ctx.loglik(case['points'])
+        assert ctx.last_path_info()['path'] == 'factored'
+    rel = rel_err_ll(got, np.array(case['ll'], dtype=float))
+    assert rel.max() <= LL_RTOL, (name, int(rel.argmax()), case['points'][int(rel.argmax())],
+                                  got[int(rel.argmax())], case['ll'][int(rel.argmax())])
+
+
+@pytest.mark.parametrize('name,c0,n_ce,n_q', [('cfg2_repeats', 30, 12, 40), ('e05_trim10_repeats', 10, 12, 40),
+                                              ('e05_repeats_allerr', 10, 6, 30),
+                                              ('cfg4_repeats_k31', 200, 2, 12)])
+def test_factored_grouped_points_against_oracle(name, c0, n_ce, n_q):
+    """Seeded points that share (coverage, error rate) pairs, as grids and stencils do, including
+    the bound and edge points of SURVEY.md section 8(d)."""
+    case = load_case(name)
+    m = _model(case)
+    rng = np.random.default_rng(123)
+    ce = np.column_stack([c0 * 3 ** rng.uniform(-1, 1, n_ce), np.exp(rng.uniform(np.log(1e-4), np.log(.5), n_ce))])
+    ce[0, 1] = 0.0
+    qs = np.column_stack([rng.uniform(.3, 1, n_q), rng.uniform(0, 1, n_q), rng.uniform(.02, 1, n_q)])
+    qs[0] = [1.0, .5, .5]
+    qs[1] = [.5, 0.0, .5]
+    qs[2] = [.5, .5, 0.0]
+    qs[3] = [.5, .5, 1.0]
+    qs[4] = [.1, 2, -1]  # clipped to (min_q1, 1, 0)
+    pts = np.array([[c, e, a, b, q] for c, e in ce for a, b, q in qs])
+    pts = pts[rng.permutation(len(pts))]
+    want = m.loglik_batch(pts, threads=8)
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_FACTORED)
+        got = ctx.loglik(pts)
+        info = ctx.last_path_info()
+        assert info['path'] == 'factored' and info['groups'] == n_ce
+    inside = ~(np.isposinf(want) | np.isnan(want))  # the reference's own overflow, DESIGN.md section 3
+    assert inside.sum() >= 0.8 * len(pts)
+    rel = rel_err_ll(got[inside], want[inside])
+    assert rel.max() <= LL_RTOL, (int(rel.argmax()), pts[inside][int(rel.argmax())])
+
+
+@pytest.mark.parametrize('bins', [200, 1000])
+def test_factored_equals_per_point_kernel_on_a_lattice(bins):
+    """BASELINE.json configs[2] shape: the candidate lattice of initial_grid.  The automatic mode
+    must choose the factored path here, and the two paths must agree far inside the tolerance."""
+    case = load_case('cfg3_repeats_dense1000')
+    hist = {j: h for j, h in case_hist(case).items() if j <= bins}
+    m = orc.Model('repeats', case['k'], case['r'], hist, case['tail'], max_error=8)
+    axes = [np.geomspace(10, 90, 6), np.geomspace(.01, .09, 4), np.linspace(.3, 1, 5),
+            np.linspace(0, 1, 5), np.linspace(.05, 1, 6)]
+    grid = _lattice(axes)
+    with context_for(m) as ctx:
+        got = ctx.loglik(grid)
+        info = ctx.last_path_info()
+        assert info['path'] == 'factored' and info['groups'] == 24, info
+        ctx.set_path(ctx.PATH_PER_POINT)
+        want = ctx.loglik(grid)
+        assert ctx.last_path_info()['path'] == 'per-point'
+        rel = rel_err_ll(got, want)
+        assert rel.max() <= PATH_RTOL, (int(rel.argmax()), grid[int(rel.argmax())])
+        # lattice entry point (points generated on the device) and strided slices
+        ctx.set_path(ctx.PATH_AUTO)
+        lat, rows = ctx.lattice_eval(axes, k_best=8)
+        assert np.array_equal(lat, got, equal_nan=True)
+        assert rows[0, 0] == np.nanmax(got)
+        ctx.set_path(ctx.PATH_FACTORED)  # 1800 points: below the automatic mode's batch size
+        part, _ = ctx.lattice_eval(axes, first=1, stride=2)
+        assert ctx.last_path_info()['path'] == 'factored'
+        assert np.array_equal(part, got[1::2], equal_nan=True)
+    # a handful against the oracle itself
+    pick = np.random.default_rng(4).choice(len(grid), 24, replace=False)
+    ref = m.loglik_batch(grid[pick], threads=8)
+    assert rel_err_ll(got[pick], ref).max() <= LL_RTOL
+
+
+def test_factored_results_do_not_depend_on_batch_composition():
+    case = load_case('cfg3_repeats_dense1000')
+    m = _model(case)
+    rng = np.random.default_rng(8)
+    axes = [np.geomspace(12, 80, 5), np.geomspace(.01, .08, 3), np.linspace(.3, 1, 6),
+            np.linspace(0, 1, 6), np.linspace(.05, 1, 8)]
+    grid = _lattice(axes)
+    perm = rng.permutation(len(grid))
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_FACTORED)
+        a = ctx.loglik(grid)
+        b = ctx.loglik(grid[perm])
+        some = ctx.loglik(grid[100:140])
+        one = ctx.loglik(grid[777:778])
+    assert np.array_equal(a[perm], b, equal_nan=True)
+    assert np.array_equal(some, a[100:140], equal_nan=True)
+    assert one[0] == a[777]
+
+
+def test_factored_edge_rows_and_small_workspace(monkeypatch):
+    """NaN rows, empty copy ranges, and a profile workspace so small that the batch runs in many
+    group ranges."""
+    case = load_case('cfg2_repeats')
+    m = _model(case)
+    axes = [np.geomspace(10, 90, 8), np.geomspace(.005, .2, 4), np.linspace(.3, 1, 4),
+            np.linspace(0, 1, 4), np.linspace(.02, 1, 5)]
+    grid = _lattice(axes)
+    grid[5, 0] = math.nan
+    grid[9, 4] = math.nan
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_PER_POINT)
+        want = ctx.loglik(grid)
+    monkeypatch.setenv('COVEST_B200_PROFILE_MIB', '1')
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_FACTORED)
+        got = ctx.loglik(grid)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert math.isnan(got[5]) and math.isnan(got[9])
+    assert rel_err_ll(got, want).max() <= PATH_RTOL
+
+
+def test_factored_with_a_tail_term():
+    """tail != 0 exercises the compensated mass sum of the GEMM epilogue (models.py:103-104)."""
+    case = load_case('cfg2_repeats_trim120')
+    assert case['tail'] != 0
+    m = _model(case)
+    axes = [np.geomspace(15, 60, 4), np.geomspace(.01, .06, 3), np.linspace(.4, .9, 4),
+            np.linspace(.1, .9, 4), np.linspace(.2, .9, 4)]
+    grid = _lattice(axes)
+    want = m.loglik_batch(grid, threads=8)
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_FACTORED)
+        got = ctx.loglik(grid)
+    assert rel_err_ll(got, want).max() <= LL_RTOL
