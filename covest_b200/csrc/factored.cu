@@ -226,40 +226,47 @@ __device__ __forceinline__ int cvf_find(const int *__restrict__ start, int n, in
 /* ------------------------------------------------------------------------------------------- */
 /* K1: profiles                                                                                 */
 /* ------------------------------------------------------------------------------------------- */
-/* Position (in doubles) of (copy o, slot) inside the profiles of a group: tiles of 16 copies x 64
- * slots, [K-chunk][N-step]; inside a tile the order in which a warp of K2 reads its B fragments:
- * [N half wn][K slice ks][n-tile pair np][lane = (slot % 8) * 4 + (o - 1) % 4][n-tile parity]. */
-__host__ __device__ __forceinline__ long long cvf_w_index(int o, int slot, int nsteps)
-{
-    const int k = o - 1;
-    const int kchunk = k >> 4, ks = (k >> 2) & 3, q = k & 3;
-    const int nstep = slot >> 6, s64 = slot & 63;
-    const int wn = s64 >> 5, nt = (s64 >> 3) & 3, r = s64 & 7;
-    const int in_tile = ((((wn * 4 + ks) * 2 + (nt >> 1)) * 32 + r * 4 + q) * 2) + (nt & 1);
-    return ((long long)kchunk * nsteps + nstep) * CVF_TILE_DOUBLES + in_tile;
-}
+/* Layout of the profiles of a group in HBM: tiles of 16 copies x 64 slots, [K-chunk][N-step];
+ * inside a tile [copy][pair L][2] where pair L = 8 * (row of the N-step) + column % 8 holds the
+ * slots with columns c and c + 8 of that row -- 512 contiguous bytes per copy, which K1 writes
+ * with one warp-wide store and K2 scatters into its fragment order while loading. */
+#define CVF_STAGE_DOUBLES (CV_GB * CV_NA_MAX * CV_W)
 
 /* The accumulators of a lane after the slices of ONE copy are its share of the profile of that
- * copy over block `blk`: rows mt of group r, columns 8 nt + 2 q + c.  The two column tiles of a
- * row land next to each other (n-tile parity), so every store is 16 bytes. */
+ * copy over block `blk`: rows mt of group r, columns 8 nt + 2 q + c.  They are transposed through
+ * the warp's stage in shared memory ([row][column % 8][column / 8], the 16-byte chunks of odd
+ * groups swapped pairwise against bank conflicts) and leave as full 512-byte lines. */
 template <int NA>
 __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int nsteps,
-                                                  double *__restrict__ Wg, const double *acc)
+                                                  double *__restrict__ Wg, double *stage, const double *acc)
 {
     const int r = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int mt = 0; mt < NA; mt++)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            const int slot = ((blk * CV_GB + r) * NA + mt) * CV_W + 2 * q + c; /* column tile 0 */
-            const long long at = cvf_w_index(o, slot, nsteps);
-            *reinterpret_cast<double2 *>(Wg + at) = make_double2(acc[4 * mt + c], acc[4 * mt + 2 + c]);
+            const int chunk = (2 * q + c) ^ (r & 1);
+            *reinterpret_cast<double2 *>(stage + (NA * r + mt) * CV_W + 2 * chunk) =
+                make_double2(acc[4 * mt + c], acc[4 * mt + 2 + c]);
         }
+    __syncwarp();
+    const int k = o - 1;
+    double *tile0 = Wg + ((long long)(k >> 4) * nsteps + (long long)blk * (2 * NA)) * CVF_TILE_DOUBLES +
+                    ((k & 15) * 32 + lane) * 2;
+#pragma unroll
+    for (int ns = 0; ns < 2 * NA; ns++) {
+        const int row = 4 * ns + (lane >> 3);
+        const int chunk = (lane & 7) ^ ((row / NA) & 1);
+        const double2 v = *reinterpret_cast<const double2 *>(stage + row * CV_W + 2 * chunk);
+        *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
+    }
+    __syncwarp();
 }
 
 template <int NA>
 __device__ __forceinline__ void cvf_profile_item(int lane, const CvModelDesc &m, CvWarpMem &M,
-                                                 int o0, int omax4, int nsteps, double *__restrict__ Wg)
+                                                 int o0, int omax4, int nsteps, double *__restrict__ Wg,
+                                                 double *stage)
 {
     const int sp = cvf_copy_slots(m.n_err);
     const int cpt = cvf_copies_per_tile(m.n_err);
@@ -278,7 +285,7 @@ __device__ __forceinline__ void cvf_profile_item(int lane, const CvModelDesc &m,
                 for (int i = 0; i < 4 * NA; i++)
                     acc[i] = 0.0;
                 cv_w_fused<NA>(lane, G, cc * kpc, (cc + 1) * kpc, *M.fx, acc);
-                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, Wg, acc);
+                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, Wg, stage, acc);
             }
             __syncwarp();
         }
@@ -305,6 +312,9 @@ cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
             tab[i] = m.tab.grp[i];
         M.grp = tab;
     }
+    double *stage = reinterpret_cast<double *>(cv_smem_raw + (size_t)groups_staged * CV_GD * sizeof(double) +
+                                               (size_t)(blockDim.x >> 5) * cv_warp_bytes(S)) +
+                    (size_t)warp * CVF_STAGE_DOUBLES;
     __syncthreads();
     for (;;) {
         long long it = 0;
@@ -327,10 +337,10 @@ cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
         double *Wg = W + (pl.w_off[g] - w_base);
         const int o0 = kchunk * CVF_KC + 1;
         switch (m.na) {
-        case 1: cvf_profile_item<1>(lane, m, M, o0, omax4, nsteps, Wg); break;
-        case 2: cvf_profile_item<2>(lane, m, M, o0, omax4, nsteps, Wg); break;
-        case 4: cvf_profile_item<4>(lane, m, M, o0, omax4, nsteps, Wg); break;
-        default: cvf_profile_item<8>(lane, m, M, o0, omax4, nsteps, Wg); break;
+        case 1: cvf_profile_item<1>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
+        case 2: cvf_profile_item<2>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
+        case 4: cvf_profile_item<4>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
+        default: cvf_profile_item<8>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
         }
     }
 }
@@ -365,6 +375,39 @@ __device__ __forceinline__ void cvf_two_sum_acc(double &hi, double &lo, double x
     lo = cv_add(lo, s.lo);
 }
 
+/* The running copy weights of one point for the generator role of a thread: b(o) of
+ * models.py:193-208 for the 8 copies of its half of a K-chunk, as a running product (relative
+ * error below 1e-13 at o = 1000).  half 0 covers copies 16 kc + 1 .. + 8, half 1 the next eight. */
+struct CvfWeights {
+    double q1, two, many, base, b16, cur0, cur;
+    int othr, half;
+};
+
+__device__ __forceinline__ void cvf_weights_chunk(CvfWeights &w, int kc, double *v)
+{
+    if (kc == 0)
+        w.cur = w.cur0;
+    if (kc == 0 && w.half == 0) {
+        v[0] = w.q1;
+        v[1] = w.two;
+        v[2] = w.many;
+#pragma unroll
+        for (int i = 3; i < 8; i++)
+            v[i] = cv_mul(v[i - 1], w.base);
+    } else {
+        v[0] = w.cur;
+#pragma unroll
+        for (int i = 1; i < 8; i++)
+            v[i] = cv_mul(v[i - 1], w.base);
+        w.cur = cv_mul(w.cur, w.b16);
+    }
+    const int o_first = kc * CVF_KC + 8 * w.half + 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (!(o_first + i < w.othr)) /* models.py:235: copies o < O_thr */
+            v[i] = 0.0;
+}
+
 __global__ void __launch_bounds__(CVF_THREADS, 2)
 cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                 const double *__restrict__ params, int clip, CvfPlan pl, int n_groups, int first_tile,
@@ -380,7 +423,23 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
     const int apos = r * 4 + (q ^ ((r >> 1) & 3)); /* swizzled position of the lane's A chunk */
     /* generator role: point gp of the tile, copies 8 half + 1 .. 8 half + 8 of every chunk */
     const int gp = (tid & 15) + 16 * (tid >> 5), half = (tid >> 4) & 1;
-    const int g_wm = gp >> 5, g_mt = (gp >> 3) & 3, g_r = gp & 7;
+    int a_at[2]; /* position (doubles) of the thread's first weight of each of its two K slices */
+    {
+        const int g_wm = gp >> 5, g_mt = (gp >> 3) & 3, g_r = gp & 7;
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+            a_at[j] = (((g_wm * 4 + 2 * half + j) * 2 + (g_mt >> 1)) * 32 + g_r * 4) * 2 + (g_mt & 1);
+    }
+    const int a_sw = (gp >> 1) & 3; /* (g_r >> 1) & 3 */
+    /* loader role: 16-byte chunks tid and tid + 256 of a profile tile ([copy][pair]) go to the
+     * fragment order [N half][K slice][n-tile pair][lane = (column % 8) * 4 + copy % 4] */
+    int b_dst[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int i = tid + j * CVF_THREADS;
+        const int oc = i >> 5, L = i & 31, row = L >> 3, rr = L & 7;
+        b_dst[j] = (((row >> 1) * 4 + (oc >> 2)) * 2 + (row & 1)) * 32 + rr * 4 + (oc & 3);
+    }
     const bool want_mass = m.tail != 0.0;
 
     for (;;) {
@@ -423,28 +482,53 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
         const int nkc = (kmax + CVF_KC - 1) / CVF_KC;
         const double *Wg = W + (pl.w_off[g] - w_base);
         const int total = nsteps * nkc;
+        /* copies the 8 points of each of the warp's row tiles need (ascending: the last live one) */
+        int kend[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            const int first = 32 * wm + 8 * mt;
+            kend[mt] = first < cnt ? S.othr[min(first + 7, cnt - 1)] - 1 : 0;
+        }
+        const int kend_warp = max(max(kend[0], kend[1]), max(kend[2], kend[3]));
 
-        /* generator constants of this thread's point */
-        const double g_q1 = S.q1[gp], g_two = S.two[gp], g_many = S.many[gp], g_base = S.base[gp];
-        const int g_othr = S.othr[gp];
-        const double b2 = cv_mul(g_base, g_base), b4 = cv_mul(b2, b2), b8 = cv_mul(b4, b4);
-        const double b16 = cv_mul(b8, b8);
-        /* b(o) of the first copy of the thread's half in chunk 0 (half 1: o = 9) resp. chunk 1 */
-        const double cur0 = half ? cv_mul(g_many, cv_mul(b4, b2)) : cv_mul(g_many, cv_mul(b8, cv_mul(b4, b2)));
-
+        CvfWeights wg;
+        wg.q1 = S.q1[gp];
+        wg.two = S.two[gp];
+        wg.many = S.many[gp];
+        wg.base = S.base[gp];
+        wg.othr = S.othr[gp];
+        wg.half = half;
+        {
+            const double b2 = cv_mul(wg.base, wg.base), b4 = cv_mul(b2, b2), b8 = cv_mul(b4, b4);
+            wg.b16 = cv_mul(b8, b8);
+            /* b(o) of the first copy of the thread's half in chunk 0 (half 1: o = 9, many base^6)
+             * resp. chunk 1 (half 0: o = 17, many base^14) */
+            wg.cur0 = half ? cv_mul(wg.many, cv_mul(b4, b2)) : cv_mul(wg.many, cv_mul(b8, cv_mul(b4, b2)));
+            wg.cur = wg.cur0;
+        }
+        auto gen = [&](int t) { /* copy weights of chunk t into As[t & 1] */
+            double v[8];
+            cvf_weights_chunk(wg, t % nkc, v);
+            double *as = reinterpret_cast<double *>(S.As[t & 1]);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                as[a_at[i >> 2] + (((i & 3) ^ a_sw) << 1)] = v[i];
+        };
         auto issue = [&](int t) {
             if (t < total) {
                 const int kc = t % nkc, ns = t / nkc;
                 const double2 *src = reinterpret_cast<const double2 *>(
                     Wg + ((long long)kc * nsteps + ns) * CVF_TILE_DOUBLES);
                 double2 *dst = S.Bs[t % 3];
-                cvf_cp_async16(dst + tid, src + tid);
-                cvf_cp_async16(dst + tid + CVF_THREADS, src + tid + CVF_THREADS);
+                cvf_cp_async16(dst + b_dst[0], src + tid);
+                cvf_cp_async16(dst + b_dst[1], src + tid + CVF_THREADS);
             }
             cvf_cp_commit();
         };
         issue(0);
         issue(1);
+        if (total > 0)
+            gen(0);
 
         double sum[4] = {0.0, 0.0, 0.0, 0.0};
         double mass_h[4] = {0.0, 0.0, 0.0, 0.0}, mass_l[4] = {0.0, 0.0, 0.0, 0.0};
@@ -454,53 +538,33 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
 #pragma unroll
             for (int i = 0; i < 32; i++)
                 acc[i] = 0.0;
-            double cur = cur0;
             for (int kc = 0; kc < nkc; kc++, t++) {
-                /* copy weights of the chunk: models.py:193-208 as a running product */
-                {
-                    double v[8];
-                    if (kc == 0 && half == 0) {
-                        v[0] = g_q1;
-                        v[1] = g_two;
-                        v[2] = g_many;
-#pragma unroll
-                        for (int i = 3; i < 8; i++)
-                            v[i] = cv_mul(v[i - 1], g_base);
-                    } else {
-                        v[0] = cur;
-#pragma unroll
-                        for (int i = 1; i < 8; i++)
-                            v[i] = cv_mul(v[i - 1], g_base);
-                        cur = cv_mul(cur, b16);
-                    }
-                    const int o_first = kc * CVF_KC + 8 * half + 1;
-                    double *as = reinterpret_cast<double *>(S.As[t & 1]);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int ks = 2 * half + (i >> 2), qq = i & 3;
-                        const int at = (((g_wm * 4 + ks) * 2 + (g_mt >> 1)) * 32 + g_r * 4 +
-                                        (qq ^ ((g_r >> 1) & 3))) * 2 + (g_mt & 1);
-                        as[at] = (o_first + i < g_othr) ? v[i] : 0.0; /* models.py:235: o < O_thr */
-                    }
-                }
                 cvf_cp_wait1();
-                __syncthreads(); /* weights written, profile tile t landed */
+                __syncthreads(); /* weights of chunk t written, profile tile t landed, chunk t - 1 consumed */
                 issue(t + 2);
-                const int nks = min(4, (kmax - kc * CVF_KC + 3) >> 2);
-                const double2 *as2 = S.As[t & 1];
-                const double2 *bs2 = S.Bs[t % 3];
-                for (int ks = 0; ks < nks; ks++) {
-                    const double2 a01 = as2[((wm * 4 + ks) * 2 + 0) * 32 + apos];
-                    const double2 a23 = as2[((wm * 4 + ks) * 2 + 1) * 32 + apos];
-                    const double2 b01 = bs2[((wn * 4 + ks) * 2 + 0) * 32 + lane];
-                    const double2 b23 = bs2[((wn * 4 + ks) * 2 + 1) * 32 + lane];
-                    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-                    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+                if (t + 1 < total)
+                    gen(t + 1);
+                const int k0 = kc * CVF_KC;
+                if (k0 < kend_warp) {
+                    const int nks = min(4, (kend_warp - k0 + 3) >> 2);
+                    const double2 *as2 = S.As[t & 1];
+                    const double2 *bs2 = S.Bs[t % 3];
+                    for (int ks = 0; ks < nks; ks++) {
+                        const double2 a01 = as2[((wm * 4 + ks) * 2 + 0) * 32 + apos];
+                        const double2 a23 = as2[((wm * 4 + ks) * 2 + 1) * 32 + apos];
+                        const double2 b01 = bs2[((wn * 4 + ks) * 2 + 0) * 32 + lane];
+                        const double2 b23 = bs2[((wn * 4 + ks) * 2 + 1) * 32 + lane];
+                        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+                        const int kk = k0 + 4 * ks;
 #pragma unroll
-                    for (int mt = 0; mt < 4; mt++)
+                        for (int mt = 0; mt < 4; mt++)
+                            if (kk < kend[mt]) { /* row tiles whose points stop earlier hold zeros */
 #pragma unroll
-                        for (int nt = 0; nt < 4; nt++)
-                            cv_dmma(acc[(mt * 4 + nt) * 2], acc[(mt * 4 + nt) * 2 + 1], a[mt], b[nt]);
+                                for (int nt = 0; nt < 4; nt++)
+                                    cv_dmma(acc[(mt * 4 + nt) * 2], acc[(mt * 4 + nt) * 2 + 1], a[mt], b[nt]);
+                            }
+                    }
                 }
             }
             /* epilogue of the N-step, models.py:100-107: the lane holds points 32 wm + 8 mt + r and
@@ -513,6 +577,9 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
                     const double2 mh = __ldg(slot_mh + slot);
                     const bool in_hist = mh.x != 0.0;
                     const bool counted = mh.y != 0.0; /* models.py:106 `if h` */
+                    const bool any_counted = __any_sync(CV_FULL_MASK, counted);
+                    if (!any_counted && !want_mass)
+                        continue;
                     double p[4];
 #pragma unroll
                     for (int mt = 0; mt < 4; mt++)
@@ -522,7 +589,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
                         for (int mt = 0; mt < 4; mt++)
                             cvf_two_sum_acc(mass_h[mt], mass_l[mt], p[mt]);
                     }
-                    if (__any_sync(CV_FULL_MASK, counted)) {
+                    if (any_counted) {
 #pragma unroll
                         for (int mt = 0; mt < 4; mt++) {
                             double lg = (p[mt] <= 0.0) ? -INFINITY : log(p[mt]); /* utils.py:32-35 */
@@ -751,10 +818,11 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     const size_t wb = cv_warp_bytes(m.n_err);
     const int groups_staged = m.n_blocks * CV_GB;
     const size_t tab = (size_t)groups_staged * CV_GD * sizeof(double);
-    int k1_warps = (int)std::min<long long>(CV_WARPS_MAX, ((long long)smem_max - (long long)tab) / (long long)wb);
+    const size_t wb1 = wb + CVF_STAGE_DOUBLES * sizeof(double); /* working set + profile stage */
+    int k1_warps = (int)std::min<long long>(CV_WARPS_MAX, ((long long)smem_max - (long long)tab) / (long long)wb1);
     if (k1_warps < 1)
         return cudaErrorInvalidConfiguration;
-    const size_t k1_smem = tab + (size_t)k1_warps * wb;
+    const size_t k1_smem = tab + (size_t)k1_warps * wb1;
     CVF_CK(cudaFuncSetAttribute(cvf_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
     CVF_CK(cudaFuncSetAttribute(cvf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(CvfSmem)));
