@@ -51,6 +51,8 @@ struct cvb_ctx {
     /* the factored path of the repeats model (factored.h) */
     CvFactorWork fw;
     const double2 *d_slot_mh = nullptr;
+    const int *d_step_mask = nullptr;
+    const double *d_log_tab = nullptr;
     int path_mode = 0;         /* 0 auto, 1 per-point kernel only, 2 factored whenever supported */
     size_t w_limit = (size_t)2 << 30; /* doubles: 16 GiB of profiles per group range */
     double min_group = 12.0;   /* auto: points per (c, e) group below which the per-point kernel runs */
@@ -258,6 +260,10 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
             for (size_t i = 0; i < mh.size(); i++)
                 mh[i] = make_double2(T.slot_mult[i], T.slot_h[i]);
             if ((e = upload(c, mh, &c->d_slot_mh)) != cudaSuccess) break;
+            if ((e = upload(c, cvf_step_masks(T.slot_h), &c->d_step_mask)) != cudaSuccess) break;
+            std::vector<double> lt(2 * CV_LOG_N);
+            cv_log_table(lt.data());
+            if ((e = upload(c, lt, &c->d_log_tab)) != cudaSuccess) break;
         }
         if (const char *pm = getenv("COVEST_B200_PATH"))
             c->path_mode = !strcmp(pm, "direct") ? 1 : !strcmp(pm, "factored") ? 2 : 0;
@@ -328,7 +334,8 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
                               (ctx->path_mode == 2 || n >= ctx->min_points);
     if (try_factored) {
         ctx->fw.timed = ctx->timing;
-        CU(cvf_eval(ctx->desc, lat, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->fw, ctx->n_sm,
+        CU(cvf_eval(ctx->desc, lat, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->d_step_mask,
+                    ctx->d_log_tab, ctx->fw, ctx->n_sm,
                     ctx->smem_max, ctx->w_limit, ctx->path_mode == 2 ? 0.0 : ctx->min_group, s, &used),
            "factored evaluation");
         ctx->last_launches += ctx->fw.launches;

@@ -247,3 +247,49 @@ CV_HD cv_dd cv_log_dd(double x)
     cv_dd r = cv_two_sum(cv_mul(ed, ln2_hi), lm.hi);
     return cv_fast_two_sum(r.hi, cv_add(r.lo, cv_fma(ed, ln2_lo, lm.lo)));
 }
+
+/* ----------------------------------------------------------------------------------------- */
+/* log(x) for the GEMM epilogue (safe_log of a bin probability, utils.py:32-35): table driven, */
+/* 128 intervals over [0.6875, 1.375), x = 2^k z, r = z * invc - 1 with |r| < 2^-7.6, then     */
+/* log x = k ln2 + logc + log1p(r), log1p as a degree-7 polynomial.  Absolute error below      */
+/* 2e-16 (1 + |log x|): far inside what the count-weighted sum needs.  `tab` holds 128 pairs   */
+/* (invc, logc) built by cv_log_table.  Zero, negative, subnormal and non-finite arguments     */
+/* take libm's log (0 -> -inf, the caller maps p <= 0 to -inf first).                          */
+/* ----------------------------------------------------------------------------------------- */
+#define CV_LOG_N 128
+#define CV_LOG_OFF 0x3fe6000000000000ULL
+
+CV_HD double cv_log_tab(double x, const double *tab)
+{
+    if (!(x >= 0x1p-1022) || !(x < INFINITY))
+        return log(x);
+    const uint64_t ix = cv_bits(x);
+    const uint64_t tmp = ix - CV_LOG_OFF;
+    const int i = (int)((tmp >> 45) & (CV_LOG_N - 1));
+    const int k = (int)((int64_t)tmp >> 52);
+    const double z = cv_from_bits(ix - (tmp & 0xfff0000000000000ULL));
+    const double invc = tab[2 * i], logc = tab[2 * i + 1];
+    const double r = cv_fma(z, invc, -1.0);
+    const double kd = (double)k;
+    const double hi = cv_fma(kd, 0x1.62e42fefa3800p-1, logc); /* ln2 to 42 bits: kd * ln2hi exact */
+    double p = cv_fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = cv_fma(r, p, 1.0 / 5.0);
+    p = cv_fma(r, p, -1.0 / 4.0);
+    p = cv_fma(r, p, 1.0 / 3.0);
+    p = cv_fma(r, p, -0.5);
+    const double r2 = cv_mul(r, r);
+    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.ef35793c76730p-45)); /* ln2 - ln2hi */
+    return cv_add(hi, cv_add(r, lo));
+}
+
+/* host: the 128 (invc, logc) pairs, logc = -log(invc) of the ROUNDED invc */
+static inline void cv_log_table(double *tab)
+{
+    for (int i = 0; i < CV_LOG_N; i++) {
+        long double u = ((long double)i + 0.5L) / CV_LOG_N;
+        long double c = u < 0.625L ? 0.5L * (1.375L + u) : 0.375L + u;
+        double invc = (double)(1.0L / c);
+        tab[2 * i] = invc;
+        tab[2 * i + 1] = (double)(-logl((long double)invc));
+    }
+}

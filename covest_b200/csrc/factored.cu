@@ -354,6 +354,7 @@ struct CvfSmem {
     double q1[CVF_M], two[CVF_M], many[CVF_M], base[CVF_M];
     double red_sum[2][CVF_M];
     double red_mh[2][CVF_M], red_ml[2][CVF_M];
+    double log_tab[2 * CV_LOG_N]; /* cv_log_tab: (invc, logc) */
     int othr[CVF_M];
     unsigned int pidx[CVF_M];
     int tile;
@@ -373,6 +374,34 @@ __device__ __forceinline__ void cvf_two_sum_acc(double &hi, double &lo, double x
     cv_dd s = cv_two_sum(hi, x);
     hi = s.hi;
     lo = cv_add(lo, s.lo);
+}
+
+/* Four MMAs of one row tile (one A value, the four column tiles of the warp), skipped as a whole
+ * when copy index kk is past the copies the 8 points of the row tile use.  The condition is the
+ * same in every lane.  Written as a loop of zero or one trips: ptxas turns a plain branch into four
+ * predicated MMAs, which still occupy the FP64 pipe when predicated off. */
+__device__ __forceinline__ void cvf_dmma4_if(double *acc, double a, const double *b, int kk, int kend)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .s32 n;\n"
+        "sub.s32 n, %14, %13;\n"       /* > 0: the row tile still has copies */
+        "min.s32 n, n, 1;\n"
+        "CVF_LOOP:\n"
+        "setp.le.s32 p, n, 0;\n"
+        "@p bra CVF_DONE;\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%9}, {%0,%1};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%8}, {%10}, {%2,%3};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%8}, {%11}, {%4,%5};\n"
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%8}, {%12}, {%6,%7};\n"
+        "sub.s32 n, n, 1;\n"
+        "bra CVF_LOOP;\n"
+        "CVF_DONE:\n"
+        "}\n"
+        : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+d"(acc[4]), "+d"(acc[5]), "+d"(acc[6]),
+          "+d"(acc[7])
+        : "d"(a), "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]), "r"(kk), "r"(kend));
 }
 
 /* The running copy weights of one point for the generator role of a thread: b(o) of
@@ -412,7 +441,8 @@ __global__ void __launch_bounds__(CVF_THREADS, 2)
 cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                 const double *__restrict__ params, int clip, CvfPlan pl, int n_groups, int first_tile,
                 int n_tiles, const double *__restrict__ W, long long w_base,
-                const double2 *__restrict__ slot_mh, int nsteps, double *__restrict__ out_ll,
+                const double2 *__restrict__ slot_mh, const int *__restrict__ step_mask,
+                const double *__restrict__ log_tab, int nsteps, double *__restrict__ out_ll,
                 unsigned long long *counter)
 {
     extern __shared__ __align__(16) unsigned char cvf_smem_raw[];
@@ -421,11 +451,16 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
     const int wm = warp >> 1, wn = warp & 1;
     const int r = lane >> 2, q = lane & 3;
     const int apos = r * 4 + (q ^ ((r >> 1) & 3)); /* swizzled position of the lane's A chunk */
-    /* generator role: point gp of the tile, copies 8 half + 1 .. 8 half + 8 of every chunk */
-    const int gp = (tid & 15) + 16 * (tid >> 5), half = (tid >> 4) & 1;
+    /* The 128 points of a tile are sorted by O_thr.  Row tile J (8 points) belongs to warp row
+     * wm = J % 4 as its tile mt = J / 4, so that every warp row holds short and long rows alike. */
+    /* generator role: point gp of the tile, copies 8 half + 1 .. 8 half + 8 of every chunk; the
+     * 16 lanes of a half warp take the row tiles J and J + 4 (different halves of a 16-byte chunk) */
+    const int gp = 8 * ((warp & 3) + 8 * (warp >> 2) + 4 * ((tid >> 3) & 1)) + (tid & 7), half = (tid >> 4) & 1;
     int a_at[2]; /* position (doubles) of the thread's first weight of each of its two K slices */
+    for (int i = tid; i < 2 * CV_LOG_N; i += CVF_THREADS)
+        S.log_tab[i] = log_tab[i];
     {
-        const int g_wm = gp >> 5, g_mt = (gp >> 3) & 3, g_r = gp & 7;
+        const int g_wm = (gp >> 3) & 3, g_mt = gp >> 5, g_r = gp & 7;
 #pragma unroll
         for (int j = 0; j < 2; j++)
             a_at[j] = (((g_wm * 4 + 2 * half + j) * 2 + (g_mt >> 1)) * 32 + g_r * 4) * 2 + (g_mt & 1);
@@ -486,7 +521,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
         int kend[4];
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) {
-            const int first = 32 * wm + 8 * mt;
+            const int first = 8 * (4 * mt + wm);
             kend[mt] = first < cnt ? S.othr[min(first + 7, cnt - 1)] - 1 : 0;
         }
         const int kend_warp = max(max(kend[0], kend[1]), max(kend[2], kend[3]));
@@ -506,49 +541,59 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
             wg.cur0 = half ? cv_mul(wg.many, cv_mul(b4, b2)) : cv_mul(wg.many, cv_mul(b8, cv_mul(b4, b2)));
             wg.cur = wg.cur0;
         }
+        int gen_kc = 0; /* chunk index inside the N-step of the next weights to generate */
         auto gen = [&](int t) { /* copy weights of chunk t into As[t & 1] */
             double v[8];
-            cvf_weights_chunk(wg, t % nkc, v);
+            cvf_weights_chunk(wg, gen_kc, v);
+            if (++gen_kc == nkc)
+                gen_kc = 0;
             double *as = reinterpret_cast<double *>(S.As[t & 1]);
 #pragma unroll
             for (int i = 0; i < 8; i++)
                 as[a_at[i >> 2] + (((i & 3) ^ a_sw) << 1)] = v[i];
         };
-        auto issue = [&](int t) {
-            if (t < total) {
-                const int kc = t % nkc, ns = t / nkc;
+        int ld_kc = 0, ld_ns = 0, ld_buf = 0; /* the next profile tile to request */
+        auto issue = [&]() {
+            if (ld_ns < nsteps) {
                 const double2 *src = reinterpret_cast<const double2 *>(
-                    Wg + ((long long)kc * nsteps + ns) * CVF_TILE_DOUBLES);
-                double2 *dst = S.Bs[t % 3];
+                    Wg + ((long long)ld_kc * nsteps + ld_ns) * CVF_TILE_DOUBLES);
+                double2 *dst = S.Bs[ld_buf];
                 cvf_cp_async16(dst + b_dst[0], src + tid);
                 cvf_cp_async16(dst + b_dst[1], src + tid + CVF_THREADS);
+                if (++ld_kc == nkc) {
+                    ld_kc = 0;
+                    ld_ns++;
+                }
+                ld_buf = ld_buf == 2 ? 0 : ld_buf + 1;
             }
             cvf_cp_commit();
         };
-        issue(0);
-        issue(1);
+        if (nkc == 0)
+            ld_ns = nsteps; /* nothing to load */
+        issue();
+        issue();
         if (total > 0)
             gen(0);
 
         double sum[4] = {0.0, 0.0, 0.0, 0.0};
         double mass_h[4] = {0.0, 0.0, 0.0, 0.0}, mass_l[4] = {0.0, 0.0, 0.0, 0.0};
-        int t = 0;
+        int t = 0, cons_buf = 0;
         for (int ns = 0; ns < nsteps; ns++) {
             double acc[32];
 #pragma unroll
             for (int i = 0; i < 32; i++)
                 acc[i] = 0.0;
-            for (int kc = 0; kc < nkc; kc++, t++) {
+            for (int kc = 0; kc < nkc; kc++, t++, cons_buf = cons_buf == 2 ? 0 : cons_buf + 1) {
                 cvf_cp_wait1();
                 __syncthreads(); /* weights of chunk t written, profile tile t landed, chunk t - 1 consumed */
-                issue(t + 2);
+                issue();
                 if (t + 1 < total)
                     gen(t + 1);
                 const int k0 = kc * CVF_KC;
                 if (k0 < kend_warp) {
                     const int nks = min(4, (kend_warp - k0 + 3) >> 2);
                     const double2 *as2 = S.As[t & 1];
-                    const double2 *bs2 = S.Bs[t % 3];
+                    const double2 *bs2 = S.Bs[cons_buf];
                     for (int ks = 0; ks < nks; ks++) {
                         const double2 a01 = as2[((wm * 4 + ks) * 2 + 0) * 32 + apos];
                         const double2 a23 = as2[((wm * 4 + ks) * 2 + 1) * 32 + apos];
@@ -558,46 +603,46 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
                         const double b[4] = {b01.x, b01.y, b23.x, b23.y};
                         const int kk = k0 + 4 * ks;
 #pragma unroll
-                        for (int mt = 0; mt < 4; mt++)
-                            if (kk < kend[mt]) { /* row tiles whose points stop earlier hold zeros */
-#pragma unroll
-                                for (int nt = 0; nt < 4; nt++)
-                                    cv_dmma(acc[(mt * 4 + nt) * 2], acc[(mt * 4 + nt) * 2 + 1], a[mt], b[nt]);
-                            }
+                        for (int mt = 0; mt < 4; mt++) /* row tiles whose points stop earlier hold zeros */
+                            cvf_dmma4_if(acc + mt * 8, a[mt], b, kk, kend[mt]);
                     }
                 }
             }
-            /* epilogue of the N-step, models.py:100-107: the lane holds points 32 wm + 8 mt + r and
-             * slots 64 ns + 32 wn + 8 nt + 2 q + c */
+            /* epilogue of the N-step, models.py:100-107: the lane holds row r of its four row
+             * tiles and slots 64 ns + 32 wn + 8 nt + 2 q + c; bit 2 nt + c of the step mask says
+             * whether any of those four slots has a count */
+            const int mask = want_mass ? 0xff : __ldg(step_mask + 2 * ns + wn);
+            if (mask) {
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++)
+                for (int nt = 0; nt < 4; nt++)
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int slot = ns * CVF_NS + 32 * wn + 8 * nt + 2 * q + c;
-                    const double2 mh = __ldg(slot_mh + slot);
-                    const bool in_hist = mh.x != 0.0;
-                    const bool counted = mh.y != 0.0; /* models.py:106 `if h` */
-                    const bool any_counted = __any_sync(CV_FULL_MASK, counted);
-                    if (!any_counted && !want_mass)
-                        continue;
-                    double p[4];
-#pragma unroll
-                    for (int mt = 0; mt < 4; mt++)
-                        p[mt] = in_hist ? cv_mul(acc[(mt * 4 + nt) * 2 + c], mh.x) : 0.0;
-                    if (want_mass) {
+                    for (int c = 0; c < 2; c++) {
+                        if (!((mask >> (2 * nt + c)) & 1))
+                            continue;
+                        const int slot = ns * CVF_NS + 32 * wn + 8 * nt + 2 * q + c;
+                        const double2 mh = __ldg(slot_mh + slot);
+                        const bool in_hist = mh.x != 0.0;
+                        const bool counted = mh.y != 0.0; /* models.py:106 `if h` */
+                        double p[4];
 #pragma unroll
                         for (int mt = 0; mt < 4; mt++)
-                            cvf_two_sum_acc(mass_h[mt], mass_l[mt], p[mt]);
-                    }
-                    if (any_counted) {
+                            p[mt] = in_hist ? cv_mul(acc[(mt * 4 + nt) * 2 + c], mh.x) : 0.0;
+                        if (want_mass) {
 #pragma unroll
-                        for (int mt = 0; mt < 4; mt++) {
-                            double lg = (p[mt] <= 0.0) ? -INFINITY : log(p[mt]); /* utils.py:32-35 */
-                            if (counted)
-                                sum[mt] = cv_add(sum[mt], cv_mul(mh.y, lg));
+                            for (int mt = 0; mt < 4; mt++)
+                                cvf_two_sum_acc(mass_h[mt], mass_l[mt], p[mt]);
+                        }
+                        if (__any_sync(CV_FULL_MASK, counted)) {
+#pragma unroll
+                            for (int mt = 0; mt < 4; mt++) {
+                                /* utils.py:32-35 safe_log */
+                                double lg = (p[mt] <= 0.0) ? -INFINITY : cv_log_tab(p[mt], S.log_tab);
+                                if (counted)
+                                    sum[mt] = cv_add(sum[mt], cv_mul(mh.y, lg));
+                            }
                         }
                     }
-                }
+            }
         }
         cvf_cp_wait0();
         /* the four lanes of a quad hold different slots of the same points */
@@ -614,7 +659,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
                 }
             }
             if (q == 0) {
-                const int pt = 32 * wm + 8 * mt + r;
+                const int pt = 8 * (4 * mt + wm) + r;
                 S.red_sum[wn][pt] = sum[mt];
                 S.red_mh[wn][pt] = mass_h[mt];
                 S.red_ml[wn][pt] = mass_l[mt];
@@ -668,8 +713,9 @@ static size_t cvf_align(size_t x) { return (x + 255) & ~(size_t)255; }
     } while (0)
 
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
-                     int clip, double *out_ll, const double2 *slot_mh, CvFactorWork &wk, int n_sm,
-                     int smem_max, size_t w_limit, double min_group, cudaStream_t stream, int *used)
+                     int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
+                     const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
+                     double min_group, cudaStream_t stream, int *used)
 {
     *used = 0;
     wk.launches = 0;
@@ -851,7 +897,8 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
             const int tiles = tile1 - tile0;
             int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;
             cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(
-                m, lat, params, clip, pl, (int)n_groups, tile0, tiles, wk.W, w0, slot_mh, nsteps, out_ll,
+                m, lat, params, clip, pl, (int)n_groups, tile0, tiles, wk.W, w0, slot_mh, step_mask, log_tab, nsteps,
+                out_ll,
                 wk.d_counters + 1);
             CVF_CK(cudaGetLastError());
             wk.launches++;

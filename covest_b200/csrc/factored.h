@@ -43,10 +43,26 @@ struct CvFactorWork {
 bool cvf_supported(const CvModelDesc &m);
 
 /* Evaluates n points.  *used = 0 when the batch does not group well enough (nothing written to
- * out_ll; the caller runs the per-point kernel).  `slot_mh` = (slot_mult, slot_h) pairs, device.
- * w_limit = largest profile workspace in doubles; larger batches run in several group ranges. */
+ * out_ll; the caller runs the per-point kernel).  Device tables: `slot_mh` = (slot_mult, slot_h)
+ * pairs; `step_mask` = per 32 slots, bit 2 nt + c set when one of the slots 8 nt + 2 q + c, q < 4,
+ * has a count (cvf_step_masks); `log_tab` = cv_log_table.  w_limit = largest profile workspace in
+ * doubles; larger batches run in several group ranges. */
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
-                     int clip, double *out_ll, const double2 *slot_mh, CvFactorWork &wk, int n_sm,
-                     int smem_max, size_t w_limit, double min_group, cudaStream_t stream, int *used);
+                     int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
+                     const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
+                     double min_group, cudaStream_t stream, int *used);
+
+/* host: the step masks of a slot_h table (length a multiple of 32) */
+#include <vector>
+static inline std::vector<int> cvf_step_masks(const std::vector<double> &slot_h)
+{
+    std::vector<int> out(slot_h.size() / 32, 0);
+    for (size_t s = 0; s < slot_h.size(); s++)
+        if (slot_h[s] != 0.0) {
+            const int in32 = (int)(s & 31), nt = in32 >> 3, c = in32 & 1;
+            out[s / 32] |= 1 << (2 * nt + c);
+        }
+    return out;
+}
 
 void cvf_release(CvFactorWork &wk);

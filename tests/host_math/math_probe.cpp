@@ -30,3 +30,29 @@ extern "C" long probe_exp_mismatches(double lo, double hi, long n, int log_unifo
     }
     return bad;
 }
+/* largest |cv_log_tab(x) - logl(x)| / (1 + |logl(x)|) over n log-uniform arguments in [lo, hi) */
+extern "C" double probe_log_tab_worst(double lo, double hi, long n, unsigned long long seed)
+{
+    static double tab[2 * CV_LOG_N];
+    cv_log_table(tab);
+    unsigned long long s = seed ? seed : 88172645463325252ULL;
+    double worst = 0.0;
+    for (long i = 0; i < n; i++) {
+        s ^= s << 13;
+        s ^= s >> 7;
+        s ^= s << 17;
+        double u = (double)(s >> 11) * (1.0 / 9007199254740992.0);
+        double x = exp(log(lo) + u * (log(hi) - log(lo)));
+        long double want = logl((long double)x);
+        double err = (double)(fabsl((long double)cv_log_tab(x, tab) - want) / (1.0L + fabsl(want)));
+        if (err > worst)
+            worst = err;
+    }
+    return worst;
+}
+extern "C" double probe_log_tab(double x)
+{
+    static double tab[2 * CV_LOG_N];
+    cv_log_table(tab);
+    return cv_log_tab(x, tab);
+}
