@@ -40,7 +40,12 @@ struct CvfPlan {
     int *tile_start; /* [n + 1] counts, then exclusive prefix */
     int *item_start;
     long long *w_off;
-    long long *header; /* n_groups, tiles, items, profile doubles */
+    int *a_start;    /* [n + 1] per group: K-chunks of copy weights of all its tiles, then prefix */
+    /* per tile of K2 (filled by cvf_tile_table once the number of tiles is known) */
+    int *t_first, *t_cnt, *t_nkc, *t_aoff, *t_group;
+    int *t_key, *t_key_alt, *t_order, *t_order_alt; /* tiles by descending number of K-chunks */
+    const int *t_sorted;
+    long long *header; /* n_groups, tiles, items, profile doubles, weight chunks */
 };
 
 /* slots a copy takes in a term tile of the profile kernel: S rounded up to a multiple of 4 */
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(256) cvf_group_counts(long long n, int slots_p
     if (g > n)
         return;
     const long long ng = pl.header[0];
-    int tiles = 0, items = 0;
+    int tiles = 0, items = 0, achunks = 0;
     long long w = 0;
     if (g < ng) {
         const int a = pl.g_start[g], b = pl.g_start[g + 1];
@@ -195,10 +200,16 @@ __global__ void __launch_bounds__(256) cvf_group_counts(long long n, int slots_p
         tiles = (b - a + CVF_M - 1) / CVF_M;
         items = (omax + CVF_KC - 1) / CVF_KC;
         w = (long long)items * CVF_KC * slots_padded;
+        for (int p = a; p < b; p += CVF_M) { /* K-chunks of every tile: its last point has the most copies */
+            const int last = min(p + CVF_M, b) - 1;
+            const int kmax = max(pl.othr[pl.idx_sorted[last]] - 1, 0);
+            achunks += (kmax + CVF_KC - 1) / CVF_KC;
+        }
     }
     pl.tile_start[g] = tiles;
     pl.item_start[g] = items;
     pl.w_off[g] = w;
+    pl.a_start[g] = achunks;
 }
 
 __global__ void cvf_totals(CvfPlan pl)
@@ -207,6 +218,30 @@ __global__ void cvf_totals(CvfPlan pl)
     pl.header[1] = pl.tile_start[ng];
     pl.header[2] = pl.item_start[ng];
     pl.header[3] = pl.w_off[ng];
+    pl.header[4] = pl.a_start[ng];
+}
+
+/* one thread per group: the records of its tiles */
+__global__ void __launch_bounds__(128) cvf_tile_table(int n_groups, CvfPlan pl)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups)
+        return;
+    const int a = pl.g_start[g], b = pl.g_start[g + 1];
+    int tile = pl.tile_start[g], aoff = pl.a_start[g];
+    for (int p = a; p < b; p += CVF_M, tile++) {
+        const int cnt = min(CVF_M, b - p);
+        const int kmax = max(pl.othr[pl.idx_sorted[p + cnt - 1]] - 1, 0);
+        const int nkc = (kmax + CVF_KC - 1) / CVF_KC;
+        pl.t_first[tile] = p;
+        pl.t_cnt[tile] = cnt;
+        pl.t_nkc[tile] = nkc;
+        pl.t_aoff[tile] = aoff;
+        pl.t_group[tile] = g;
+        pl.t_key[tile] = nkc;
+        pl.t_order[tile] = tile;
+        aoff += nkc;
+    }
 }
 
 /* largest g in [0, n) with start[g] <= x (start ascending, start[0] <= x) */
@@ -349,9 +384,8 @@ cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
 /* K2: GEMM + epilogue                                                                          */
 /* ------------------------------------------------------------------------------------------- */
 struct CvfSmem {
-    double2 Bs[3][CVF_TILE_DOUBLES / 2];          /* profile tiles in flight, fragment order */
-    double2 As[2][CVF_M * CVF_KC / 2];            /* copy weights of the current chunk, fragment order */
-    double q1[CVF_M], two[CVF_M], many[CVF_M], base[CVF_M];
+    double2 Bs[3][CVF_TILE_DOUBLES / 2];     /* profile tiles in flight, fragment order */
+    double2 As[3][CVF_M * CVF_KC / 2];       /* copy-weight tiles in flight, fragment order */
     double red_sum[2][CVF_M];
     double red_mh[2][CVF_M], red_ml[2][CVF_M];
     double log_tab[2 * CV_LOG_N]; /* cv_log_tab: (invc, logc) */
@@ -437,11 +471,82 @@ __device__ __forceinline__ void cvf_weights_chunk(CvfWeights &w, int kc, double 
             v[i] = 0.0;
 }
 
+/* Position (in doubles) inside a 128 x 16 tile of copy weights of (row p of the tile, copy index
+ * k % 16): the order in which the warps of K2 read their A fragments,
+ * [warp row wm][K slice][row-tile pair][lane = r * 4 + (k % 4 ^ swizzle)][row-tile parity].
+ * Row tile J = p / 8 belongs to warp row wm = J % 4 as its tile mt = J / 4, so that every warp row
+ * holds short and long rows of the sorted tile alike. */
+__device__ __forceinline__ int cvf_a_index(int p, int kin)
+{
+    const int J = p >> 3, r = p & 7, wm = J & 3, mt = J >> 2;
+    const int ks = kin >> 2, q = kin & 3;
+    return ((((wm * 4 + ks) * 2 + (mt >> 1)) * 32 + r * 4 + (q ^ ((r >> 1) & 3))) * 2) + (mt & 1);
+}
+
+/* K1b: the copy weights b(o) of models.py:193-208 of every tile of K2, masked by o < O_thr
+ * (models.py:235), written as ready-made A tiles.  One CTA per tile; thread (point, half) fills 8
+ * copies of every K-chunk, the chunk leaves through shared memory as 16-byte stores. */
+__global__ void __launch_bounds__(CVF_THREADS)
+cvf_weights_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
+                   const double *__restrict__ params, int clip, CvfPlan pl, int first_tile, int n_tiles,
+                   double *__restrict__ A, long long a_base)
+{
+    __shared__ double2 stage[CVF_M * CVF_KC / 2];
+    const int tid = threadIdx.x;
+    const int tile = first_tile + blockIdx.x;
+    if (blockIdx.x >= n_tiles)
+        return;
+    const int nkc = pl.t_nkc[tile];
+    if (nkc == 0)
+        return;
+    const int pfirst = pl.t_first[tile], cnt = pl.t_cnt[tile];
+    /* the 16 lanes of a half warp take the row tiles J and J + 4 (different halves of a 16-byte
+     * chunk of the stage): conflict-free stores */
+    const int warp = tid >> 5;
+    const int gp = 8 * ((warp & 3) + 8 * (warp >> 2) + 4 * ((tid >> 3) & 1)) + (tid & 7), half = (tid >> 4) & 1;
+    CvfWeights wg;
+    wg.q1 = wg.two = wg.many = wg.base = 0.0;
+    wg.othr = 0;
+    wg.half = half;
+    if (gp < cnt) {
+        const unsigned int pi = pl.idx_sorted[pfirst + gp];
+        double row[CV_MAX_PARAMS];
+        cvf_raw_row(m, lat, params, pi, row);
+        wg.q1 = cvf_clipped(m, row, clip, 2);
+        const double q2 = cvf_clipped(m, row, clip, 3), qq = cvf_clipped(m, row, clip, 4);
+        wg.two = cv_mul(cv_sub(1.0, wg.q1), q2);
+        wg.many = cv_mul(cv_mul(cv_sub(1.0, wg.q1), cv_sub(1.0, q2)), qq);
+        wg.base = cv_sub(1.0, qq);
+        wg.othr = pl.othr[pi];
+    }
+    {
+        const double b2 = cv_mul(wg.base, wg.base), b4 = cv_mul(b2, b2), b8 = cv_mul(b4, b4);
+        wg.b16 = cv_mul(b8, b8);
+        /* b(o) of the first copy of the thread's half in chunk 0 (half 1: o = 9, many base^6)
+         * resp. chunk 1 (half 0: o = 17, many base^14) */
+        wg.cur0 = half ? cv_mul(wg.many, cv_mul(b4, b2)) : cv_mul(wg.many, cv_mul(b8, cv_mul(b4, b2)));
+        wg.cur = wg.cur0;
+    }
+    double2 *out = reinterpret_cast<double2 *>(A + ((long long)pl.t_aoff[tile] - a_base) * (CVF_M * CVF_KC));
+    for (int kc = 0; kc < nkc; kc++) {
+        double v[8];
+        cvf_weights_chunk(wg, kc, v);
+        double *st = reinterpret_cast<double *>(stage);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            st[cvf_a_index(gp, 8 * half + i)] = v[i];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            out[(long long)kc * (CVF_M * CVF_KC / 2) + tid + j * CVF_THREADS] = stage[tid + j * CVF_THREADS];
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(CVF_THREADS, 2)
-cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
-                const double *__restrict__ params, int clip, CvfPlan pl, int n_groups, int first_tile,
-                int n_tiles, const double *__restrict__ W, long long w_base,
-                const double2 *__restrict__ slot_mh, const int *__restrict__ step_mask,
+cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_tile, int n_tiles,
+                const double *__restrict__ W, long long w_base, const double *__restrict__ A,
+                long long a_base, const double2 *__restrict__ slot_mh, const int *__restrict__ step_mask,
                 const double *__restrict__ log_tab, int nsteps, double *__restrict__ out_ll,
                 unsigned long long *counter)
 {
@@ -451,21 +556,8 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
     const int wm = warp >> 1, wn = warp & 1;
     const int r = lane >> 2, q = lane & 3;
     const int apos = r * 4 + (q ^ ((r >> 1) & 3)); /* swizzled position of the lane's A chunk */
-    /* The 128 points of a tile are sorted by O_thr.  Row tile J (8 points) belongs to warp row
-     * wm = J % 4 as its tile mt = J / 4, so that every warp row holds short and long rows alike. */
-    /* generator role: point gp of the tile, copies 8 half + 1 .. 8 half + 8 of every chunk; the
-     * 16 lanes of a half warp take the row tiles J and J + 4 (different halves of a 16-byte chunk) */
-    const int gp = 8 * ((warp & 3) + 8 * (warp >> 2) + 4 * ((tid >> 3) & 1)) + (tid & 7), half = (tid >> 4) & 1;
-    int a_at[2]; /* position (doubles) of the thread's first weight of each of its two K slices */
     for (int i = tid; i < 2 * CV_LOG_N; i += CVF_THREADS)
         S.log_tab[i] = log_tab[i];
-    {
-        const int g_wm = (gp >> 3) & 3, g_mt = gp >> 5, g_r = gp & 7;
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-            a_at[j] = (((g_wm * 4 + 2 * half + j) * 2 + (g_mt >> 1)) * 32 + g_r * 4) * 2 + (g_mt & 1);
-    }
-    const int a_sw = (gp >> 1) & 3; /* (g_r >> 1) & 3 */
     /* loader role: 16-byte chunks tid and tid + 256 of a profile tile ([copy][pair]) go to the
      * fragment order [N half][K slice][n-tile pair][lane = (column % 8) * 4 + copy % 4] */
     int b_dst[2];
@@ -484,38 +576,22 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
         __syncthreads();
         if (S.tile >= n_tiles)
             break;
-        const int tile = first_tile + S.tile;
-        const int g = cvf_find(pl.tile_start, n_groups, tile);
-        const int pfirst = pl.g_start[g] + (tile - pl.tile_start[g]) * CVF_M;
-        const int cnt = min(CVF_M, pl.g_start[g + 1] - pfirst);
+        const int tile = pl.t_sorted[S.tile]; /* longest tiles first */
+        const int pfirst = pl.t_first[tile], cnt = pl.t_cnt[tile], nkc = pl.t_nkc[tile];
+        const int g = pl.t_group[tile];
         if (tid < CVF_M) {
-            double q1 = 0.0, two = 0.0, many = 0.0, base = 0.0;
-            int othr = 0;
             unsigned int pi = 0;
+            int othr = 0;
             if (tid < cnt) {
                 pi = pl.idx_sorted[pfirst + tid];
-                double row[CV_MAX_PARAMS];
-                cvf_raw_row(m, lat, params, pi, row);
-                q1 = cvf_clipped(m, row, clip, 2);
-                const double q2 = cvf_clipped(m, row, clip, 3), qq = cvf_clipped(m, row, clip, 4);
-                two = cv_mul(cv_sub(1.0, q1), q2);
-                many = cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), qq);
-                base = cv_sub(1.0, qq);
                 othr = pl.othr[pi];
             }
-            S.q1[tid] = q1;
-            S.two[tid] = two;
-            S.many[tid] = many;
-            S.base[tid] = base;
             S.othr[tid] = othr;
             S.pidx[tid] = pi;
         }
         __syncthreads();
-        int kmax = S.othr[cnt - 1] - 1; /* ascending inside the tile */
-        if (kmax < 0)
-            kmax = 0;
-        const int nkc = (kmax + CVF_KC - 1) / CVF_KC;
         const double *Wg = W + (pl.w_off[g] - w_base);
+        const double2 *Ag = reinterpret_cast<const double2 *>(A + ((long long)pl.t_aoff[tile] - a_base) * (CVF_M * CVF_KC));
         const int total = nsteps * nkc;
         /* copies the 8 points of each of the warp's row tiles need (ascending: the last live one) */
         int kend[4];
@@ -524,35 +600,10 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
             const int first = 8 * (4 * mt + wm);
             kend[mt] = first < cnt ? S.othr[min(first + 7, cnt - 1)] - 1 : 0;
         }
-        const int kend_warp = max(max(kend[0], kend[1]), max(kend[2], kend[3]));
+        const int kend_hi = max(max(kend[0], kend[1]), max(kend[2], kend[3]));
+        const int kend_lo = min(min(kend[0], kend[1]), min(kend[2], kend[3]));
 
-        CvfWeights wg;
-        wg.q1 = S.q1[gp];
-        wg.two = S.two[gp];
-        wg.many = S.many[gp];
-        wg.base = S.base[gp];
-        wg.othr = S.othr[gp];
-        wg.half = half;
-        {
-            const double b2 = cv_mul(wg.base, wg.base), b4 = cv_mul(b2, b2), b8 = cv_mul(b4, b4);
-            wg.b16 = cv_mul(b8, b8);
-            /* b(o) of the first copy of the thread's half in chunk 0 (half 1: o = 9, many base^6)
-             * resp. chunk 1 (half 0: o = 17, many base^14) */
-            wg.cur0 = half ? cv_mul(wg.many, cv_mul(b4, b2)) : cv_mul(wg.many, cv_mul(b8, cv_mul(b4, b2)));
-            wg.cur = wg.cur0;
-        }
-        int gen_kc = 0; /* chunk index inside the N-step of the next weights to generate */
-        auto gen = [&](int t) { /* copy weights of chunk t into As[t & 1] */
-            double v[8];
-            cvf_weights_chunk(wg, gen_kc, v);
-            if (++gen_kc == nkc)
-                gen_kc = 0;
-            double *as = reinterpret_cast<double *>(S.As[t & 1]);
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                as[a_at[i >> 2] + (((i & 3) ^ a_sw) << 1)] = v[i];
-        };
-        int ld_kc = 0, ld_ns = 0, ld_buf = 0; /* the next profile tile to request */
+        int ld_kc = 0, ld_ns = 0, ld_buf = 0; /* the next (profile, weight) tile pair to request */
         auto issue = [&]() {
             if (ld_ns < nsteps) {
                 const double2 *src = reinterpret_cast<const double2 *>(
@@ -560,6 +611,11 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
                 double2 *dst = S.Bs[ld_buf];
                 cvf_cp_async16(dst + b_dst[0], src + tid);
                 cvf_cp_async16(dst + b_dst[1], src + tid + CVF_THREADS);
+                const double2 *asrc = Ag + (long long)ld_kc * (CVF_M * CVF_KC / 2);
+                double2 *adst = S.As[ld_buf];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    cvf_cp_async16(adst + tid + j * CVF_THREADS, asrc + tid + j * CVF_THREADS);
                 if (++ld_kc == nkc) {
                     ld_kc = 0;
                     ld_ns++;
@@ -572,33 +628,42 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ C
             ld_ns = nsteps; /* nothing to load */
         issue();
         issue();
-        if (total > 0)
-            gen(0);
 
         double sum[4] = {0.0, 0.0, 0.0, 0.0};
         double mass_h[4] = {0.0, 0.0, 0.0, 0.0}, mass_l[4] = {0.0, 0.0, 0.0, 0.0};
-        int t = 0, cons_buf = 0;
+        int cons_buf = 0;
         for (int ns = 0; ns < nsteps; ns++) {
             double acc[32];
 #pragma unroll
             for (int i = 0; i < 32; i++)
                 acc[i] = 0.0;
-            for (int kc = 0; kc < nkc; kc++, t++, cons_buf = cons_buf == 2 ? 0 : cons_buf + 1) {
+            for (int kc = 0; kc < nkc; kc++, cons_buf = cons_buf == 2 ? 0 : cons_buf + 1) {
                 cvf_cp_wait1();
-                __syncthreads(); /* weights of chunk t written, profile tile t landed, chunk t - 1 consumed */
+                __syncthreads(); /* this chunk's tiles landed, the previous chunk is consumed */
                 issue();
-                if (t + 1 < total)
-                    gen(t + 1);
                 const int k0 = kc * CVF_KC;
-                if (k0 < kend_warp) {
-                    const int nks = min(4, (kend_warp - k0 + 3) >> 2);
-                    const double2 *as2 = S.As[t & 1];
-                    const double2 *bs2 = S.Bs[cons_buf];
+                if (k0 >= kend_hi)
+                    continue;
+                const double2 *as2 = S.As[cons_buf] + (wm * 4) * 2 * 32 + apos;
+                const double2 *bs2 = S.Bs[cons_buf] + (wn * 4) * 2 * 32 + lane;
+                if (k0 + CVF_KC <= kend_lo) { /* every row tile uses the whole chunk */
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const double2 a01 = as2[(ks * 2 + 0) * 32], a23 = as2[(ks * 2 + 1) * 32];
+                        const double2 b01 = bs2[(ks * 2 + 0) * 32], b23 = bs2[(ks * 2 + 1) * 32];
+                        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                            for (int nt = 0; nt < 4; nt++)
+                                cv_dmma(acc[(mt * 4 + nt) * 2], acc[(mt * 4 + nt) * 2 + 1], a[mt], b[nt]);
+                    }
+                } else {
+                    const int nks = min(4, (kend_hi - k0 + 3) >> 2);
                     for (int ks = 0; ks < nks; ks++) {
-                        const double2 a01 = as2[((wm * 4 + ks) * 2 + 0) * 32 + apos];
-                        const double2 a23 = as2[((wm * 4 + ks) * 2 + 1) * 32 + apos];
-                        const double2 b01 = bs2[((wn * 4 + ks) * 2 + 0) * 32 + lane];
-                        const double2 b23 = bs2[((wn * 4 + ks) * 2 + 1) * 32 + lane];
+                        const double2 a01 = as2[(ks * 2 + 0) * 32], a23 = as2[(ks * 2 + 1) * 32];
+                        const double2 b01 = bs2[(ks * 2 + 0) * 32], b23 = bs2[(ks * 2 + 1) * 32];
                         const double a[4] = {a01.x, a01.y, a23.x, a23.y};
                         const double b[4] = {b01.x, b01.y, b23.x, b23.y};
                         const int kk = k0 + 4 * ks;
@@ -725,14 +790,16 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     const int nsteps = slots_padded / CVF_NS;
 
     /* ---- carve the plan ---- */
-    size_t sort_tmp = 0, scan_tmp_i = 0, scan_tmp_l = 0;
+    size_t sort_tmp = 0, sort_tmp_t = 0, scan_tmp_i = 0, scan_tmp_l = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned long long *)nullptr,
                                     (unsigned long long *)nullptr, (unsigned int *)nullptr,
                                     (unsigned int *)nullptr, (int)n, 0, 32 + CVF_OBITS, stream);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp_t, (int *)nullptr, (int *)nullptr,
+                                              (int *)nullptr, (int *)nullptr, (int)n, 0, 32, stream);
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_i, (int *)nullptr, (int *)nullptr, (int)n + 1, stream);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_l, (long long *)nullptr, (long long *)nullptr,
                                   (int)n + 1, stream);
-    const size_t tmp_bytes = std::max(sort_tmp, std::max(scan_tmp_i, scan_tmp_l)) + 256;
+    const size_t tmp_bytes = std::max(std::max(sort_tmp, sort_tmp_t), std::max(scan_tmp_i, scan_tmp_l)) + 256;
     const size_t n1 = (size_t)n + 1;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -743,6 +810,10 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     const size_t o_keys = take(n * 8), o_keys_alt = take(n * 8), o_idx = take(n * 4), o_idx_alt = take(n * 4);
     const size_t o_othr = take(n * 4), o_head = take(n * 4), o_gid = take(n * 4);
     const size_t o_gstart = take(n1 * 4), o_tile = take(n1 * 4), o_item = take(n1 * 4), o_woff = take(n1 * 8);
+    const size_t o_astart = take(n1 * 4);
+    size_t o_t[9];
+    for (size_t &o : o_t)
+        o = take(n1 * 4);
     const size_t o_header = take(64), o_tmp = take(tmp_bytes);
     if (off > wk.plan_cap) {
         if (wk.plan)
@@ -773,6 +844,17 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     pl.tile_start = (int *)(base + o_tile);
     pl.item_start = (int *)(base + o_item);
     pl.w_off = (long long *)(base + o_woff);
+    pl.a_start = (int *)(base + o_astart);
+    pl.t_first = (int *)(base + o_t[0]);
+    pl.t_cnt = (int *)(base + o_t[1]);
+    pl.t_nkc = (int *)(base + o_t[2]);
+    pl.t_aoff = (int *)(base + o_t[3]);
+    pl.t_group = (int *)(base + o_t[4]);
+    pl.t_key = (int *)(base + o_t[5]);
+    pl.t_key_alt = (int *)(base + o_t[6]);
+    pl.t_order = (int *)(base + o_t[7]);
+    pl.t_order_alt = (int *)(base + o_t[8]);
+    pl.t_sorted = nullptr;
     pl.header = (long long *)(base + o_header);
     void *tmp = base + o_tmp;
 
@@ -806,32 +888,39 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.item_start, pl.item_start, (int)n + 1, stream));
         tb_ = tmp_bytes;
         CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.w_off, pl.w_off, (int)n + 1, stream));
+        tb_ = tmp_bytes;
+        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.a_start, pl.a_start, (int)n + 1, stream));
     }
     cvf_totals<<<1, 1, 0, stream>>>(pl);
     CVF_CK(cudaGetLastError());
-    CVF_CK(cudaMemcpyAsync(wk.h_header, pl.header, 4 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    CVF_CK(cudaMemcpyAsync(wk.h_header, pl.header, 5 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
     CVF_CK(cudaStreamSynchronize(stream));
-    wk.launches += 9;
+    wk.launches += 10;
     const long long n_groups = wk.h_header[0], n_tiles = wk.h_header[1], n_items = wk.h_header[2];
-    const long long w_total = wk.h_header[3];
+    const long long w_total = wk.h_header[3], a_total = wk.h_header[4];
     wk.n_groups = n_groups;
     wk.n_tiles = n_tiles;
     wk.n_items = n_items;
     wk.w_doubles = w_total;
     if (n_groups <= 0 || (double)n < min_group * (double)n_groups)
         return cudaSuccess; /* too little sharing: the per-point kernel is the better tool */
+    cvf_tile_table<<<(unsigned int)((n_groups + 127) / 128), 128, 0, stream>>>((int)n_groups, pl);
+    CVF_CK(cudaGetLastError());
+    wk.launches++;
 
-    /* ---- group ranges that fit the workspace ---- */
+    /* ---- group ranges whose profiles fit the workspace ---- */
     std::vector<int> cut; /* group boundaries */
     cut.push_back(0);
-    std::vector<int> h_tile, h_item;
+    std::vector<int> h_tile, h_item, h_achunk;
     std::vector<long long> h_woff;
     if ((size_t)w_total > w_limit) {
         h_tile.resize(n_groups + 1);
         h_item.resize(n_groups + 1);
+        h_achunk.resize(n_groups + 1);
         h_woff.resize(n_groups + 1);
         CVF_CK(cudaMemcpyAsync(h_tile.data(), pl.tile_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaMemcpyAsync(h_item.data(), pl.item_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
+        CVF_CK(cudaMemcpyAsync(h_achunk.data(), pl.a_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaMemcpyAsync(h_woff.data(), pl.w_off, (n_groups + 1) * 8, cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaStreamSynchronize(stream));
         int g0 = 0;
@@ -845,22 +934,25 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     } else {
         cut.push_back((int)n_groups);
     }
-    size_t w_need = 0;
+    const bool ranged = !h_woff.empty();
+    size_t w_need = 0, a_need = 0;
     for (size_t i = 0; i + 1 < cut.size(); i++) {
-        long long a = h_woff.empty() ? 0 : h_woff[cut[i]];
-        long long b = h_woff.empty() ? w_total : h_woff[cut[i + 1]];
-        w_need = std::max(w_need, (size_t)(b - a));
+        const long long wa = ranged ? h_woff[cut[i]] : 0, wb_ = ranged ? h_woff[cut[i + 1]] : w_total;
+        const long long aa = ranged ? h_achunk[cut[i]] : 0, ab = ranged ? h_achunk[cut[i + 1]] : a_total;
+        w_need = std::max(w_need, (size_t)(wb_ - wa));
+        a_need = std::max(a_need, (size_t)(ab - aa) * (CVF_M * CVF_KC));
     }
-    if (w_need > wk.w_cap) {
+    if (w_need + a_need > wk.w_cap) { /* profiles, then the copy-weight tiles */
         if (wk.W)
             cudaFree(wk.W);
         wk.W = nullptr;
         wk.w_cap = 0;
-        CVF_CK(cudaMalloc((void **)&wk.W, std::max(w_need, (size_t)1) * sizeof(double)));
-        wk.w_cap = w_need;
+        CVF_CK(cudaMalloc((void **)&wk.W, std::max(w_need + a_need, (size_t)2) * sizeof(double)));
+        wk.w_cap = w_need + a_need;
     }
+    double *A = wk.W + w_need;
 
-    /* ---- K1 / K2 per range ---- */
+    /* ---- K1 / K1b / K2 per range ---- */
     const size_t wb = cv_warp_bytes(m.n_err);
     const int groups_staged = m.n_blocks * CV_GB;
     const size_t tab = (size_t)groups_staged * CV_GD * sizeof(double);
@@ -876,9 +968,10 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         CVF_CK(cudaEventRecord(wk.ev[1], stream));
     for (size_t i = 0; i + 1 < cut.size(); i++) {
         const int g0 = cut[i], g1 = cut[i + 1];
-        const int item0 = h_item.empty() ? 0 : h_item[g0], item1 = h_item.empty() ? (int)n_items : h_item[g1];
-        const int tile0 = h_tile.empty() ? 0 : h_tile[g0], tile1 = h_tile.empty() ? (int)n_tiles : h_tile[g1];
-        const long long w0 = h_woff.empty() ? 0 : h_woff[g0];
+        const int item0 = ranged ? h_item[g0] : 0, item1 = ranged ? h_item[g1] : (int)n_items;
+        const int tile0 = ranged ? h_tile[g0] : 0, tile1 = ranged ? h_tile[g1] : (int)n_tiles;
+        const long long w0 = ranged ? h_woff[g0] : 0;
+        const long long a0 = ranged ? h_achunk[g0] : 0;
         CVF_CK(cudaMemsetAsync(wk.d_counters, 0, 2 * sizeof(unsigned long long), stream));
         if (item1 > item0) {
             const int items = item1 - item0;
@@ -891,17 +984,24 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
             CVF_CK(cudaGetLastError());
             wk.launches++;
         }
-        if (wk.timed && i + 2 == cut.size())
-            CVF_CK(cudaEventRecord(wk.ev[2], stream));
         if (tile1 > tile0) {
             const int tiles = tile1 - tile0;
+            cvf_weights_kernel<<<tiles, CVF_THREADS, 0, stream>>>(m, lat, params, clip, pl, tile0, tiles, A, a0);
+            CVF_CK(cudaGetLastError());
+            /* tiles of the range by descending number of K-chunks: the long ones start first */
+            cub::DoubleBuffer<int> dk(pl.t_key + tile0, pl.t_key_alt + tile0);
+            cub::DoubleBuffer<int> dv(pl.t_order + tile0, pl.t_order_alt + tile0);
+            size_t tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb_, dk, dv, tiles, 0, 32, stream));
+            pl.t_sorted = dv.Current();
+            if (wk.timed && i + 2 == cut.size())
+                CVF_CK(cudaEventRecord(wk.ev[2], stream));
             int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;
             cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(
-                m, lat, params, clip, pl, (int)n_groups, tile0, tiles, wk.W, w0, slot_mh, step_mask, log_tab, nsteps,
-                out_ll,
+                m, pl, tile0, tiles, wk.W, w0, A, a0, slot_mh, step_mask, log_tab, nsteps, out_ll,
                 wk.d_counters + 1);
             CVF_CK(cudaGetLastError());
-            wk.launches++;
+            wk.launches += 3;
         }
     }
     if (wk.timed)
