@@ -383,9 +383,10 @@ cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
 /* ------------------------------------------------------------------------------------------- */
 /* K2: GEMM + epilogue                                                                          */
 /* ------------------------------------------------------------------------------------------- */
+#define CVF_STAGES 4
 struct CvfSmem {
-    double2 Bs[3][CVF_TILE_DOUBLES / 2];     /* profile tiles in flight, fragment order */
-    double2 As[3][CVF_M * CVF_KC / 2];       /* copy-weight tiles in flight, fragment order */
+    double2 Bs[CVF_STAGES][CVF_TILE_DOUBLES / 2];     /* profile tiles in flight, fragment order */
+    double2 As[CVF_STAGES][CVF_M * CVF_KC / 2];       /* copy-weight tiles in flight, fragment order */
     double red_sum[2][CVF_M];
     double red_mh[2][CVF_M], red_ml[2][CVF_M];
     double log_tab[2 * CV_LOG_N]; /* cv_log_tab: (invc, logc) */
@@ -400,7 +401,10 @@ __device__ __forceinline__ void cvf_cp_async16(void *dst_smem, const void *src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cvf_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cvf_cp_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+__device__ __forceinline__ void cvf_cp_wait_pipe()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(CVF_STAGES - 2) : "memory");
+}
 __device__ __forceinline__ void cvf_cp_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 __device__ __forceinline__ void cvf_two_sum_acc(double &hi, double &lo, double x)
@@ -469,6 +473,34 @@ __device__ __forceinline__ void cvf_weights_chunk(CvfWeights &w, int kc, double 
     for (int i = 0; i < 8; i++)
         if (!(o_first + i < w.othr)) /* models.py:235: copies o < O_thr */
             v[i] = 0.0;
+}
+
+/* The MMAs of one K-chunk for the row tiles LO .. HI - 1 of a warp: 4 K slices x (HI - LO) row
+ * tiles x 4 column tiles.  as2 / bs2 point at the lane's chunk of K slice 0. */
+template <int LO, int HI>
+__device__ __forceinline__ void cvf_chunk_mma(double *acc, const double2 *as2, const double2 *bs2)
+{
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        if (LO < 2) {
+            const double2 a01 = as2[(ks * 2 + 0) * 32];
+            a[0] = a01.x;
+            a[1] = a01.y;
+        }
+        if (HI > 2) {
+            const double2 a23 = as2[(ks * 2 + 1) * 32];
+            a[2] = a23.x;
+            a[3] = a23.y;
+        }
+        const double2 b01 = bs2[(ks * 2 + 0) * 32], b23 = bs2[(ks * 2 + 1) * 32];
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int mt = LO; mt < HI; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+                cv_dmma(acc[(mt * 4 + nt) * 2], acc[(mt * 4 + nt) * 2 + 1], a[mt], b[nt]);
+    }
 }
 
 /* Position (in doubles) inside a 128 x 16 tile of copy weights of (row p of the tile, copy index
@@ -548,7 +580,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
                 const double *__restrict__ W, long long w_base, const double *__restrict__ A,
                 long long a_base, const double2 *__restrict__ slot_mh, const int *__restrict__ step_mask,
                 const double *__restrict__ log_tab, int nsteps, double *__restrict__ out_ll,
-                unsigned long long *counter)
+                unsigned long long *counter, int dbg)
 {
     extern __shared__ __align__(16) unsigned char cvf_smem_raw[];
     CvfSmem &S = *reinterpret_cast<CvfSmem *>(cvf_smem_raw);
@@ -601,11 +633,15 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
             kend[mt] = first < cnt ? S.othr[min(first + 7, cnt - 1)] - 1 : 0;
         }
         const int kend_hi = max(max(kend[0], kend[1]), max(kend[2], kend[3]));
-        const int kend_lo = min(min(kend[0], kend[1]), min(kend[2], kend[3]));
+        int nlive = 0; /* row tiles of this warp row that hold points */
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+            nlive += 8 * (4 * mt + wm) < cnt;
 
         int ld_kc = 0, ld_ns = 0, ld_buf = 0; /* the next (profile, weight) tile pair to request */
         auto issue = [&]() {
             if (ld_ns < nsteps) {
+                if (!(dbg & 4)) {
                 const double2 *src = reinterpret_cast<const double2 *>(
                     Wg + ((long long)ld_kc * nsteps + ld_ns) * CVF_TILE_DOUBLES);
                 double2 *dst = S.Bs[ld_buf];
@@ -616,18 +652,20 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     cvf_cp_async16(adst + tid + j * CVF_THREADS, asrc + tid + j * CVF_THREADS);
+                }
                 if (++ld_kc == nkc) {
                     ld_kc = 0;
                     ld_ns++;
                 }
-                ld_buf = ld_buf == 2 ? 0 : ld_buf + 1;
+                ld_buf = ld_buf == CVF_STAGES - 1 ? 0 : ld_buf + 1;
             }
             cvf_cp_commit();
         };
         if (nkc == 0)
             ld_ns = nsteps; /* nothing to load */
-        issue();
-        issue();
+#pragma unroll
+        for (int i = 0; i < CVF_STAGES - 1; i++)
+            issue();
 
         double sum[4] = {0.0, 0.0, 0.0, 0.0};
         double mass_h[4] = {0.0, 0.0, 0.0, 0.0}, mass_l[4] = {0.0, 0.0, 0.0, 0.0};
@@ -637,27 +675,39 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 #pragma unroll
             for (int i = 0; i < 32; i++)
                 acc[i] = 0.0;
-            for (int kc = 0; kc < nkc; kc++, cons_buf = cons_buf == 2 ? 0 : cons_buf + 1) {
-                cvf_cp_wait1();
+            for (int kc = 0; kc < nkc; kc++, cons_buf = cons_buf == CVF_STAGES - 1 ? 0 : cons_buf + 1) {
+                cvf_cp_wait_pipe();
                 __syncthreads(); /* this chunk's tiles landed, the previous chunk is consumed */
                 issue();
                 const int k0 = kc * CVF_KC;
-                if (k0 >= kend_hi)
+                if (k0 >= kend_hi || (dbg & 1))
                     continue;
                 const double2 *as2 = S.As[cons_buf] + (wm * 4) * 2 * 32 + apos;
                 const double2 *bs2 = S.Bs[cons_buf] + (wn * 4) * 2 * 32 + lane;
-                if (k0 + CVF_KC <= kend_lo) { /* every row tile uses the whole chunk */
+                /* row tiles lo .. nlive - 1 are still running (ascending copies along the sorted
+                 * rows); when none of them ends inside this chunk the MMAs need no checks */
+                int lo = 0;
+                bool partial = false;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const double2 a01 = as2[(ks * 2 + 0) * 32], a23 = as2[(ks * 2 + 1) * 32];
-                        const double2 b01 = bs2[(ks * 2 + 0) * 32], b23 = bs2[(ks * 2 + 1) * 32];
-                        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-                        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                        for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-                            for (int nt = 0; nt < 4; nt++)
-                                cv_dmma(acc[(mt * 4 + nt) * 2], acc[(mt * 4 + nt) * 2 + 1], a[mt], b[nt]);
+                for (int mt = 0; mt < 4; mt++)
+                    if (mt < nlive) {
+                        const int rem = kend[mt] - k0;
+                        lo += rem <= 0;
+                        partial |= rem > 0 && rem < CVF_KC;
+                    }
+                if (!partial) {
+                    switch (lo * 4 + nlive) {
+                    case 0 * 4 + 4: cvf_chunk_mma<0, 4>(acc, as2, bs2); break;
+                    case 1 * 4 + 4: cvf_chunk_mma<1, 4>(acc, as2, bs2); break;
+                    case 2 * 4 + 4: cvf_chunk_mma<2, 4>(acc, as2, bs2); break;
+                    case 3 * 4 + 4: cvf_chunk_mma<3, 4>(acc, as2, bs2); break;
+                    case 0 * 4 + 3: cvf_chunk_mma<0, 3>(acc, as2, bs2); break;
+                    case 1 * 4 + 3: cvf_chunk_mma<1, 3>(acc, as2, bs2); break;
+                    case 2 * 4 + 3: cvf_chunk_mma<2, 3>(acc, as2, bs2); break;
+                    case 0 * 4 + 2: cvf_chunk_mma<0, 2>(acc, as2, bs2); break;
+                    case 1 * 4 + 2: cvf_chunk_mma<1, 2>(acc, as2, bs2); break;
+                    case 0 * 4 + 1: cvf_chunk_mma<0, 1>(acc, as2, bs2); break;
+                    default: break;
                     }
                 } else {
                     const int nks = min(4, (kend_hi - k0 + 3) >> 2);
@@ -677,7 +727,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
              * tiles and slots 64 ns + 32 wn + 8 nt + 2 q + c; bit 2 nt + c of the step mask says
              * whether any of those four slots has a count */
             const int mask = want_mass ? 0xff : __ldg(step_mask + 2 * ns + wn);
-            if (mask) {
+            if (mask && !(dbg & 2)) {
 #pragma unroll
                 for (int nt = 0; nt < 4; nt++)
 #pragma unroll
@@ -999,7 +1049,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
             int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;
             cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(
                 m, pl, tile0, tiles, wk.W, w0, A, a0, slot_mh, step_mask, log_tab, nsteps, out_ll,
-                wk.d_counters + 1);
+                wk.d_counters + 1, getenv("COVEST_B200_DBG") ? atoi(getenv("COVEST_B200_DBG")) : 0);
             CVF_CK(cudaGetLastError());
             wk.launches += 3;
         }
