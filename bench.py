@@ -12,8 +12,10 @@ number of points.
 
   value      device-resident inputs, CUDA-event timed, max over ranks
   e2e        the same batch through the C ABI with HOST buffers (pinned), copies in the timed region
-  roofline   FP64 pipe: algorithmic flop of one launch / its CUDA-event duration / the DFMA peak
-             measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+  roofline   FP64 pipe, dominant kernel (cvf_gemm_kernel: copy weights x bin profiles on the FP64
+             tensor cores + the log-likelihood epilogue): its algorithmic flop per launch / its
+             CUDA-event duration / the DFMA peak measured in this run (MEASURED_PEAKS.json has no
+             FP64 figure).  `phases` breaks the whole evaluation down.
   cpu_baseline / --impl reference: the reference's own C module (oracle/_ref) driven by a Python
              restatement of models.py with a fork pool over all host cores, on a bounded sample.
 """
@@ -161,7 +163,8 @@ def workload_config(name, world, n_bins, axes):
     return {'workload': '%s: repeats model k=21 r=100, lattice %s = %d points x %d bins, %d per rank' % (
         name, 'x'.join(map(str, lens)), int(np.prod(lens)), n_bins, int(np.prod(lens)) // world),
         'bins': n_bins, 'points_per_rank': int(np.prod(lens)) // world, 'lattice': lens,
-        'max_error': 8, 'k_best': K_BEST, 'sharding': 'strided lattice slices, rank r takes index r + i*N',
+        'max_error': 8, 'k_best': K_BEST,
+        'sharding': 'whole (coverage, error_rate) groups of the lattice dealt round-robin: rank r takes groups r, r+N, ...',
         'l2': 'flushed between timed steps (256 MiB write)'}
 
 
@@ -194,8 +197,10 @@ def run_b200(args, rank, world, local_rank):
     if args.points:
         count = min(count, args.points)
 
-    # the rank's candidate points, resident in HBM
-    host_pts = workload.lattice_points(axes, first=rank, stride=world, count=count)
+    # the rank's candidate points, resident in HBM: whole (c, e) groups, dealt round-robin
+    block = int(np.prod([len(a) for a in axes[2:]]))
+    count -= count % block
+    host_pts = workload.lattice_points(axes, first=rank, stride=world, count=count, block=block)
     dev_pts = torch.from_numpy(host_pts).to(dev)
     dev_ll = torch.empty(count, dtype=torch.float64, device=dev)
     pin_pts = torch.from_numpy(host_pts).pin_memory()
@@ -203,7 +208,8 @@ def run_b200(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
 
     terms = workload.term_counts(model, host_pts)
-    flop_launch = workload.algorithmic_flop(n_bins, terms)
+    counted_bins = int(sum(1 for v in hist.values() if v))
+    work = workload.factored_flop(model, host_pts, n_bins, counted_bins)
 
     peak_tflops = ctx.fp64_peak(0) if rank == 0 else None
     peak_dmma = ctx.fp64_peak(1) if rank == 0 else None
@@ -247,13 +253,15 @@ def run_b200(args, rank, world, local_rank):
             # last_kernel_ms reports the most recent call (top-K); the loglik launch is timed below
             launches += 4  # loglik kernel + 2 top-K passes + row gather
         step_ms = [a.elapsed_time(b) for a, b in ev]
-        # dominant kernel alone, CUDA events around the launch on the launching stream
+        # the kernels of the evaluation alone, CUDA events around the launches on the launching stream
+        phases = []
         for _ in range(args.steps):
             flush.fill_(1)
             torch.cuda.synchronize()
             ctx.loglik(dev_pts, out=dev_ll, stream=stream)
             torch.cuda.synchronize()
             kernel_ms.append(ctx.last_kernel_ms()[0])
+            phases.append(ctx.last_path_info())
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -278,7 +286,16 @@ def run_b200(args, rank, world, local_rank):
     best = rows if isinstance(rows, np.ndarray) else rows.cpu().numpy()
     if rank == 0:
         km = float(np.mean(kernel_ms))
-        achieved = flop_launch / (km * 1e-3) / 1e12
+        info = phases[-1]
+        factored = info['path'] == 'factored'
+        if factored:
+            gemm_ms = float(np.mean([p['gemm_ms'] for p in phases]))
+            flop_launch = work['gemm_flop']
+            dominant, dom_ms = 'cvf_gemm_kernel', gemm_ms
+        else:
+            flop_launch = workload.algorithmic_flop(n_bins, terms)
+            dominant, dom_ms = 'cv_loglik_kernel', km
+        achieved = flop_launch / (dom_ms * 1e-3) / 1e12
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
@@ -287,15 +304,24 @@ def run_b200(args, rank, world, local_rank):
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': int(count * 5 * 8),
                     'd2h_bytes_per_step': int(count * 8 + K_BEST * 6 * 8)},
-            'gpu_launches': launches + args.steps,
+            'gpu_launches': (ctx.last_kernel_ms()[1] + 3) * 2 * args.steps,
             'clocks': clocks.summary(),
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
                          'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': None,
-                         'kernel': 'cv_loglik_kernel', 'kernel_ms': km,
+                         'kernel': dominant, 'kernel_ms': dom_ms,
                          'flop_per_launch': flop_launch, 'mean_terms_per_point': float(terms.mean()),
                          'peak_source': 'register-resident DFMA chain measured in this run (cvb_fp64_peak); '
                                         'DMMA m8n8k4 chain: %.2f TFLOP/s' % peak_dmma,
-                         'kernel_share_of_step': km * args.steps / total_ms if world == 1 else None},
+                         'kernel_share_of_step': dom_ms * args.steps / total_ms if world == 1 else None},
+            'phases': ({'path': 'factored', 'groups': info['groups'], 'tiles': info['tiles'],
+                        'profile_workspace_bytes': 8 * info['profile_doubles'],
+                        'plan_ms': float(np.mean([p['plan_ms'] for p in phases])),
+                        'profile_ms': float(np.mean([p['profile_ms'] for p in phases])),
+                        'gemm_ms': gemm_ms, 'evaluation_ms': km,
+                        'profile_flop': work['profile_flop'], 'gemm_flop': work['gemm_flop'],
+                        'counted_bins': counted_bins,
+                        'evaluation_tflops': (work['profile_flop'] + work['gemm_flop']) / (km * 1e-3) / 1e12}
+                       if factored else {'path': info['path'], 'evaluation_ms': km}),
             'best_row': [float(x) for x in best[0]],
         }
         if world == 1 and not args.no_cpu:

@@ -56,8 +56,8 @@ def load():
     L.cvb_loglik_topk.restype = ctypes.c_int
     L.cvb_loglik_topk.argtypes = [vp, i64, vp, vp, ctypes.c_int, vp, vp]
     L.cvb_lattice_eval.restype = ctypes.c_int
-    L.cvb_lattice_eval.argtypes = [vp, c_int32_p, c_double_p, i64, i64, i64, vp, ctypes.c_int, vp,
-                                   vp]
+    L.cvb_lattice_eval.argtypes = [vp, c_int32_p, c_double_p, i64, i64, i64, i64, vp, ctypes.c_int,
+                                   vp, vp]
     L.cvb_fp64_peak.restype = ctypes.c_int
     L.cvb_fp64_peak.argtypes = [vp, ctypes.c_int, ctypes.c_int, c_double_p]
     L.cvb_set_timing.restype = ctypes.c_int

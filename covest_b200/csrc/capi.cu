@@ -19,6 +19,7 @@
 
 #define CVB_CHUNK_POINTS (1LL << 22) /* staging granularity for host-resident batches */
 #define CVB_MAX_TIMED_CHUNKS 64
+#define CVB_TOPK_SORT_MIN 32768 /* batches from this size on select their top-K by a radix sort */
 
 struct cvb_ctx {
     int device = 0;
@@ -38,6 +39,8 @@ struct cvb_ctx {
     long long *d_cand_idx = nullptr, *d_sel_idx = nullptr;
     int cap_k = 0;
     int topk_ctas = 0;
+    unsigned char *d_topk_scratch = nullptr;
+    size_t cap_topk_scratch = 0;
     double *d_axes = nullptr;
     size_t cap_axes = 0;
     unsigned long long *d_counter = nullptr;
@@ -146,7 +149,7 @@ extern "C" void cvb_ctx_destroy(cvb_ctx *ctx)
         cudaFree(p);
     void *bufs[] = {ctx->d_params, ctx->d_ll,      ctx->d_probs, ctx->d_cand_ll, ctx->d_sel_ll,
                     ctx->d_rows,   ctx->d_cand_idx, ctx->d_sel_idx, ctx->d_axes,   ctx->d_counter,
-                    ctx->d_sink};
+                    ctx->d_sink,   ctx->d_topk_scratch};
     for (void *p : bufs)
         if (p)
             cudaFree(p);
@@ -494,14 +497,22 @@ static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, c
     int rc = ensure_topk(ctx, K);
     if (rc != CVB_OK)
         return rc;
-    int ctas = ctx->topk_ctas;
-    if ((long long)ctas * 1024 > n) /* small inputs: fewer, fuller slices */
-        ctas = (int)((n + 1023) / 1024);
-    if (ctas < 1)
-        ctas = 1;
-    CU(cv_launch_topk(d_ll, n, K, ctx->d_cand_ll, ctx->d_cand_idx, ctas, ctx->d_sel_ll,
-                      ctx->d_sel_idx, s),
-       "cv_topk_select launch");
+    if (n >= CVB_TOPK_SORT_MIN && n <= 0x7fffffffLL) { /* large batch: one radix sort (topk.cu) */
+        const size_t need = cv_topk_sort_bytes(n);
+        CU(grow(&ctx->d_topk_scratch, &ctx->cap_topk_scratch, need), "cudaMalloc(topk scratch)");
+        CU(cv_launch_topk_sort(d_ll, n, K, ctx->d_topk_scratch, ctx->cap_topk_scratch, ctx->d_sel_ll,
+                               ctx->d_sel_idx, s),
+           "top-K sort");
+    } else {
+        int ctas = ctx->topk_ctas;
+        if ((long long)ctas * 1024 > n) /* small inputs: fewer, fuller slices */
+            ctas = (int)((n + 1023) / 1024);
+        if (ctas < 1)
+            ctas = 1;
+        CU(cv_launch_topk(d_ll, n, K, ctx->d_cand_ll, ctx->d_cand_idx, ctas, ctx->d_sel_ll,
+                          ctx->d_sel_idx, s),
+           "cv_topk_select launch");
+    }
     const int np = ctx->desc.n_param;
     const bool r_dev = is_device_ptr(out_rows);
     double *dr = r_dev ? out_rows : ctx->d_rows;
@@ -548,12 +559,12 @@ extern "C" int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const 
 
 /* ---- lattice ------------------------------------------------------------------------------ */
 extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double *axis_values,
-                                int64_t first, int64_t stride, int64_t count, double *out_ll,
-                                int k_best, double *out_rows, void *stream)
+                                int64_t first, int64_t stride, int64_t block, int64_t count,
+                                double *out_ll, int k_best, double *out_rows, void *stream)
 {
     if (!ctx)
         return CVB_EINVAL;
-    if (!axis_len || !axis_values || first < 0 || stride < 1 || count < 0)
+    if (!axis_len || !axis_values || first < 0 || stride < 1 || block < 1 || count < 0)
         return fail(ctx, CVB_EINVAL, "bad lattice arguments");
     if (k_best < 0 || (k_best > 0 && !out_rows))
         return fail(ctx, CVB_EINVAL, "k_best > 0 needs out_rows");
@@ -570,8 +581,11 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
         total_vals += (size_t)axis_len[a];
         total_pts *= (double)axis_len[a];
     }
-    if (count > 0 && (double)first + (double)(count - 1) * (double)stride >= total_pts)
-        return fail(ctx, CVB_EINVAL, "lattice slice runs past the end of the lattice");
+    if (count > 0) {
+        const int64_t last_run = (count - 1) / block, last_in = (count - 1) % block;
+        if (((double)first + (double)last_run * (double)stride) * (double)block + (double)last_in >= total_pts)
+            return fail(ctx, CVB_EINVAL, "lattice slice runs past the end of the lattice");
+    }
     CU(grow(&ctx->d_axes, &ctx->cap_axes, total_vals), "cudaMalloc(axes)");
     CU(cudaMemcpyAsync(ctx->d_axes, axis_values, total_vals * sizeof(double), cudaMemcpyHostToDevice, s),
        "cudaMemcpyAsync(axes)");
@@ -587,6 +601,7 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     }
     lat.first = first;
     lat.stride = stride;
+    lat.block = block;
     const bool l_dev = out_ll && is_device_ptr(out_ll);
     double *dl = l_dev ? out_ll : nullptr;
     if (!dl) {

@@ -624,7 +624,6 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
         __syncthreads();
         const double *Wg = W + (pl.w_off[g] - w_base);
         const double2 *Ag = reinterpret_cast<const double2 *>(A + ((long long)pl.t_aoff[tile] - a_base) * (CVF_M * CVF_KC));
-        const int total = nsteps * nkc;
         /* copies the 8 points of each of the warp's row tiles need (ascending: the last live one) */
         int kend[4];
 #pragma unroll

@@ -9,6 +9,10 @@
 __device__ __forceinline__ void cv_lattice_point(const CvLattice &lat, long long i, double *row)
 {
     long long idx = lat.first + i * lat.stride;
+    if (lat.block > 1) {
+        const long long run = i / lat.block;
+        idx = (lat.first + run * lat.stride) * lat.block + (i - run * lat.block);
+    }
 #pragma unroll
     for (int a = CV_MAX_PARAMS - 1; a >= 0; a--) {
         if (a < lat.n_axes) {

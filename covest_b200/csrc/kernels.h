@@ -7,15 +7,17 @@
 
 #include "cvpoint.h"
 
-/* A Cartesian lattice of parameter points generated on the device: point `i` of a launch is the
- * lattice index first + i * stride, decoded with the LAST axis varying fastest (the order of
- * itertools.product, which grid.py:33 uses for its candidate grids). */
+/* A Cartesian lattice of parameter points generated on the device, decoded with the LAST axis
+ * varying fastest (the order of itertools.product, which grid.py:33 uses for its candidate
+ * grids).  A launch takes runs of `block` consecutive lattice indices: point i is the lattice
+ * index (first + (i / block) * stride) * block + i % block -- with block = 1 the strided slice
+ * first + i * stride, with block = the number of (q1, q2, q) combinations whole (c, e) groups. */
 struct CvLattice {
     int enabled;
     int n_axes;
     int len[CV_MAX_PARAMS];
     const double *axis[CV_MAX_PARAMS]; /* device pointers */
-    long long first, stride;
+    long long first, stride, block;
 };
 
 /* K1/K2: log-likelihood (and optionally the per-bin probabilities) of n_points points.
@@ -32,6 +34,12 @@ cudaError_t cv_launch_loglik(const CvModelDesc &m, const CvLattice &lat, const d
 cudaError_t cv_launch_topk(const double *ll, long long n_points, int K, double *cand_ll,
                            long long *cand_idx, int n_cta, double *out_ll, long long *out_idx,
                            cudaStream_t stream);
+
+/* K3 for large batches (topk.cu): the same selection by one stable descending radix sort of
+ * order-preserving keys.  `scratch`: device, cv_topk_sort_bytes(n) bytes. */
+size_t cv_topk_sort_bytes(long long n);
+cudaError_t cv_launch_topk_sort(const double *ll, long long n, int K, void *scratch, size_t scratch_bytes,
+                                double *out_ll, long long *out_idx, cudaStream_t stream);
 
 /* gathers rows (ll, params...) for selected indices; params from a buffer or from the lattice */
 cudaError_t cv_launch_gather_rows(const CvLattice &lat, const double *params, int n_param,

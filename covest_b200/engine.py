@@ -173,24 +173,29 @@ class LikelihoodContext:
         return ll, rows
 
     def lattice_eval(self, axes, first=0, stride=1, count=None, want_ll=True, k_best=0,
-                     out_ll=None, stream=None):
+                     out_ll=None, stream=None, block=1):
         """Evaluate the Cartesian lattice of `axes` (one 1-D array per model parameter, last axis
-        fastest) at indices first + i*stride, i < count, generating the points on the device.
-        Returns (ll or None, rows or None)."""
+        fastest), generating the points on the device: runs of `block` consecutive lattice
+        indices, run j starting at (first + j*stride)*block -- with block = 1 the indices
+        first + i*stride, i < count.  Returns (ll or None, rows or None)."""
         if len(axes) != self.n_param:
             raise ValueError('need %d axes' % self.n_param)
         lens = np.ascontiguousarray([len(a) for a in axes], dtype=np.int32)
         vals = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in axes]))
         total = int(np.prod(lens.astype(np.int64)))
         if count is None:
-            count = max(0, (total - first + stride - 1) // stride)
+            runs = (total + block - 1) // block
+            mine = max(0, (runs - first + stride - 1) // stride)
+            count = mine * block
+            if mine and (first + (mine - 1) * stride + 1) * block > total:
+                count -= (first + (mine - 1) * stride + 1) * block - total
         ll = out_ll
         if ll is None and want_ll:
             ll = np.empty(count, dtype=np.float64)
         rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64) if k_best > 0 else None
         self._check(self._lib.cvb_lattice_eval(self._ctx, lens.ctypes.data_as(_capi.c_int32_p),
                                                vals.ctypes.data_as(_capi.c_double_p), int(first),
-                                               int(stride), int(count), _ptr(ll), int(k_best),
+                                               int(stride), int(block), int(count), _ptr(ll), int(k_best),
                                                _ptr(rows), _stream_ptr(stream)), 'cvb_lattice_eval')
         return ll, rows
 

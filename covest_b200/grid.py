@@ -122,21 +122,24 @@ def initial_grid(initial_guess, count=constants.INITIAL_GRID_COUNT, bounds=None,
 
 def lattice_search(model, axes, k_best=64):
     """Best rows of a Cartesian candidate lattice, sharded over the ranks of torch.distributed
-    when it is initialised: every rank evaluates a strided slice with
-    points generated on the device, the per-rank best rows are all-gathered, and every rank
-    returns the same global (k_best, 1 + n_param) best-first array."""
+    when it is initialised: the (coverage, error_rate) groups of the
+    lattice are dealt round-robin to the ranks, every rank evaluates its groups with points
+    generated on the device, the per-rank best rows are all-gathered, and every rank returns the
+    same global (k_best, 1 + n_param) best-first array."""
     from . import parallel
-    total = int(np.prod([len(a) for a in axes]))
+    lens = [len(a) for a in axes]
+    total = int(np.prod(lens))
+    block = int(np.prod(lens[2:])) if len(lens) > 2 else 1
     ctx = model.device_context
 
-    def evaluate_slice(first, stride, count):
-        _, rows = ctx.lattice_eval(axes, first=first, stride=stride, count=count, want_ll=False,
-                                   k_best=k_best)
+    def evaluate_slice(first, stride, block, count):
+        _, rows = ctx.lattice_eval(axes, first=first, stride=stride, block=block, count=count,
+                                   want_ll=False, k_best=k_best)
         rank, world = parallel.world()
         if world > 1:
             import torch
             return torch.from_numpy(rows).to(torch.device('cuda', ctx.device))
         return rows
 
-    rows = parallel.sharded_best_rows(evaluate_slice, total, k_best)
+    rows = parallel.sharded_best_rows(evaluate_slice, total, k_best, block=block)
     return rows.cpu().numpy() if hasattr(rows, 'cpu') else np.asarray(rows)

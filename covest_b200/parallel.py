@@ -31,6 +31,20 @@ def shard_strided(total, rank, world_size):
     return rank, world_size, count
 
 
+def shard_blocked(total, block, rank, world_size):
+    """(first, stride, block, count) of the rank's slice when it takes whole runs of `block`
+    consecutive indices: runs rank, rank + W, ...  For a repeats-model lattice block is the number
+    of (q1, q2, q) combinations, so that every (coverage, error_rate) group -- whose bin profiles
+    the factored path computes once -- lives on one rank; all groups cost the same, so the split
+    is balanced."""
+    runs = (total + block - 1) // block
+    mine = (runs - rank + world_size - 1) // world_size if runs > rank else 0
+    count = mine * block
+    if mine and (rank + (mine - 1) * world_size + 1) * block > total:
+        count -= (rank + (mine - 1) * world_size + 1) * block - total
+    return rank, world_size, block, count
+
+
 def shard_contiguous(total, rank, world_size):
     """[lo, hi) of a balanced contiguous split."""
     base, extra = divmod(total, world_size)
@@ -72,13 +86,13 @@ def merge_topk(rows, k_best):
     return rows[order[:k_best]]
 
 
-def sharded_best_rows(evaluate_slice, total, k_best):
-    """Every rank evaluates its strided slice with `evaluate_slice(first, stride, count)` ->
-    (k_best, C) best-first rows, the blocks are all-gathered and merged.  Returns the global
-    k_best rows (identical on every rank)."""
+def sharded_best_rows(evaluate_slice, total, k_best, block=1):
+    """Every rank evaluates its slice (runs of `block` indices, dealt round-robin) with
+    `evaluate_slice(first, stride, block, count)` -> (k_best, C) best-first rows, the row blocks
+    are all-gathered and merged.  Returns the global k_best rows (identical on every rank)."""
     rank, w = world()
-    first, stride, count = shard_strided(total, rank, w)
-    rows = evaluate_slice(first, stride, count)
+    first, stride, block, count = shard_blocked(total, block, rank, w)
+    rows = evaluate_slice(first, stride, block, count)
     return merge_topk(allgather_rows(rows), k_best)
 
 

@@ -46,13 +46,20 @@ def lattice_axes(theta, n_c=40, n_e=25, n_q1=10, n_q2=10, n_q=10):
             np.linspace(0.3, 1.0, n_q1), np.linspace(0.0, 1.0, n_q2), np.linspace(0.05, 1.0, n_q)]
 
 
-def lattice_points(axes, first=0, stride=1, count=None):
-    """Explicit rows of a lattice slice, last axis fastest (itertools.product order)."""
+def lattice_points(axes, first=0, stride=1, count=None, block=1):
+    """Explicit rows of a lattice slice, last axis fastest (itertools.product order): runs of
+    `block` consecutive indices, run j starting at (first + j*stride)*block (the slicing of
+    cvb_lattice_eval)."""
     lens = [len(a) for a in axes]
     total = int(np.prod(lens))
     if count is None:
-        count = max(0, (total - first + stride - 1) // stride)
-    idx = first + stride * np.arange(count, dtype=np.int64)
+        runs = (total + block - 1) // block
+        mine = max(0, (runs - first + stride - 1) // stride)
+        count = mine * block
+        if mine and (first + (mine - 1) * stride + 1) * block > total:
+            count -= (first + (mine - 1) * stride + 1) * block - total
+    i = np.arange(count, dtype=np.int64)
+    idx = (first + (i // block) * stride) * block + i % block
     cols = []
     for a, n in zip(reversed(axes), reversed(lens)):
         cols.append(np.asarray(a, dtype=np.float64)[idx % n])
@@ -114,6 +121,26 @@ FLOP_PER_BIN = 64.0
 def algorithmic_flop(n_bins, terms):
     terms = np.asarray(terms, dtype=np.float64)
     return float(np.sum(n_bins * (FLOP_PER_TERM_BIN * terms + FLOP_PER_BIN)))
+
+
+def factored_flop(model, points, n_bins, counted_bins):
+    """FP64 work of the factored path on a batch:
+      profile_flop  one FMA per (error class, copy number, bin) for every copy number up to the
+                    largest cut-off of each distinct (coverage, error_rate)
+      gemm_flop     one FMA per (copy number below the point's cut-off, bin) for every point, plus
+                    64 flop per (point, bin with a non-zero count): the multiply by the bin's
+                    scale, the logarithm and the count-weighted accumulation of models.py:100-107
+    """
+    pts = _clip(model, np.asarray(points, dtype=np.float64))
+    copies = np.maximum(copy_cutoff(pts, max(model.hist), model.threshold) - 1, 0).astype(np.float64)
+    keys = np.ascontiguousarray(pts[:, :2]).view([('c', 'f8'), ('e', 'f8')]).ravel()
+    _, inverse = np.unique(keys, return_inverse=True)
+    gmax = np.zeros(inverse.max() + 1)
+    np.maximum.at(gmax, inverse, copies)
+    profile = FLOP_PER_TERM_BIN * model.max_error * n_bins * float(gmax.sum())
+    gemm = float(np.sum(FLOP_PER_TERM_BIN * n_bins * copies + FLOP_PER_BIN * counted_bins))
+    return {'profile_flop': profile, 'gemm_flop': gemm, 'groups': int(len(gmax)),
+            'mean_copies': float(copies.mean())}
 
 
 def lattice_term_stats(model, axes):

@@ -96,13 +96,17 @@ CVB_API int cvb_loglik_topk(cvb_ctx *ctx, int64_t n_points, const double *params
 
 /* A Cartesian lattice of candidate points generated on the device (no host->device parameter
  * traffic): n_param axes, axis a has axis_len[a] values stored consecutively in axis_values
- * (host).  Point i of the call is lattice index first + i * stride, last axis fastest -- the
- * order of itertools.product in covest/grid.py:33.  Evaluates `count` points; out_ll (host or
- * device, may be NULL) receives them; if k_best > 0, out_rows (host or device) receives the
- * k_best best rows as in cvb_topk. */
+ * (host), last axis fastest -- the order of itertools.product in covest/grid.py:33.  The call
+ * takes runs of `block` consecutive lattice indices: point i is the lattice index
+ * (first + (i / block) * stride) * block + i % block.  block = 1 is the strided slice
+ * first + i * stride; block = the number of (q1, q2, q) combinations hands whole
+ * (coverage, error_rate) groups to a rank, which is how the ranks of a multi-GPU run shard a
+ * repeats-model lattice (each group's bin profiles are then computed on one rank only).
+ * Evaluates `count` points; out_ll (host or device, may be NULL) receives them; if k_best > 0,
+ * out_rows (host or device) receives the k_best best rows as in cvb_topk. */
 CVB_API int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double *axis_values,
-                     int64_t first, int64_t stride, int64_t count, double *out_ll, int k_best,
-                     double *out_rows, void *stream);
+                     int64_t first, int64_t stride, int64_t block, int64_t count, double *out_ll,
+                     int k_best, double *out_rows, void *stream);
 
 /* Measures the FP64 roofline denominator on the context's device: kind 0 = dependent-free DFMA
  * chains, kind 1 = DMMA m8n8k4 chains, kind 2 = both at once (half of the warps each), all register

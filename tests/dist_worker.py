@@ -29,8 +29,10 @@ def main():
     total = int(np.prod([len(a) for a in axes]))
     k_best = 8
 
-    def evaluate_slice(first, stride, count):
-        pts = workload.lattice_points(axes, first=first, stride=stride, count=count)
+    block = 27  # the (q1, q2, q) combinations: whole (coverage, error_rate) groups per rank
+
+    def evaluate_slice(first, stride, block, count):
+        pts = workload.lattice_points(axes, first=first, stride=stride, count=count, block=block)
         ll = model.loglik_batch(pts, threads=2)
         key = np.where(np.isnan(ll), -np.inf, ll)
         order = np.lexsort((np.arange(len(key)), -key))[:k_best]
@@ -41,14 +43,14 @@ def main():
             rows = np.vstack([rows, pad])
         return torch.from_numpy(rows)
 
-    rows = parallel.sharded_best_rows(evaluate_slice, total, k_best)
+    rows = parallel.sharded_best_rows(evaluate_slice, total, k_best, block=block)
     mine = parallel.split_starts(rows)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine.numpy().tolist())
     if rank == 0:
         with open(out_path, 'w') as f:
             json.dump({'world': world, 'rows': rows.numpy().tolist(), 'starts': gathered,
-                       'slice': list(parallel.shard_strided(total, rank, world))}, f)
+                       'slice': list(parallel.shard_blocked(total, block, rank, world))}, f)
     dist.barrier()
     dist.destroy_process_group()
 

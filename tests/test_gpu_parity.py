@@ -135,6 +135,33 @@ def test_lattice_equals_explicit_points_and_topk():
         assert np.all(np.isneginf(rows3[5:, 0])) and np.all(np.isnan(rows3[5:, 1:]))
 
 
+def test_topk_of_a_large_batch_equals_the_selection_order():
+    """Batches of >= 32768 points select their top-K by a radix sort (topk.cu): same total order
+    as the small-batch kernel -- larger first, ties to the lower index, NaN as -inf."""
+    case = load_case('e05_repeats')
+    m = _model(case)
+    rng = np.random.default_rng(21)
+    n = 100000
+    ll = -np.exp(rng.uniform(0, 20, n))
+    ll[rng.choice(n, 5000, replace=False)] = -np.inf
+    ll[rng.choice(n, 300, replace=False)] = np.nan
+    top = np.sort(ll[np.isfinite(ll)])[-40]
+    ll[rng.choice(n, 50, replace=False)] = top  # ties inside the selection
+    pts = rng.uniform(0.1, 1, (n, 5))
+    key = np.where(np.isnan(ll), -np.inf, ll)
+    order = np.lexsort((np.arange(n), -key))
+    with context_for(m) as ctx:
+        rows = ctx.topk(ll, pts, 128)
+        assert np.array_equal(rows[:, 0], key[order[:128]])
+        assert np.array_equal(rows[:, 1:], pts[order[:128]])
+        few = ctx.topk(ll[:1000], pts[:1000], 16)  # small batch: the selection kernel
+        o2 = np.lexsort((np.arange(1000), -key[:1000]))[:16]
+        assert np.array_equal(few[:, 1:], pts[o2])
+        allbad = np.full(40000, np.nan)
+        rows = ctx.topk(allbad, pts[:40000], 4)
+        assert np.all(np.isneginf(rows[:, 0])) and np.array_equal(rows[:, 1:], pts[:4])
+
+
 def test_full_size_properties_cfg3():
     """BASELINE.json configs[2] shape (repeats, 1000 dense bins) at a batch the oracle could not
     finish: q1 = 1 makes the repeats model the basic model (SURVEY.md section 8(c) invariants),

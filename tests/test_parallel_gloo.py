@@ -32,6 +32,17 @@ def test_lattice_points_order_is_itertools_product():
     want = np.array(list(itertools.product(*axes)))
     assert np.array_equal(workload.lattice_points(axes), want)
     assert np.array_equal(workload.lattice_points(axes, first=1, stride=5), want[1::5])
+    # runs of `block` consecutive indices, dealt round-robin: the slicing of cvb_lattice_eval
+    n = len(want)
+    for w in (2, 3):
+        seen = []
+        for r in range(w):
+            first, stride, block, count = parallel.shard_blocked(n, 4, r, w)
+            part = workload.lattice_points(axes, first=first, stride=stride, count=count, block=block)
+            idx = [(first + (i // block) * stride) * block + i % block for i in range(count)]
+            assert np.array_equal(part, want[idx])
+            seen += idx
+        assert sorted(seen) == list(range(n))
 
 
 def test_world_size_two_equals_single_process(tmp_path):
