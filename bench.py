@@ -116,6 +116,48 @@ def cpu_reference_rate(hist, cfg, axes, n_points, cores):
     return n_points * len(hist) / dt, dt, kind
 
 
+def covest_end_to_end(cores):
+    """Wall time of the estimator flow (process_histogram -> model -> CoverageEstimator, the body of
+    `covest cfg2.hist -m repeat -k 21 -r 100 -sf 1`) on the synthetic cfg2 histogram: on the device,
+    and with the likelihood routed to the reference's own C module over a fork pool of all host
+    cores (the same batches, so both arms follow the same optimiser path)."""
+    from covest_b200 import constants
+    from covest_b200.covest import CoverageEstimator
+    from covest_b200.histogram import process_histogram
+    from covest_b200.models import RepeatsModel
+    from oracle import covest_oracle as orc
+    constants.VERBOSE = False
+    with open(os.path.join(ROOT, 'tests', 'golden', 'e2e_golden.json')) as f:
+        g = json.load(f)['cfg2_repeats']
+    hist = {int(j): int(h) for j, h in g['hist']}
+
+    def flow(cls):
+        t0 = time.perf_counter()
+        h2, tail, sf, gc, ge = process_histogram(hist, g['k'], g['r'], sample_factor=1)
+        model = cls(g['k'], g['r'], h2, tail, max_error=8)
+        guess = list(model.defaults)
+        guess[:2] = gc, ge
+        est = CoverageEstimator(model)
+        x, ok = est.compute_coverage(guess)
+        return time.perf_counter() - t0, [float(v) for v in x], est.evaluations
+
+    class CpuRepeats(RepeatsModel):  # likelihood on the host cores, everything else unchanged
+        def loglikelihood_batch(self, points):
+            m = orc.Model('repeats', self.k, self.r, self.hist, self.tail, max_error=self.max_error)
+            pts = np.asarray(points, dtype=np.float64).reshape(-1, self.param_count)
+            if orc.ref_module() is not None:
+                return orc.ref_loglik_batch(m, pts, processes=min(cores, len(pts)))
+            return m.loglik_batch(pts, mode=orc.FAITHFUL, threads=cores)
+
+    flow(RepeatsModel)  # warm-up: context creation, first launches
+    dev_s, dev_x, dev_n = flow(RepeatsModel)
+    cpu_s, cpu_x, cpu_n = flow(CpuRepeats)
+    return {'workload': 'cfg2: repeats model k=21 r=100, %d bins, single start, L-BFGS-B' % len(hist),
+            'device_s': dev_s, 'device_coverage': dev_x[0], 'device_evaluations': dev_n,
+            'cpu_s': cpu_s, 'cpu_coverage': cpu_x[0], 'cpu_evaluations': cpu_n, 'cpu_cores': cores,
+            'cpu_kind': 'reference' if orc.ref_module() is not None else 'port'}
+
+
 def reference_histogram(name):
     """The workload histogram for the CPU-only reference arm: drawn from the oracle's p_j (the
     product arm draws it from the device's, the same numbers to ~1e-15)."""
@@ -334,6 +376,10 @@ def run_b200(args, rank, world, local_rank):
                 rate, dt, kind = cpu_reference_rate(ref_hist, cfg, axes, n_cpu, cores)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': kind,
                                     'sample': '%d seeded lattice points x %d bins in %.1f s' % (n_cpu, n_bins, dt)}
+            try:  # BASELINE.json's second figure: covest end-to-end wall time
+                line['covest_e2e'] = covest_end_to_end(cores)
+            except Exception as exc:  # never lose the throughput line over the extra figure
+                line['covest_e2e'] = {'error': repr(exc)}
         print(json.dumps(line), flush=True)
     barrier()
     if world > 1:

@@ -156,6 +156,16 @@ def ref_module():
         return None
 
 
+def _guard_zero_rate(tp):
+    """`truncated_poisson(0, j)` is undefined behaviour in the reference (c:15-17 passes an int
+    through "d" varargs): it returns whatever the xmm register held, sometimes NaN, always times a
+    weight that is exactly 0.  This wrapper returns the 0 the source intends, so that the CPU arm
+    does not depend on register garbage."""
+    def guarded(l, j):
+        return tp(l, j) if l else 0.0
+    return guarded
+
+
 def py_probs(model, params, tp):
     """models.py:81-98 (basic) / :211-242 (repeats) with `tp` as truncated_poisson."""
     k, r, S = model.k, model.r, model.max_error
@@ -163,6 +173,8 @@ def py_probs(model, params, tp):
     ck = c * (r - k + 1) / r
     l_s = [ck * (3 ** -s) * (1.0 - err) ** (k - s) * err ** s for s in range(S)]
     comb = model.comb
+    if not all(l_s):  # a zero rate (err = 0): see _guard_zero_rate; no overhead on ordinary points
+        tp = _guard_zero_rate(tp)
     if model.kind == BASIC:
         n_s = [comb[s] * (1.0 - math.exp(-l_s[s])) for s in range(S)]
         tot = sum(n_s)
