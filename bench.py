@@ -12,10 +12,12 @@ number of points.
 
   value      device-resident inputs, CUDA-event timed, max over ranks
   e2e        the same batch through the C ABI with HOST buffers (pinned), copies in the timed region
-  roofline   FP64 pipe, dominant kernel (cvf_gemm_kernel: copy weights x bin profiles on the FP64
-             tensor cores + the log-likelihood epilogue): its algorithmic flop per launch / its
-             CUDA-event duration / the DFMA peak measured in this run (MEASURED_PEAKS.json has no
-             FP64 figure).  `phases` breaks the whole evaluation down.
+  roofline   FP64 pipe, dominant kernel (cvf_prefix_kernel: running sums over the copy numbers per
+             q-run, three-term combination and log-likelihood epilogue per point; with
+             --path gemm cvf_gemm_kernel: copy weights x bin profiles on the FP64 tensor cores): its
+             algorithmic flop per launch / its CUDA-event duration / the DFMA peak measured in this
+             run (MEASURED_PEAKS.json has no FP64 figure).  `phases` breaks the
+             whole evaluation down.
   cpu_baseline / --impl reference: the reference's own C module (oracle/_ref) driven by a Python
              restatement of models.py with a fork pool over all host cores, on a bounded sample.
 """
@@ -232,6 +234,9 @@ def run_b200(args, rank, world, local_rank):
     hist = workload.synthetic_histogram(args.workload)
     model = RepeatsModel(cfg['k'], cfg['r'], hist, 0, max_error=8)
     ctx = model.device_context
+    if args.path != 'auto':
+        ctx.set_path({'prefix': ctx.PATH_FACTORED_PREFIX, 'gemm': ctx.PATH_FACTORED_GEMM,
+                      'direct': ctx.PATH_PER_POINT}[args.path])
     n_bins = len(hist)
     axes = workload_axes(args.workload, world)
     total = int(np.prod([len(a) for a in axes]))
@@ -332,8 +337,8 @@ def run_b200(args, rank, world, local_rank):
         factored = info['path'] == 'factored'
         if factored:
             gemm_ms = float(np.mean([p['gemm_ms'] for p in phases]))
-            flop_launch = work['gemm_flop']
-            dominant, dom_ms = 'cvf_gemm_kernel', gemm_ms
+            dominant, dom_ms = info['kernel'], gemm_ms
+            flop_launch = work['prefix_flop'] if dominant == 'cvf_prefix_kernel' else work['gemm_flop']
         else:
             flop_launch = workload.algorithmic_flop(n_bins, terms)
             dominant, dom_ms = 'cv_loglik_kernel', km
@@ -355,14 +360,15 @@ def run_b200(args, rank, world, local_rank):
                          'peak_source': 'register-resident DFMA chain measured in this run (cvb_fp64_peak); '
                                         'DMMA m8n8k4 chain: %.2f TFLOP/s' % peak_dmma,
                          'kernel_share_of_step': dom_ms * args.steps / total_ms if world == 1 else None},
-            'phases': ({'path': 'factored', 'groups': info['groups'], 'tiles': info['tiles'],
+            'phases': ({'path': 'factored', 'kernel': info['kernel'], 'groups': info['groups'],
+                        'q_runs': info['q_runs'], 'tiles': info['tiles'],
                         'profile_workspace_bytes': 8 * info['profile_doubles'],
                         'plan_ms': float(np.mean([p['plan_ms'] for p in phases])),
                         'profile_ms': float(np.mean([p['profile_ms'] for p in phases])),
-                        'gemm_ms': gemm_ms, 'evaluation_ms': km,
-                        'profile_flop': work['profile_flop'], 'gemm_flop': work['gemm_flop'],
-                        'counted_bins': counted_bins,
-                        'evaluation_tflops': (work['profile_flop'] + work['gemm_flop']) / (km * 1e-3) / 1e12}
+                        'kernel_ms': gemm_ms, 'evaluation_ms': km,
+                        'profile_flop': work['profile_flop'], 'kernel_flop': flop_launch,
+                        'counted_bins': counted_bins, 'mean_copies_per_point': work['mean_copies'],
+                        'evaluation_tflops': (work['profile_flop'] + flop_launch) / (km * 1e-3) / 1e12}
                        if factored else {'path': info['path'], 'evaluation_ms': km}),
             'best_row': [float(x) for x in best[0]],
         }
@@ -395,6 +401,8 @@ def main():
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5'])
     ap.add_argument('--points', type=int, default=0, help='cap the points per rank (development)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--path', default='auto', choices=['auto', 'prefix', 'gemm', 'direct'],
+                    help='evaluation path of the device arm (development; auto = what a user gets)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -60,7 +60,8 @@ struct cvb_ctx {
     size_t w_limit = (size_t)2 << 30; /* doubles: 16 GiB of profiles per group range */
     double min_group = 12.0;   /* auto: points per (c, e) group below which the per-point kernel runs */
     long long min_points = 2048; /* auto: batches below this go straight to the per-point kernel */
-    int last_path = 0;         /* 1 per-point, 2 factored */
+    int last_path = 0;         /* 1 per-point, 2 factored (GEMM), 3 factored (prefix kernel) */
+    double min_run = 4.0;      /* auto: points per q-run below which the GEMM runs instead of the prefix kernel */
     std::string err;
 };
 
@@ -269,7 +270,8 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
             if ((e = upload(c, lt, &c->d_log_tab)) != cudaSuccess) break;
         }
         if (const char *pm = getenv("COVEST_B200_PATH"))
-            c->path_mode = !strcmp(pm, "direct") ? 1 : !strcmp(pm, "factored") ? 2 : 0;
+            c->path_mode = !strcmp(pm, "direct") ? 1 : !strcmp(pm, "factored") ? 2 : !strcmp(pm, "gemm") ? 3
+                           : !strcmp(pm, "prefix") ? 4 : 0;
         if (const char *wl = getenv("COVEST_B200_PROFILE_MIB"))
             if (atoll(wl) > 0)
                 c->w_limit = (size_t)atoll(wl) * (1 << 20) / sizeof(double);
@@ -333,13 +335,15 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
     if (timed)
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks], s), "cudaEventRecord");
     int used = 0;
+    const bool forced = ctx->path_mode >= 2;
     const bool try_factored = !d_probs && ctx->path_mode != 1 && cvf_supported(ctx->desc) &&
-                              (ctx->path_mode == 2 || n >= ctx->min_points);
+                              (forced || n >= ctx->min_points);
     if (try_factored) {
         ctx->fw.timed = ctx->timing;
         CU(cvf_eval(ctx->desc, lat, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->d_step_mask,
                     ctx->d_log_tab, ctx->fw, ctx->n_sm,
-                    ctx->smem_max, ctx->w_limit, ctx->path_mode == 2 ? 0.0 : ctx->min_group, s, &used),
+                    ctx->smem_max, ctx->w_limit, forced ? 0.0 : ctx->min_group, ctx->min_run,
+                    ctx->path_mode == 3 ? 1 : ctx->path_mode == 4 ? 2 : 0, s, &used),
            "factored evaluation");
         ctx->last_launches += ctx->fw.launches;
     }
@@ -349,7 +353,7 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
            "cv_loglik_kernel launch");
         ctx->last_launches++;
     }
-    ctx->last_path = used ? 2 : 1;
+    ctx->last_path = used ? 1 + used : 1;
     if (timed) {
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks + 1], s), "cudaEventRecord");
         ctx->timed_chunks++;
@@ -634,8 +638,9 @@ extern "C" int cvb_set_path(cvb_ctx *ctx, int mode)
 {
     if (!ctx)
         return CVB_EINVAL;
-    if (mode < 0 || mode > 2)
-        return fail(ctx, CVB_EINVAL, "path mode must be 0 (auto), 1 (per-point) or 2 (factored)");
+    if (mode < 0 || mode > 4)
+        return fail(ctx, CVB_EINVAL, "path mode must be 0 (auto), 1 (per-point), 2 (factored), 3 (factored, GEMM) "
+                                     "or 4 (factored, prefix kernel)");
     ctx->path_mode = mode;
     return CVB_OK;
 }
@@ -647,12 +652,13 @@ extern "C" int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out)
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     double v[CVB_PATH_INFO_LEN] = {0};
     v[0] = ctx->last_path;
-    if (ctx->last_path == 2) {
+    if (ctx->last_path >= 2) {
         const CvFactorWork &w = ctx->fw;
         v[1] = (double)w.n_groups;
         v[2] = (double)w.n_tiles;
         v[3] = (double)w.n_items;
         v[4] = (double)w.w_doubles;
+        v[8] = (double)w.n_runs;
         if (w.timed && w.ev[0]) {
             float ms = 0.f;
             CU(cudaEventSynchronize(w.ev[3]), "cudaEventSynchronize");

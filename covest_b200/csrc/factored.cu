@@ -36,6 +36,10 @@ struct CvfPlan {
     const unsigned int *idx_sorted;
     int *othr;       /* by ORIGINAL point index */
     int *head, *gid; /* by sorted position */
+    int *head2, *rid; /* q-runs: points of a group that also share q (prefix path); rid = running count */
+    int *g_omax;      /* [n + 1] per group: the largest O_thr of its points */
+    int *r_start;     /* [n + 1] sorted position of the first point of a q-run */
+    int *g_rfirst;    /* [n + 1] per group: index of its first q-run */
     int *g_start;    /* [n + 1] sorted position of the first point of a group */
     int *tile_start; /* [n + 1] counts, then exclusive prefix */
     int *item_start;
@@ -45,7 +49,10 @@ struct CvfPlan {
     int *t_first, *t_cnt, *t_nkc, *t_aoff, *t_group;
     int *t_key, *t_key_alt, *t_order, *t_order_alt; /* tiles by descending number of K-chunks */
     const int *t_sorted;
-    long long *header; /* n_groups, tiles, items, profile doubles, weight chunks */
+    long long *header; /* n_groups, tiles, items, profile doubles, weight chunks, q-runs */
+    int obits;         /* bits of O_thr in the sort key: enough for max(hist) + padding */
+    int tile_points;   /* points per tile of K2 (the prefix kernel's tiles are whole q-runs) */
+    int prefix;        /* 1: sorted by (c, e), q, O_thr and tiled for the prefix kernel */
 };
 
 /* slots a copy takes in a term tile of the profile kernel: S rounded up to a multiple of 4 */
@@ -144,7 +151,18 @@ cvf_point_keys(const __grid_constant__ CvModelDesc m, const __grid_constant__ Cv
     const int othr = cvf_cutoff(m, q1, two, many, base);
     pl.othr[i] = othr;
     pl.idx[i] = (unsigned int)i;
-    pl.keys[i] = ((unsigned long long)cvf_hash(c, e) << CVF_OBITS) | (unsigned long long)othr;
+    /* (c, e) hash | q hash (prefix path only) | O_thr: one sort makes groups of equal (c, e), inside
+     * them runs of equal q, inside those ascending cut-offs */
+    unsigned long long key = ((unsigned long long)cvf_hash(c, e) << 32) | (unsigned long long)othr;
+    if (pl.prefix) { /* q in the bits above O_thr: runs of a group in ascending q, so that neighbours
+                        need about the same number of copies; q-values closer than the key's
+                        resolution share a key and merely interleave (more, shorter runs) */
+        const int qbits = 32 - pl.obits;
+        const double qc = q > 0.0 ? (q < 1.0 ? q : 1.0) : 0.0; /* NaN -> 0 */
+        const unsigned long long qk = (unsigned long long)(qc * (double)((1u << qbits) - 1u));
+        key |= qk << pl.obits;
+    }
+    pl.keys[i] = key;
 }
 
 /* head[i] = 1 when sorted position i opens a group: its (c, e) differs from the position before */
@@ -155,7 +173,7 @@ cvf_heads(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLatti
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    int h = 1;
+    int h = 1, h2 = 1;
     if (i > 0) {
         double a[CV_MAX_PARAMS], b[CV_MAX_PARAMS];
         cvf_raw_row(m, lat, params, pl.idx_sorted[i], a);
@@ -165,8 +183,11 @@ cvf_heads(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLatti
         const long long e0 = __double_as_longlong(cvf_clipped(m, a, clip, 1));
         const long long e1 = __double_as_longlong(cvf_clipped(m, b, clip, 1));
         h = (c0 != c1) || (e0 != e1);
+        h2 = h || (pl.prefix && __double_as_longlong(cvf_clipped(m, a, clip, 4)) !=
+                                    __double_as_longlong(cvf_clipped(m, b, clip, 4)));
     }
     pl.head[i] = h;
+    pl.head2[i] = h2;
 }
 
 __global__ void __launch_bounds__(256) cvf_group_starts(long long n, CvfPlan pl)
@@ -174,12 +195,50 @@ __global__ void __launch_bounds__(256) cvf_group_starts(long long n, CvfPlan pl)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    if (pl.head[i])
+    if (pl.head[i]) {
         pl.g_start[pl.gid[i] - 1] = (int)i;
+        pl.g_rfirst[pl.gid[i] - 1] = pl.rid[i] - 1;
+    }
+    if (pl.head2[i])
+        pl.r_start[pl.rid[i] - 1] = (int)i;
     if (i == n - 1) {
         pl.header[0] = pl.gid[i];
+        pl.header[5] = pl.rid[i];
         pl.g_start[pl.gid[i]] = (int)n;
+        pl.g_rfirst[pl.gid[i]] = pl.rid[i];
+        pl.r_start[pl.rid[i]] = (int)n;
     }
+    /* cut-offs ascend inside a q-run: its last point holds the run's maximum */
+    if (i == n - 1 || pl.head2[i + 1])
+        atomicMax(pl.g_omax + (pl.gid[i] - 1), pl.othr[pl.idx_sorted[i]]);
+}
+
+/* Tiles of the prefix kernel of group g: up to CVF_PNQ consecutive whole q-runs with at most
+ * CVF_PPB points together (one batch of the kernel), or one longer run alone, cut every
+ * CVF_PSPLIT points.  emit(first sorted position, points, first run, runs). */
+#define CVF_PNQ 4
+#define CVF_PPB 512
+#define CVF_PSPLIT 2048
+template <class F>
+__device__ __forceinline__ int cvf_prefix_tiles(const CvfPlan &pl, int g, F emit)
+{
+    const int r1 = pl.g_rfirst[g + 1];
+    int r = pl.g_rfirst[g], tiles = 0;
+    while (r < r1) {
+        const int first = pl.r_start[r], rfirst = r;
+        int end = first, runs = 0;
+        while (r < r1 && runs < CVF_PNQ) {
+            const int re = pl.r_start[r + 1];
+            if (runs > 0 && re - first > CVF_PPB)
+                break;
+            end = re;
+            r++;
+            runs++;
+        }
+        for (int p = first; p < end; p += CVF_PSPLIT, tiles++)
+            emit(tiles, p, min(CVF_PSPLIT, end - p), rfirst, runs);
+    }
+    return tiles;
 }
 
 /* per group: tiles of K2, items of K1, doubles of its profiles; zeros past the last group so that
@@ -194,17 +253,17 @@ __global__ void __launch_bounds__(256) cvf_group_counts(long long n, int slots_p
     long long w = 0;
     if (g < ng) {
         const int a = pl.g_start[g], b = pl.g_start[g + 1];
-        int omax = pl.othr[pl.idx_sorted[b - 1]] - 1; /* ascending O_thr inside a group */
-        if (omax < 0)
-            omax = 0;
-        tiles = (b - a + CVF_M - 1) / CVF_M;
+        const int tp = pl.tile_points;
+        const int omax = max(pl.g_omax[g] - 1, 0);
+        tiles = pl.prefix ? cvf_prefix_tiles(pl, (int)g, [](int, int, int, int, int) {}) : (b - a + tp - 1) / tp;
         items = (omax + CVF_KC - 1) / CVF_KC;
         w = (long long)items * CVF_KC * slots_padded;
-        for (int p = a; p < b; p += CVF_M) { /* K-chunks of every tile: its last point has the most copies */
-            const int last = min(p + CVF_M, b) - 1;
-            const int kmax = max(pl.othr[pl.idx_sorted[last]] - 1, 0);
-            achunks += (kmax + CVF_KC - 1) / CVF_KC;
-        }
+        if (!pl.prefix)
+            for (int p = a; p < b; p += tp) { /* K-chunks of every tile of K2: its last point has the most copies */
+                const int last = min(p + tp, b) - 1;
+                const int kmax = max(pl.othr[pl.idx_sorted[last]] - 1, 0);
+                achunks += (kmax + CVF_KC - 1) / CVF_KC;
+            }
     }
     pl.tile_start[g] = tiles;
     pl.item_start[g] = items;
@@ -228,17 +287,38 @@ __global__ void __launch_bounds__(128) cvf_tile_table(int n_groups, CvfPlan pl)
     if (g >= n_groups)
         return;
     const int a = pl.g_start[g], b = pl.g_start[g + 1];
-    int tile = pl.tile_start[g], aoff = pl.a_start[g];
-    for (int p = a; p < b; p += CVF_M, tile++) {
-        const int cnt = min(CVF_M, b - p);
-        const int kmax = max(pl.othr[pl.idx_sorted[p + cnt - 1]] - 1, 0);
+    const int tile0 = pl.tile_start[g];
+    if (pl.prefix) {
+        cvf_prefix_tiles(pl, g, [&](int t, int first, int cnt, int rfirst, int runs) {
+            const int tile = tile0 + t;
+            int kmax = 0; /* cut-offs ascend inside a q-run: the last points hold the maxima */
+            for (int r = rfirst; r < rfirst + runs; r++) {
+                const int last = min(pl.r_start[r + 1], first + cnt) - 1;
+                if (last >= first)
+                    kmax = max(kmax, pl.othr[pl.idx_sorted[last]] - 1);
+            }
+            pl.t_first[tile] = first;
+            pl.t_cnt[tile] = cnt;
+            pl.t_nkc[tile] = (kmax + CVF_KC - 1) / CVF_KC;
+            pl.t_aoff[tile] = 0;
+            pl.t_group[tile] = g;
+            pl.t_key[tile] = 4 * cnt + 3 * kmax; /* about the cost: the costly tiles start first */
+            pl.t_order[tile] = tile;
+        });
+        return;
+    }
+    const int tp = pl.tile_points;
+    int tile = tile0, aoff = pl.a_start[g];
+    for (int p = a; p < b; p += tp, tile++) {
+        const int cnt = min(tp, b - p);
+        const int kmax = max(pl.othr[pl.idx_sorted[p + cnt - 1]] - 1, 0); /* cut-offs ascend along the group */
         const int nkc = (kmax + CVF_KC - 1) / CVF_KC;
         pl.t_first[tile] = p;
         pl.t_cnt[tile] = cnt;
         pl.t_nkc[tile] = nkc;
         pl.t_aoff[tile] = aoff;
         pl.t_group[tile] = g;
-        pl.t_key[tile] = nkc;
+        pl.t_key[tile] = nkc; /* the long tiles start first */
         pl.t_order[tile] = tile;
         aoff += nkc;
     }
@@ -273,6 +353,7 @@ __device__ __forceinline__ int cvf_find(const int *__restrict__ start, int n, in
  * groups swapped pairwise against bank conflicts) and leave as full 512-byte lines. */
 template <int NA>
 __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int nsteps,
+                                                  const double *__restrict__ slot_mult,
                                                   double *__restrict__ Wg, double *stage, const double *acc)
 {
     const int r = lane >> 2, q = lane & 3;
@@ -292,7 +373,13 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
     for (int ns = 0; ns < 2 * NA; ns++) {
         const int row = 4 * ns + (lane >> 3);
         const int chunk = (lane & 7) ^ ((row / NA) & 1);
-        const double2 v = *reinterpret_cast<const double2 *>(stage + row * CV_W + 2 * chunk);
+        double2 v = *reinterpret_cast<const double2 *>(stage + row * CV_W + 2 * chunk);
+        /* the scale of the accumulators ends here: slot_mult of the pair's two slots (0 = the slot
+         * is no bin of the histogram; its profile is an exact zero) */
+        const int s0 = (blk * (2 * NA) + ns) * CVF_NS + 16 * (lane >> 3) + (lane & 7);
+        const double m0 = __ldg(slot_mult + s0), m1 = __ldg(slot_mult + s0 + 8);
+        v.x = m0 != 0.0 ? cv_mul(v.x, m0) : 0.0;
+        v.y = m1 != 0.0 ? cv_mul(v.y, m1) : 0.0;
         *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
     }
     __syncwarp();
@@ -320,7 +407,7 @@ __device__ __forceinline__ void cvf_profile_item(int lane, const CvModelDesc &m,
                 for (int i = 0; i < 4 * NA; i++)
                     acc[i] = 0.0;
                 cv_w_fused<NA>(lane, G, cc * kpc, (cc + 1) * kpc, *M.fx, acc);
-                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, Wg, stage, acc);
+                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, m.tab.slot_mult, Wg, stage, acc);
             }
             __syncwarp();
         }
@@ -361,8 +448,8 @@ cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
         const int item = first_item + (int)it;
         const int g = cvf_find(pl.item_start, n_groups, item);
         const int kchunk = item - pl.item_start[g];
-        const int a = pl.g_start[g], b = pl.g_start[g + 1];
-        int omax = pl.othr[pl.idx_sorted[b - 1]] - 1;
+        const int a = pl.g_start[g];
+        const int omax = pl.g_omax[g] - 1;
         const int omax4 = (omax + 3) & ~3;
         double row[CV_MAX_PARAMS];
         cvf_raw_row(m, lat, params, pl.idx_sorted[a], row);
@@ -740,7 +827,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
                         double p[4];
 #pragma unroll
                         for (int mt = 0; mt < 4; mt++)
-                            p[mt] = in_hist ? cv_mul(acc[(mt * 4 + nt) * 2 + c], mh.x) : 0.0;
+                            p[mt] = in_hist ? acc[(mt * 4 + nt) * 2 + c] : 0.0; /* K1 applied slot_mult */
                         if (want_mass) {
 #pragma unroll
                             for (int mt = 0; mt < 4; mt++)
@@ -793,6 +880,467 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* K2p: prefix kernel                                                                           */
+/* ------------------------------------------------------------------------------------------- */
+/* The copy weights beyond o = 2 are geometric, b(o) = many * (1 - q)^(o - 3) (models.py:196-208), so
+ * for points of a group that share q
+ *
+ *     p[j] = q1 P_1[j] + two P_2[j] + many * R_q(O_thr)[j],   R_q(O)[j] = sum_{3 <= o < O} (1 - q)^(o-3) P_o[j]
+ *
+ * and all cut-offs O_thr of such a *q-run* are served by ONE running sum over the copies: the
+ * contraction over o is done once per q-run instead of once per point.  A CTA takes a tile (one
+ * batch: up to CVF_NQ whole q-runs of a group with up to CVF_PB points; or a window of a longer
+ * run).  Every thread owns CVF_SL slots per pass and keeps the CVF_NQ running sums of its slots in
+ * registers.  The points of the batch are put in the order of their cut-offs once (the *schedule*);
+ * the threads then walk the copies upwards -- the profile of copy o travels through a private
+ * cp.async ring, CVF_PD copies ahead -- and finish every point as soon as its copies are in: the
+ * three-term combination for the thread's slots, models.py:100-107 per bin (log only for bins with
+ * counts), the lane partials parked in a transpose buffer and summed over the lanes for CVF_PE points
+ * at a time.  Values do not depend on what else is in the batch: a point's sums run over its own
+ * copies and over the bins in a fixed order.
+ *
+ * Slots to threads: a pass covers 32 * CVF_PW * CVF_SL slots = CVF_PW * CVF_SL half-lines (a line
+ * = the 64 doubles of one copy and one N-step in the layout of K1); warp w takes the half-lines
+ * u = i * CVF_PW + w, i < CVF_SL, lane l the double l of each.  Bins with counts usually are the
+ * first ones of the histogram, so this deals them evenly to the warps. */
+#define CVF_NQ CVF_PNQ /* q-runs whose running sums a thread holds */
+#define CVF_SL 4       /* slots per thread and pass */
+#define CVF_PB CVF_PPB /* points per batch */
+#define CVF_PT 256     /* threads of the prefix kernel */
+#define CVF_PW (CVF_PT / 32)
+#define CVF_PD 4       /* copies in flight per thread (cp.async ring in shared memory) */
+#define CVF_PL2 12     /* copies ahead of the ring that are requested into L2 */
+#define CVF_PE 4       /* points whose lane partials wait in the transpose buffer of a warp */
+#define CVF_PEW 33     /* doubles per row of that buffer (odd: conflict-free both ways) */
+#define CVF_PASS_SLOTS (CVF_PT * CVF_SL)
+
+struct CvfPrefixSmem {
+    double log_tab[2 * CV_LOG_N];
+    /* the points of the batch by ascending cut-off (the schedule): weights of copy 1, copy 2 and
+     * of the running sum; (batch position | run << 16, copies = O_thr - 1) */
+    double q1[CVF_PB], two[CVF_PB], many[CVF_PB];
+    int2 sched[CVF_PB + 1];
+    int need[CVF_PB];  /* by batch position: copies of the point */
+    double base[CVF_NQ];
+    int seg[CVF_NQ + 1]; /* batch positions where its q-runs start */
+    int tile, bend;
+    /* then, in this order:
+     *   double ring[CVF_PD][CVF_SL][CVF_PT]   every thread's own slots of the copies in flight
+     *   double tbuf[planes][CVF_PW][CVF_PE][CVF_PEW]   lane partials of the last points, per warp
+     * planes = 2 (sum, mass) or, with a tail, 3 (sum, mass high, mass low: compensated)
+     * and in global memory, per CTA (L2-resident scratch):
+     *   double red[3][CVF_PW][CVF_PB]    per (warp, point) partial */
+};
+#define CVF_RING_BYTES (CVF_PD * CVF_SL * CVF_PT * 8)
+#define CVF_TBUF_DOUBLES (CVF_PW * CVF_PE * CVF_PEW)
+
+static size_t cvf_prefix_smem_bytes(bool mass)
+{
+    const size_t planes = mass ? 3 : 2;
+    return sizeof(CvfPrefixSmem) + CVF_RING_BYTES + planes * CVF_TBUF_DOUBLES * sizeof(double);
+}
+
+/* safe_log (utils.py:32-35) off the fast path: zero, negative, subnormal, infinite, NaN */
+__device__ __noinline__ double cvf_log_rare(double x)
+{
+    return (x <= 0.0) ? -INFINITY : log(x);
+}
+
+/* cv_log_tab (the same bits) for positive normal x with the index arithmetic on the high word;
+ * everything else takes cvf_log_rare */
+__device__ __forceinline__ double cvf_safe_log(double x, const double *tab)
+{
+    const int hi = __double2hiint(x);
+    if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u)
+        return cvf_log_rare(x);
+    const int t = hi - (int)(CV_LOG_OFF >> 32);
+    const int i = (t >> 13) & (CV_LOG_N - 1);
+    const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
+    const double2 c = *reinterpret_cast<const double2 *>(tab + 2 * i); /* (invc, logc) */
+    const double r = cv_fma(z, c.x, -1.0);
+    const double kd = (double)(t >> 20);
+    const double hi_part = cv_fma(kd, 0x1.62e42fefa3800p-1, c.y);
+    double p = cv_fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = cv_fma(r, p, 1.0 / 5.0);
+    p = cv_fma(r, p, -1.0 / 4.0);
+    p = cv_fma(r, p, 1.0 / 3.0);
+    p = cv_fma(r, p, -0.5);
+    const double r2 = cv_mul(r, r);
+    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.ef35793c76730p-45));
+    return cv_add(hi_part, cv_add(r, lo));
+}
+
+/* number of entries of the ascending a[0..n) that are < x (strict) resp. <= x */
+__device__ __forceinline__ int cvf_count_below(const int *a, int n, int x, bool or_equal)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = a[mid];
+        if (v < x || (or_equal && v == x))
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+/* MASS: the histogram has a tail (models.py:103-104): the mass sum_j p_j enters the result through
+ * 1 - mass and is summed compensated (the reference uses fsum); without a tail it only has to
+ * tell whether it is below 1 (models.py:104), a plain sum.
+ * FULL: the slots are a multiple of CVF_PASS_SLOTS, no thread ever idles in a pass. */
+template <bool MASS, bool FULL>
+__global__ void __launch_bounds__(CVF_PT, 2)
+cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
+                  const double *__restrict__ params, int clip, CvfPlan pl, int first_tile, int n_tiles,
+                  const double *__restrict__ W, long long w_base, const double2 *__restrict__ slot_mh,
+                  const double *__restrict__ log_tab, int nsteps, double *__restrict__ out_ll,
+                  unsigned long long *counter, double *__restrict__ scratch)
+{
+    extern __shared__ __align__(16) unsigned char cvf_smem_raw[];
+    CvfPrefixSmem &S = *reinterpret_cast<CvfPrefixSmem *>(cvf_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *ring = reinterpret_cast<double *>(cvf_smem_raw + sizeof(CvfPrefixSmem)) + tid;
+    double *tbuf = reinterpret_cast<double *>(cvf_smem_raw + sizeof(CvfPrefixSmem) + CVF_RING_BYTES) +
+                   warp * (CVF_PE * CVF_PEW); /* plane stride CVF_TBUF_DOUBLES */
+    double *red_all = scratch + (size_t)blockIdx.x * (3 * CVF_PW * CVF_PB);
+    double *red = red_all + warp * CVF_PB; /* plane stride CVF_PW * CVF_PB */
+    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
+    for (int i = tid; i < 2 * CV_LOG_N; i += CVF_PT)
+        S.log_tab[i] = log_tab[i];
+    const int nslots = nsteps * CVF_NS;
+    const long long chunk_stride = (long long)nsteps * CVF_TILE_DOUBLES;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0)
+            S.tile = (int)atomicAdd(counter, 1ULL);
+        __syncthreads();
+        if (S.tile >= n_tiles)
+            break;
+        const int tile = pl.t_sorted[S.tile];
+        const int tfirst = pl.t_first[tile], tend = tfirst + pl.t_cnt[tile];
+        const double *Wg = W + (pl.w_off[pl.t_group[tile]] - w_base);
+
+        for (int b0 = tfirst; b0 < tend;) {
+            /* ---- the batch: up to CVF_PB points in up to CVF_NQ q-runs ---- */
+            const int nload = min(CVF_PB, tend - b0);
+            const int rid0 = pl.rid[b0];
+            if (tid == 0)
+                S.bend = nload;
+            if (tid <= CVF_NQ)
+                S.seg[tid] = nload;
+            __syncthreads();
+            for (int t = tid; t < nload; t += CVF_PT) {
+                const int rel = pl.rid[b0 + t] - rid0;
+                if (rel >= CVF_NQ)
+                    atomicMin(&S.bend, t);
+                else if (t == 0 || pl.head2[b0 + t])
+                    S.seg[rel] = t;
+            }
+            __syncthreads();
+            const int npts = S.bend;
+            /* per point: the weights (kept in registers until its place in the schedule is known) */
+            constexpr int PPT = CVF_PB / CVF_PT;
+            double pq1[PPT], ptwo[PPT], pmany[PPT];
+#pragma unroll
+            for (int j = 0; j < PPT; j++) {
+                const int t = tid + j * CVF_PT;
+                pq1[j] = ptwo[j] = pmany[j] = 0.0;
+                if (t < npts) {
+                    const unsigned int pi = pl.idx_sorted[b0 + t];
+                    double row[CV_MAX_PARAMS];
+                    cvf_raw_row(m, lat, params, pi, row);
+                    const double q1 = cvf_clipped(m, row, clip, 2), q2 = cvf_clipped(m, row, clip, 3),
+                                 qq = cvf_clipped(m, row, clip, 4);
+                    const int need = pl.othr[pi] - 1;
+                    /* copies beyond the cut-off do not enter (models.py:235): exact zero weights (the
+                     * profiles are probabilities, finite) */
+                    pq1[j] = need >= 1 ? q1 : 0.0;
+                    ptwo[j] = need >= 2 ? cv_mul(cv_sub(1.0, q1), q2) : 0.0;
+                    pmany[j] = need >= 3 ? cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), qq) : 0.0;
+                    S.need[t] = need;
+                    if (t == 0 || pl.head2[b0 + t])
+                        S.base[pl.rid[b0 + t] - rid0] = cv_sub(1.0, qq);
+                }
+            }
+            __syncthreads();
+            int seg0[CVF_NQ], seg_end[CVF_NQ], last_need[CVF_NQ];
+            double base[CVF_NQ];
+            int omax_b = 0; /* copies the batch needs: cut-offs ascend inside a q-run */
+#pragma unroll
+            for (int s = 0; s < CVF_NQ; s++) {
+                seg0[s] = min(S.seg[s], npts);
+                seg_end[s] = s + 1 < CVF_NQ ? min(S.seg[s + 1], npts) : npts;
+                if (seg_end[s] < seg0[s])
+                    seg_end[s] = seg0[s];
+                base[s] = seg_end[s] > seg0[s] ? S.base[s] : 0.0;
+                last_need[s] = seg_end[s] > seg0[s] ? S.need[seg_end[s] - 1] : -1;
+                omax_b = max(omax_b, last_need[s]);
+            }
+            /* the schedule: rank of a point = points before it by (copies, run, position) */
+#pragma unroll
+            for (int j = 0; j < PPT; j++) {
+                const int t = tid + j * CVF_PT;
+                if (t < npts) {
+                    const int need = S.need[t];
+                    int rank = 0, mine = 0;
+#pragma unroll
+                    for (int s = 0; s < CVF_NQ; s++)
+                        if (t >= seg0[s] && t < seg_end[s]) {
+                            mine = s;
+                            rank += t - seg0[s];
+                        }
+#pragma unroll
+                    for (int s = 0; s < CVF_NQ; s++)
+                        if (s != mine && seg_end[s] > seg0[s])
+                            rank += cvf_count_below(S.need + seg0[s], seg_end[s] - seg0[s], need, s < mine);
+                    S.sched[rank] = make_int2(t | (mine << 16), need);
+                    S.q1[rank] = pq1[j];
+                    S.two[rank] = ptwo[j];
+                    S.many[rank] = pmany[j];
+                }
+            }
+            if (tid == 0)
+                S.sched[npts] = make_int2(0, 0); /* read ahead by the loop below, never used */
+            __syncthreads();
+
+            /* ---- passes over the slots ---- */
+            for (int pass0 = 0; pass0 < nslots; pass0 += CVF_PASS_SLOTS) {
+                /* the thread's slots: double `lane` of the half-lines u = pass0 / 32 + i * CVF_PW + warp */
+                const int u0 = (pass0 >> 5) + warp;
+                const double *src0 = Wg + (long long)(u0 >> 1) * CVF_TILE_DOUBLES + (u0 & 1) * 32 + lane;
+                constexpr long long SRC_STEP = (long long)(CVF_PW / 2) * CVF_TILE_DOUBLES; /* doubles between i and i + 1 */
+                double hcnt[CVF_SL];
+                int log_mask = 0;
+                bool live[CVF_SL];
+#pragma unroll
+                for (int i = 0; i < CVF_SL; i++) {
+                    const int u = u0 + i * CVF_PW;
+                    live[i] = FULL || u * 32 < nslots;
+                    const int e = (u & 1) * 32 + lane, L = e >> 1; /* pair L, member e & 1 of N-step u / 2 */
+                    const int slot = (u >> 1) * CVF_NS + 16 * (L >> 3) + (L & 7) + 8 * (e & 1);
+                    hcnt[i] = live[i] ? __ldg(&slot_mh[slot].y) : 0.0;
+                    log_mask |= (__any_sync(CV_FULL_MASK, hcnt[i] != 0.0) ? 1 : 0) << i;
+                }
+                /* The profile of copy o for the thread's slots: copy o lives at (o - 1) / 16 chunks +
+                 * (o - 1) % 16 lines of 64 doubles.  Copies travel through the thread's own places
+                 * of a ring in shared memory (cp.async, CVF_PD copies in flight, nothing to
+                 * synchronise between threads); further ahead they are requested into L2. */
+                int o_req = 1;                 /* the next copy to request */
+                unsigned int dst_req = ring_s; /* its place in the ring */
+                const double *src_req = src0;  /* its first slot */
+                const double *src_far = src0 + (long long)(CVF_PL2 >> 4) * chunk_stride + (CVF_PL2 & 15) * 64;
+                const bool far_lane = (lane & 15) == 0; /* one request per 128-byte line */
+                auto request = [&]() { /* one commit group per call, also when there is nothing left to load */
+                    if (o_req <= omax_b) {
+#pragma unroll
+                        for (int i = 0; i < CVF_SL; i++)
+                            if (live[i])
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst_req + i * CVF_PT * 8),
+                                             "l"(src_req + i * SRC_STEP)
+                                             : "memory");
+                        if (o_req + CVF_PL2 <= omax_b && far_lane) {
+#pragma unroll
+                            for (int i = 0; i < CVF_SL; i++)
+                                if (live[i])
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src_far + i * SRC_STEP));
+                        }
+                    }
+                    cvf_cp_commit();
+                    src_req += ((o_req & 15) == 0) ? chunk_stride - 15 * 64 : 64;
+                    src_far += (((o_req + CVF_PL2) & 15) == 0) ? chunk_stride - 15 * 64 : 64;
+                    dst_req = (o_req % CVF_PD == 0) ? ring_s : dst_req + CVF_SL * CVF_PT * 8;
+                    o_req++;
+                };
+                int slot_take = 0;
+                auto take = [&](double *x) { /* the oldest copy in flight has landed */
+                    asm volatile("cp.async.wait_group %0;\n" ::"n"(CVF_PD - 1) : "memory");
+#pragma unroll
+                    for (int i = 0; i < CVF_SL; i++) {
+                        const double v = ring[(slot_take * CVF_SL + i) * CVF_PT];
+                        x[i] = live[i] ? v : 0.0;
+                    }
+                    slot_take = slot_take == CVF_PD - 1 ? 0 : slot_take + 1;
+                };
+#pragma unroll
+                for (int o = 1; o <= CVF_PD; o++)
+                    request();
+                double P1[CVF_SL], P2[CVF_SL];
+#pragma unroll
+                for (int i = 0; i < CVF_SL; i++)
+                    P1[i] = P2[i] = 0.0;
+                if (omax_b >= 1) {
+                    take(P1);
+                    request();
+                }
+                if (omax_b >= 2) {
+                    take(P2);
+                    request();
+                }
+                double R[CVF_NQ][CVF_SL], w[CVF_NQ];
+#pragma unroll
+                for (int s = 0; s < CVF_NQ; s++) {
+#pragma unroll
+                    for (int i = 0; i < CVF_SL; i++)
+                        R[s][i] = 0.0;
+                    w[s] = 1.0;
+                }
+                const bool first_pass = pass0 == 0;
+                int pending = 0; /* points in the transpose buffer */
+                int mypt = 0;    /* lane e: the point in row e of the buffer */
+                /* row e of the buffer summed over the 32 lane partials (32 / CVF_PE columns per lane,
+                 * then across the lane groups): fixed order, the warp's partial of that point */
+                auto flush = [&]() {
+                    __syncwarp();
+                    /* lane group g = lane / CVF_PE takes the columns g * CVF_PE .. + CVF_PE - 1 of row e */
+                    const int e = lane & (CVF_PE - 1), c0 = (lane / CVF_PE) * CVF_PE;
+                    const double *rowp = tbuf + e * CVF_PEW + c0;
+                    double acc0 = rowp[0], acc1 = rowp[CVF_TBUF_DOUBLES], acc2 = 0.0;
+                    if (MASS)
+                        acc2 = rowp[2 * CVF_TBUF_DOUBLES];
+#pragma unroll
+                    for (int c = 1; c < CVF_PE; c++) {
+                        acc0 = cv_add(acc0, rowp[c]);
+                        if (MASS) { /* high parts exactly (two-sum), low parts plainly */
+                            cvf_two_sum_acc(acc1, acc2, rowp[CVF_TBUF_DOUBLES + c]);
+                            acc2 = cv_add(acc2, rowp[2 * CVF_TBUF_DOUBLES + c]);
+                        } else {
+                            acc1 = cv_add(acc1, rowp[CVF_TBUF_DOUBLES + c]);
+                        }
+                    }
+#pragma unroll
+                    for (int d = CVF_PE; d <= 16; d <<= 1) {
+                        acc0 = cv_add(acc0, __shfl_xor_sync(CV_FULL_MASK, acc0, d));
+                        const double oh = __shfl_xor_sync(CV_FULL_MASK, acc1, d);
+                        if (MASS) {
+                            const double ol = __shfl_xor_sync(CV_FULL_MASK, acc2, d);
+                            cvf_two_sum_acc(acc1, acc2, oh);
+                            acc2 = cv_add(acc2, ol);
+                        } else {
+                            acc1 = cv_add(acc1, oh);
+                        }
+                    }
+                    const int pt = __shfl_sync(CV_FULL_MASK, mypt, e);
+                    if (lane < pending) {
+                        double *r0 = red + pt, *r1 = r0 + CVF_PW * CVF_PB, *r2 = r1 + CVF_PW * CVF_PB;
+                        if (first_pass) {
+                            *r0 = acc0;
+                            *r1 = acc1;
+                            if (MASS)
+                                *r2 = acc2;
+                        } else {
+                            *r0 = cv_add(*r0, acc0);
+                            if (MASS) {
+                                double h = *r1, l = *r2;
+                                cvf_two_sum_acc(h, l, acc1);
+                                *r1 = h;
+                                *r2 = cv_add(l, acc2);
+                            } else {
+                                *r1 = cv_add(*r1, acc1);
+                            }
+                        }
+                    }
+                    pending = 0;
+                    __syncwarp();
+                };
+                int o_done = 2;
+                int2 ev = S.sched[0];
+                double q1 = S.q1[0], two = S.two[0], many = S.many[0];
+                for (int k = 0; k < npts; k++) {
+                    /* the next point's record travels while this one is worked on */
+                    const int2 ev_next = S.sched[k + 1];
+                    const double q1_next = S.q1[min(k + 1, CVF_PB - 1)], two_next = S.two[min(k + 1, CVF_PB - 1)],
+                                 many_next = S.many[min(k + 1, CVF_PB - 1)];
+                    while (o_done < ev.y) { /* one more copy into the running sums (o_done >= 3) */
+                        o_done++;
+                        double x[CVF_SL];
+                        take(x);
+                        request();
+#pragma unroll
+                        for (int s = 0; s < CVF_NQ; s++)
+                            if (o_done <= last_need[s]) { /* runs whose points are all out need no more copies */
+#pragma unroll
+                                for (int i = 0; i < CVF_SL; i++)
+                                    R[s][i] = cv_fma(w[s], x[i], R[s][i]);
+                                w[s] = cv_mul(w[s], base[s]);
+                            }
+                    }
+                    /* the three-term combination for the thread's slots, models.py:235-241 */
+                    const int pt = ev.x & 0xffff;
+                    double p[CVF_SL];
+#pragma unroll
+                    for (int i = 0; i < CVF_SL; i++)
+                        p[i] = cv_fma(two, P2[i], cv_mul(q1, P1[i]));
+                    switch (ev.x >> 16) {
+#define CVF_CASE(s_)                                                                                   \
+    case s_:                                                                                           \
+        _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) p[i] = cv_fma(many, R[s_][i], p[i]);        \
+        break;
+                        CVF_CASE(0)
+                        CVF_CASE(1)
+                        CVF_CASE(2)
+                        CVF_CASE(3)
+#undef CVF_CASE
+                    }
+                    ev = ev_next;
+                    q1 = q1_next;
+                    two = two_next;
+                    many = many_next;
+                    /* models.py:100-107 for the thread's slots */
+                    double sum = 0.0, mh = 0.0, ml = 0.0;
+#pragma unroll
+                    for (int i = 0; i < CVF_SL; i++) {
+                        if (MASS)
+                            cvf_two_sum_acc(mh, ml, p[i]);
+                        else
+                            mh = cv_add(mh, p[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CVF_SL; i++)
+                        if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
+                            double term = cv_mul(hcnt[i], cvf_safe_log(p[i], S.log_tab)); /* utils.py:32-35 */
+                            if (hcnt[i] == 0.0) /* models.py:106 `if h` */
+                                term = 0.0;
+                            sum = cv_add(sum, term);
+                        }
+                    tbuf[pending * CVF_PEW + lane] = sum;
+                    tbuf[CVF_TBUF_DOUBLES + pending * CVF_PEW + lane] = mh;
+                    if (MASS)
+                        tbuf[2 * CVF_TBUF_DOUBLES + pending * CVF_PEW + lane] = ml;
+                    if (lane == pending)
+                        mypt = pt;
+                    if (++pending == CVF_PE)
+                        flush();
+                }
+                if (pending)
+                    flush();
+                cvf_cp_wait0();
+            }
+            __syncthreads();
+            for (int t = tid; t < npts; t += CVF_PT) {
+                CvPartial part;
+                part.sum = red_all[t];
+                part.mass_h = red_all[CVF_PW * CVF_PB + t];
+                part.mass_l = MASS ? red_all[2 * CVF_PW * CVF_PB + t] : 0.0;
+                for (int wv = 1; wv < CVF_PW; wv++) {
+                    part.sum = cv_add(part.sum, red_all[wv * CVF_PB + t]);
+                    if (MASS) {
+                        cvf_two_sum_acc(part.mass_h, part.mass_l, red_all[(CVF_PW + wv) * CVF_PB + t]);
+                        part.mass_l = cv_add(part.mass_l, red_all[(2 * CVF_PW + wv) * CVF_PB + t]);
+                    } else {
+                        part.mass_h = cv_add(part.mass_h, red_all[(CVF_PW + wv) * CVF_PB + t]);
+                    }
+                }
+                out_ll[pl.idx_sorted[b0 + t]] = cv_point_finish(m, part);
+            }
+            b0 += npts;
+            __syncthreads();
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* host side                                                                                    */
 /* ------------------------------------------------------------------------------------------- */
 void cvf_release(CvFactorWork &wk)
@@ -805,6 +1353,9 @@ void cvf_release(CvFactorWork &wk)
         cudaFreeHost(wk.h_header);
     if (wk.d_counters)
         cudaFree(wk.d_counters);
+    if (wk.d_scratch)
+        cudaFree(wk.d_scratch);
+    wk.d_scratch = nullptr;
     for (cudaEvent_t &e : wk.ev)
         if (e) {
             cudaEventDestroy(e);
@@ -829,7 +1380,7 @@ static size_t cvf_align(size_t x) { return (x + 255) & ~(size_t)255; }
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
                      int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
-                     double min_group, cudaStream_t stream, int *used)
+                     double min_group, double min_run, int kernel_mode, cudaStream_t stream, int *used)
 {
     *used = 0;
     wk.launches = 0;
@@ -842,7 +1393,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     size_t sort_tmp = 0, sort_tmp_t = 0, scan_tmp_i = 0, scan_tmp_l = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned long long *)nullptr,
                                     (unsigned long long *)nullptr, (unsigned int *)nullptr,
-                                    (unsigned int *)nullptr, (int)n, 0, 32 + CVF_OBITS, stream);
+                                    (unsigned int *)nullptr, (int)n, 0, 64, stream);
     cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp_t, (int *)nullptr, (int *)nullptr,
                                               (int *)nullptr, (int *)nullptr, (int)n, 0, 32, stream);
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_i, (int *)nullptr, (int *)nullptr, (int)n + 1, stream);
@@ -858,6 +1409,8 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     };
     const size_t o_keys = take(n * 8), o_keys_alt = take(n * 8), o_idx = take(n * 4), o_idx_alt = take(n * 4);
     const size_t o_othr = take(n * 4), o_head = take(n * 4), o_gid = take(n * 4);
+    const size_t o_head2 = take(n * 4), o_rid = take(n * 4), o_gomax = take(n1 * 4);
+    const size_t o_rstart = take(n1 * 4), o_grfirst = take(n1 * 4);
     const size_t o_gstart = take(n1 * 4), o_tile = take(n1 * 4), o_item = take(n1 * 4), o_woff = take(n1 * 8);
     const size_t o_astart = take(n1 * 4);
     size_t o_t[9];
@@ -876,6 +1429,9 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         CVF_CK(cudaMallocHost((void **)&wk.h_header, 64));
     if (!wk.d_counters)
         CVF_CK(cudaMalloc((void **)&wk.d_counters, 2 * sizeof(unsigned long long)));
+    const int kp_grid_max = 4 * n_sm; /* CTAs of the prefix kernel at most; each owns a scratch of partials */
+    if (!wk.d_scratch)
+        CVF_CK(cudaMalloc((void **)&wk.d_scratch, (size_t)kp_grid_max * 3 * CVF_PW * CVF_PB * sizeof(double)));
     if (wk.timed && !wk.ev[0])
         for (cudaEvent_t &e : wk.ev)
             CVF_CK(cudaEventCreate(&e));
@@ -889,6 +1445,11 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     pl.othr = (int *)(base + o_othr);
     pl.head = (int *)(base + o_head);
     pl.gid = (int *)(base + o_gid);
+    pl.head2 = (int *)(base + o_head2);
+    pl.rid = (int *)(base + o_rid);
+    pl.g_omax = (int *)(base + o_gomax);
+    pl.r_start = (int *)(base + o_rstart);
+    pl.g_rfirst = (int *)(base + o_grfirst);
     pl.g_start = (int *)(base + o_gstart);
     pl.tile_start = (int *)(base + o_tile);
     pl.item_start = (int *)(base + o_item);
@@ -905,54 +1466,80 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     pl.t_order_alt = (int *)(base + o_t[8]);
     pl.t_sorted = nullptr;
     pl.header = (long long *)(base + o_header);
+    pl.obits = 1;
+    while ((1 << pl.obits) <= m.max_bin + CV_COPY_PAD)
+        pl.obits++;
     void *tmp = base + o_tmp;
 
     const int tb = 256;
     const unsigned int nb = (unsigned int)((n + tb - 1) / tb), nb1 = (unsigned int)((n + 1 + tb - 1) / tb);
     if (wk.timed)
         CVF_CK(cudaEventRecord(wk.ev[0], stream));
-    cvf_point_keys<<<nb, tb, 0, stream>>>(m, lat, params, n, clip, pl);
-    CVF_CK(cudaGetLastError());
-    {
-        cub::DoubleBuffer<unsigned long long> dk(pl.keys, pl.keys_alt);
-        cub::DoubleBuffer<unsigned int> dv(pl.idx, pl.idx_alt);
-        size_t tb_ = tmp_bytes;
-        CVF_CK(cub::DeviceRadixSort::SortPairs(tmp, tb_, dk, dv, (int)n, 0, 32 + CVF_OBITS, stream));
-        pl.idx_sorted = dv.Current();
+
+    /* K0 .. totals for one ordering of the points; ends with the header on the host */
+    auto build_plan = [&](int prefix) -> cudaError_t {
+        pl.prefix = prefix;
+        pl.tile_points = CVF_M;
+        pl.keys = (unsigned long long *)(base + o_keys);
+        pl.keys_alt = (unsigned long long *)(base + o_keys_alt);
+        pl.idx = (unsigned int *)(base + o_idx);
+        pl.idx_alt = (unsigned int *)(base + o_idx_alt);
+        cvf_point_keys<<<nb, tb, 0, stream>>>(m, lat, params, n, clip, pl);
+        CVF_CK(cudaGetLastError());
+        {
+            cub::DoubleBuffer<unsigned long long> dk(pl.keys, pl.keys_alt);
+            cub::DoubleBuffer<unsigned int> dv(pl.idx, pl.idx_alt);
+            size_t tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceRadixSort::SortPairs(tmp, tb_, dk, dv, (int)n, 0, 64, stream));
+            pl.idx_sorted = dv.Current();
+        }
+        cvf_heads<<<nb, tb, 0, stream>>>(m, lat, params, n, clip, pl);
+        CVF_CK(cudaGetLastError());
+        {
+            size_t tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceScan::InclusiveSum(tmp, tb_, pl.head, pl.gid, (int)n, stream));
+            tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceScan::InclusiveSum(tmp, tb_, pl.head2, pl.rid, (int)n, stream));
+        }
+        CVF_CK(cudaMemsetAsync(pl.g_omax, 0, n1 * sizeof(int), stream));
+        cvf_group_starts<<<nb, tb, 0, stream>>>(n, pl);
+        CVF_CK(cudaGetLastError());
+        cvf_group_counts<<<nb1, tb, 0, stream>>>(n, slots_padded, pl);
+        CVF_CK(cudaGetLastError());
+        {
+            size_t tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.tile_start, pl.tile_start, (int)n + 1, stream));
+            tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.item_start, pl.item_start, (int)n + 1, stream));
+            tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.w_off, pl.w_off, (int)n + 1, stream));
+            tb_ = tmp_bytes;
+            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.a_start, pl.a_start, (int)n + 1, stream));
+        }
+        cvf_totals<<<1, 1, 0, stream>>>(pl);
+        CVF_CK(cudaGetLastError());
+        CVF_CK(cudaMemcpyAsync(wk.h_header, pl.header, 6 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        CVF_CK(cudaStreamSynchronize(stream));
+        wk.launches += 12;
+        return cudaSuccess;
+    };
+    /* ordering for the prefix kernel first: it also tells how many q-runs the batch has */
+    int prefix = kernel_mode != 1;
+    CVF_CK(build_plan(prefix));
+    wk.n_groups = wk.h_header[0];
+    wk.n_runs = wk.h_header[5];
+    if (wk.n_groups <= 0 || (double)n < min_group * (double)wk.n_groups)
+        return cudaSuccess; /* too little sharing: the per-point kernel is the better tool */
+    if (prefix && kernel_mode == 0 && (double)n < min_run * (double)wk.n_runs) {
+        prefix = 0; /* few points per q-run: the GEMM shares the profiles between all points of a group */
+        CVF_CK(build_plan(0));
     }
-    cvf_heads<<<nb, tb, 0, stream>>>(m, lat, params, n, clip, pl);
-    CVF_CK(cudaGetLastError());
-    {
-        size_t tb_ = tmp_bytes;
-        CVF_CK(cub::DeviceScan::InclusiveSum(tmp, tb_, pl.head, pl.gid, (int)n, stream));
-    }
-    cvf_group_starts<<<nb, tb, 0, stream>>>(n, pl);
-    CVF_CK(cudaGetLastError());
-    cvf_group_counts<<<nb1, tb, 0, stream>>>(n, slots_padded, pl);
-    CVF_CK(cudaGetLastError());
-    {
-        size_t tb_ = tmp_bytes;
-        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.tile_start, pl.tile_start, (int)n + 1, stream));
-        tb_ = tmp_bytes;
-        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.item_start, pl.item_start, (int)n + 1, stream));
-        tb_ = tmp_bytes;
-        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.w_off, pl.w_off, (int)n + 1, stream));
-        tb_ = tmp_bytes;
-        CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.a_start, pl.a_start, (int)n + 1, stream));
-    }
-    cvf_totals<<<1, 1, 0, stream>>>(pl);
-    CVF_CK(cudaGetLastError());
-    CVF_CK(cudaMemcpyAsync(wk.h_header, pl.header, 5 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
-    CVF_CK(cudaStreamSynchronize(stream));
-    wk.launches += 10;
     const long long n_groups = wk.h_header[0], n_tiles = wk.h_header[1], n_items = wk.h_header[2];
     const long long w_total = wk.h_header[3], a_total = wk.h_header[4];
-    wk.n_groups = n_groups;
     wk.n_tiles = n_tiles;
     wk.n_items = n_items;
     wk.w_doubles = w_total;
-    if (n_groups <= 0 || (double)n < min_group * (double)n_groups)
-        return cudaSuccess; /* too little sharing: the per-point kernel is the better tool */
+    wk.prefix = prefix;
     cvf_tile_table<<<(unsigned int)((n_groups + 127) / 128), 128, 0, stream>>>((int)n_groups, pl);
     CVF_CK(cudaGetLastError());
     wk.launches++;
@@ -1001,7 +1588,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     }
     double *A = wk.W + w_need;
 
-    /* ---- K1 / K1b / K2 per range ---- */
+    /* ---- K1, then K1b + K2 or the prefix kernel, per range ---- */
     const size_t wb = cv_warp_bytes(m.n_err);
     const int groups_staged = m.n_blocks * CV_GB;
     const size_t tab = (size_t)groups_staged * CV_GD * sizeof(double);
@@ -1010,9 +1597,15 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     if (k1_warps < 1)
         return cudaErrorInvalidConfiguration;
     const size_t k1_smem = tab + (size_t)k1_warps * wb1;
+    const bool want_mass = m.tail != 0.0;
+    const size_t kp_smem = cvf_prefix_smem_bytes(want_mass);
+    const bool full_passes = (nsteps * CVF_NS) % CVF_PASS_SLOTS == 0;
     CVF_CK(cudaFuncSetAttribute(cvf_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
     CVF_CK(cudaFuncSetAttribute(cvf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(CvfSmem)));
+    auto kp = want_mass ? (full_passes ? cvf_prefix_kernel<true, true> : cvf_prefix_kernel<true, false>)
+                        : (full_passes ? cvf_prefix_kernel<false, true> : cvf_prefix_kernel<false, false>);
+    CVF_CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kp_smem));
     if (wk.timed)
         CVF_CK(cudaEventRecord(wk.ev[1], stream));
     for (size_t i = 0; i + 1 < cut.size(); i++) {
@@ -1035,9 +1628,12 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         }
         if (tile1 > tile0) {
             const int tiles = tile1 - tile0;
-            cvf_weights_kernel<<<tiles, CVF_THREADS, 0, stream>>>(m, lat, params, clip, pl, tile0, tiles, A, a0);
-            CVF_CK(cudaGetLastError());
-            /* tiles of the range by descending number of K-chunks: the long ones start first */
+            if (!prefix) {
+                cvf_weights_kernel<<<tiles, CVF_THREADS, 0, stream>>>(m, lat, params, clip, pl, tile0, tiles, A, a0);
+                CVF_CK(cudaGetLastError());
+                wk.launches++;
+            }
+            /* tiles of the range by descending cost: the long ones start first */
             cub::DoubleBuffer<int> dk(pl.t_key + tile0, pl.t_key_alt + tile0);
             cub::DoubleBuffer<int> dv(pl.t_order + tile0, pl.t_order_alt + tile0);
             size_t tb_ = tmp_bytes;
@@ -1046,15 +1642,22 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
             if (wk.timed && i + 2 == cut.size())
                 CVF_CK(cudaEventRecord(wk.ev[2], stream));
             int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;
-            cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(
-                m, pl, tile0, tiles, wk.W, w0, A, a0, slot_mh, step_mask, log_tab, nsteps, out_ll,
-                wk.d_counters + 1, getenv("COVEST_B200_DBG") ? atoi(getenv("COVEST_B200_DBG")) : 0);
+            if (prefix) {
+                const int per_sm = std::max(1, std::min(4, (int)((size_t)smem_max / (kp_smem + 1024))));
+                grid = tiles < per_sm * n_sm ? tiles : per_sm * n_sm;
+                kp<<<grid, CVF_PT, kp_smem, stream>>>(m, lat, params, clip, pl, tile0, tiles, wk.W, w0, slot_mh,
+                                                       log_tab, nsteps, out_ll, wk.d_counters + 1, wk.d_scratch);
+            } else {
+                cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(
+                    m, pl, tile0, tiles, wk.W, w0, A, a0, slot_mh, step_mask, log_tab, nsteps, out_ll,
+                    wk.d_counters + 1, getenv("COVEST_B200_DBG") ? atoi(getenv("COVEST_B200_DBG")) : 0);
+            }
             CVF_CK(cudaGetLastError());
-            wk.launches += 3;
+            wk.launches += 2;
         }
     }
     if (wk.timed)
         CVF_CK(cudaEventRecord(wk.ev[3], stream));
-    *used = 1;
+    *used = prefix ? 2 : 1;
     return cudaSuccess;
 }

@@ -13,8 +13,11 @@
  *   K1  per group and copy number o <= max O_thr of the group: the profile over all bins, with the
  *       machinery of the per-point kernel (cvpoint.h), written to HBM in the fragment order K2 reads
  *   K2  per tile of 128 points of one group: P[point][bin] = sum_o b_point(o) * profile[o][bin] as a
- *       dense FP64 GEMM on the tensor cores (m8n8k4), b(o) generated on the fly in shared memory,
+ *       dense FP64 GEMM on the tensor cores (m8n8k4), copy weights from K1b,
  *       then the epilogue of models.py:100-107 straight from the accumulators
+ *   K2p (instead of K1b + K2 when points of a group also share q, as lattices do): b(o) is geometric
+ *       beyond o = 2, so one running sum over the copies per q-run serves all its cut-offs; per
+ *       point only the three-term combination and the epilogue remain
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -30,11 +33,13 @@ struct CvFactorWork {
     long long *h_header = nullptr; /* pinned host: n_groups, tiles, items, profile doubles */
     std::size_t h_arrays_cap = 0;
     unsigned long long *d_counters = nullptr; /* two device words */
+    double *d_scratch = nullptr; /* prefix kernel: per CTA the per-(warp, point) partials of a batch */
     /* timing of the most recent evaluation (events recorded when `timed`) */
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
     /* facts about the most recent evaluation */
-    long long n_groups = 0, n_tiles = 0, n_items = 0, w_doubles = 0;
+    long long n_groups = 0, n_tiles = 0, n_items = 0, w_doubles = 0, n_runs = 0;
+    int prefix = 0; /* 1: the prefix kernel ran, 0: the GEMM */
     int launches = 0;
     double gemm_fma = 0.0; /* FMAs the tiles of K2 issue (128 rows x padded copies x padded slots) */
 };
@@ -43,14 +48,16 @@ struct CvFactorWork {
 bool cvf_supported(const CvModelDesc &m);
 
 /* Evaluates n points.  *used = 0 when the batch does not group well enough (nothing written to
- * out_ll; the caller runs the per-point kernel).  Device tables: `slot_mh` = (slot_mult, slot_h)
+ * out_ll; the caller runs the per-point kernel), 1 when K2 (the GEMM) ran, 2 when the prefix kernel
+ * ran.  kernel_mode: 0 = prefix kernel when the batch has at least min_run points per q-run (points
+ * of a group that also share q), else the GEMM; 1 = GEMM; 2 = prefix kernel.  Device tables: `slot_mh` = (slot_mult, slot_h)
  * pairs; `step_mask` = per 32 slots, bit 2 nt + c set when one of the slots 8 nt + 2 q + c, q < 4,
  * has a count (cvf_step_masks); `log_tab` = cv_log_table.  w_limit = largest profile workspace in
  * doubles; larger batches run in several group ranges. */
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
                      int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
-                     double min_group, cudaStream_t stream, int *used);
+                     double min_group, double min_run, int kernel_mode, cudaStream_t stream, int *used);
 
 /* host: the step masks of a slot_h table (length a multiple of 32) */
 #include <vector>

@@ -218,21 +218,23 @@ class LikelihoodContext:
                     'cvb_last_kernel_ms')
         return ms.value, n.value
 
-    PATH_AUTO, PATH_PER_POINT, PATH_FACTORED = 0, 1, 2
+    PATH_AUTO, PATH_PER_POINT, PATH_FACTORED, PATH_FACTORED_GEMM, PATH_FACTORED_PREFIX = 0, 1, 2, 3, 4
 
     def set_path(self, mode):
-        """Evaluation path of the repeats model: PATH_AUTO, PATH_PER_POINT or PATH_FACTORED
+        """Evaluation path of the repeats model: PATH_AUTO, PATH_PER_POINT, PATH_FACTORED (GEMM or
+        prefix kernel by the sharing of q), PATH_FACTORED_GEMM or PATH_FACTORED_PREFIX
         (include/covest_b200.h, cvb_set_path)."""
         self._check(self._lib.cvb_set_path(self._ctx, int(mode)), 'cvb_set_path')
 
     def last_path_info(self):
         """Facts about the most recent evaluation (cvb_last_path_info)."""
-        buf = (ctypes.c_double * 8)()
-        self._check(self._lib.cvb_last_path_info(self._ctx, buf, 8), 'cvb_last_path_info')
+        buf = (ctypes.c_double * 12)()
+        self._check(self._lib.cvb_last_path_info(self._ctx, buf, 12), 'cvb_last_path_info')
         v = list(buf)
-        return {'path': {1: 'per-point', 2: 'factored'}.get(int(v[0]), 'none'), 'groups': int(v[1]),
-                'tiles': int(v[2]), 'items': int(v[3]), 'profile_doubles': int(v[4]),
-                'plan_ms': v[5], 'profile_ms': v[6], 'gemm_ms': v[7]}
+        return {'path': {1: 'per-point', 2: 'factored', 3: 'factored'}.get(int(v[0]), 'none'),
+                'kernel': {1: 'cv_loglik_kernel', 2: 'cvf_gemm_kernel', 3: 'cvf_prefix_kernel'}.get(int(v[0]), 'none'),
+                'groups': int(v[1]), 'tiles': int(v[2]), 'items': int(v[3]), 'profile_doubles': int(v[4]),
+                'plan_ms': v[5], 'profile_ms': v[6], 'gemm_ms': v[7], 'q_runs': int(v[8])}
 
     @property
     def sm_count(self):

@@ -116,6 +116,7 @@ def _clip(model, pts):
 # 64 flop per bin for the epilogue (a log, the count-weighted sum, the mass).
 FLOP_PER_TERM_BIN = 2.0
 FLOP_PER_BIN = 64.0
+PREFIX_FLOP_PER_BIN = 6.0  # q1*P1 (1) + two*P2 (2) + many*R (2) + the add into the mass (1)
 
 
 def algorithmic_flop(n_bins, terms):
@@ -139,8 +140,17 @@ def factored_flop(model, points, n_bins, counted_bins):
     np.maximum.at(gmax, inverse, copies)
     profile = FLOP_PER_TERM_BIN * model.max_error * n_bins * float(gmax.sum())
     gemm = float(np.sum(FLOP_PER_TERM_BIN * n_bins * copies + FLOP_PER_BIN * counted_bins))
-    return {'profile_flop': profile, 'gemm_flop': gemm, 'groups': int(len(gmax)),
-            'mean_copies': float(copies.mean())}
+    # prefix kernel: per (point, bin) the three-term combination (a multiply and two FMAs) and the
+    # add into the mass; per (point, bin with a count) the same 64 flop as above; per (q-run, copy
+    # number beyond 2 up to the run's largest cut-off, bin) one FMA into the running sum
+    rkeys = np.ascontiguousarray(pts[:, [0, 1, 4]]).view([('c', 'f8'), ('e', 'f8'), ('q', 'f8')]).ravel()
+    _, rinv = np.unique(rkeys, return_inverse=True)
+    rmax = np.zeros(rinv.max() + 1)
+    np.maximum.at(rmax, rinv, copies)
+    prefix = float(len(pts)) * (PREFIX_FLOP_PER_BIN * n_bins + FLOP_PER_BIN * counted_bins) + \
+        FLOP_PER_TERM_BIN * n_bins * float(np.maximum(rmax - 2, 0).sum())
+    return {'profile_flop': profile, 'gemm_flop': gemm, 'prefix_flop': prefix, 'groups': int(len(gmax)),
+            'q_runs': int(len(rmax)), 'mean_copies': float(copies.mean())}
 
 
 def lattice_term_stats(model, axes):

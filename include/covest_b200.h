@@ -123,18 +123,22 @@ CVB_API int cvb_last_kernel_ms(cvb_ctx *ctx, double *out_ms, int *out_launches);
  * (cv_loglik_kernel: one warp per point, reference models.py:211-242 term by term) or *factored*:
  * the per-copy-number bin profiles sum_s a_os * tp(o * l_s, j) -- the inner sum of models.py:236 --
  * are computed once per distinct (coverage, error_rate) of the batch and contracted with the copy
- * weights b(o) of every point (models.py:193-208) by an FP64 tensor-core GEMM.  mode 0 = automatic
- * (factored for batches of >= 2048 points with >= 12 points per distinct (c, e)), 1 = per-point
- * only, 2 = factored whenever the model supports it.  The environment variable
- * COVEST_B200_PATH=direct|factored|auto sets the initial mode.  Per-bin probabilities
- * (cvb_probs_batch) always use the per-point kernel. */
+ * weights b(o) of every point (models.py:193-208) -- by an FP64 tensor-core GEMM, or, when points
+ * of a (c, e) group also share q (lattices: grid.py:25-33, :95-98), by the *prefix kernel*: b(o) is
+ * geometric beyond o = 2 (models.py:196-208), so one running sum over the copy numbers serves every
+ * cut-off of such a q-run.  mode 0 = automatic (factored for batches of >= 2048 points with >= 12
+ * points per distinct (c, e); prefix kernel at >= 4 points per q-run), 1 = per-point only,
+ * 2 = factored whenever the model supports it, 3 = factored with the GEMM, 4 = factored with the
+ * prefix kernel.  The environment variable COVEST_B200_PATH=direct|factored|gemm|prefix|auto sets
+ * the initial mode.  Per-bin probabilities (cvb_probs_batch) always use the per-point kernel. */
 CVB_API int cvb_set_path(cvb_ctx *ctx, int mode);
 
-/* Facts about the most recent evaluation: out[0] = path used (1 per-point, 2 factored); for the
- * factored path out[1] = distinct (c, e) groups, out[2] = 128-point tiles, out[3] = profile items
- * (16 copy numbers each), out[4] = doubles of profile workspace, out[5..7] = device ms of the
- * planning kernels, the profile kernel and the GEMM kernel (after cvb_set_timing(ctx, 1)). */
-#define CVB_PATH_INFO_LEN 8
+/* Facts about the most recent evaluation: out[0] = path used (1 per-point, 2 factored with the
+ * GEMM, 3 factored with the prefix kernel); for the factored path out[1] = distinct (c, e) groups,
+ * out[2] = tiles, out[3] = profile items (16 copy numbers each), out[4] = doubles of profile
+ * workspace, out[5..7] = device ms of the planning kernels, the profile kernel and the GEMM /
+ * prefix kernel (after cvb_set_timing(ctx, 1)), out[8] = q-runs (0 when the GEMM ordering ran). */
+#define CVB_PATH_INFO_LEN 12
 CVB_API int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out);
 
 /* number of model parameters of the context (2 or 5), number of SMs of its device */

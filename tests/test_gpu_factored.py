@@ -25,18 +25,31 @@ def _repeats_cases():
     return [n for n in golden_case_names() if load_case(n)['model'] == 'repeats']
 
 
+KERNELS = ['gemm', 'prefix']
+
+
+def _force(ctx, kernel):
+    ctx.set_path({'gemm': ctx.PATH_FACTORED_GEMM, 'prefix': ctx.PATH_FACTORED_PREFIX}[kernel])
+
+
+def _ran(ctx, kernel):
+    info = ctx.last_path_info()
+    return info['path'] == 'factored' and info['kernel'] == 'cvf_%s_kernel' % kernel
+
+
 def _lattice(axes):
     return np.ascontiguousarray(np.array(np.meshgrid(*axes, indexing='ij')).reshape(len(axes), -1).T)
 
 
+@pytest.mark.parametrize('kernel', KERNELS)
 @pytest.mark.parametrize('name', _repeats_cases())
-def test_factored_matches_reference_golden(name):
+def test_factored_matches_reference_golden(name, kernel):
     case = load_case(name)
     m = _model(case)
     with context_for(m) as ctx:
-        ctx.set_path(ctx.PATH_FACTORED)
+        _force(ctx, kernel)
         got = ctx.loglik(case['points'])
-        assert ctx.last_path_info()['path'] == 'factored'
+        assert _ran(ctx, kernel)
     rel = rel_err_ll(got, np.array(case['ll'], dtype=float))
     assert rel.max() <= LL_RTOL, (name, int(rel.argmax()), case['points'][int(rel.argmax())],
                                   got[int(rel.argmax())], case['ll'][int(rel.argmax())])
@@ -45,7 +58,8 @@ def test_factored_matches_reference_golden(name):
 @pytest.mark.parametrize('name,c0,n_ce,n_q', [('cfg2_repeats', 30, 12, 40), ('e05_trim10_repeats', 10, 12, 40),
                                               ('e05_repeats_allerr', 10, 6, 30),
                                               ('cfg4_repeats_k31', 200, 2, 12)])
-def test_factored_grouped_points_against_oracle(name, c0, n_ce, n_q):
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_factored_grouped_points_against_oracle(name, c0, n_ce, n_q, kernel):
     """Seeded points that share (coverage, error rate) pairs, as grids and stencils do, including
     the bound and edge points of SURVEY.md section 8(d)."""
     case = load_case(name)
@@ -59,14 +73,15 @@ def test_factored_grouped_points_against_oracle(name, c0, n_ce, n_q):
     qs[2] = [.5, .5, 0.0]
     qs[3] = [.5, .5, 1.0]
     qs[4] = [.1, 2, -1]  # clipped to (min_q1, 1, 0)
+    qs[8:, 2] = qs[5 + np.arange(n_q - 8) % 3, 2]  # three shared q: runs with many cut-offs each
     pts = np.array([[c, e, a, b, q] for c, e in ce for a, b, q in qs])
     pts = pts[rng.permutation(len(pts))]
     want = m.loglik_batch(pts, threads=8)
     with context_for(m) as ctx:
-        ctx.set_path(ctx.PATH_FACTORED)
+        _force(ctx, kernel)
         got = ctx.loglik(pts)
         info = ctx.last_path_info()
-        assert info['path'] == 'factored' and info['groups'] == n_ce
+        assert _ran(ctx, kernel) and info['groups'] == n_ce
     inside = ~(np.isposinf(want) | np.isnan(want))  # the reference's own overflow, DESIGN.md section 3
     assert inside.sum() >= 0.8 * len(pts)
     rel = rel_err_ll(got[inside], want[inside])
@@ -86,7 +101,11 @@ def test_factored_equals_per_point_kernel_on_a_lattice(bins):
     with context_for(m) as ctx:
         got = ctx.loglik(grid)
         info = ctx.last_path_info()
-        assert info['path'] == 'factored' and info['groups'] == 24, info
+        assert _ran(ctx, 'prefix') and info['groups'] == 24 and info['q_runs'] == 24 * 6, info
+        ctx.set_path(ctx.PATH_FACTORED_GEMM)
+        gemm = ctx.loglik(grid)
+        assert _ran(ctx, 'gemm')
+        assert rel_err_ll(got, gemm).max() <= PATH_RTOL
         ctx.set_path(ctx.PATH_PER_POINT)
         want = ctx.loglik(grid)
         assert ctx.last_path_info()['path'] == 'per-point'
@@ -107,7 +126,8 @@ def test_factored_equals_per_point_kernel_on_a_lattice(bins):
     assert rel_err_ll(got[pick], ref).max() <= LL_RTOL
 
 
-def test_factored_results_do_not_depend_on_batch_composition():
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_factored_results_do_not_depend_on_batch_composition(kernel):
     case = load_case('cfg3_repeats_dense1000')
     m = _model(case)
     rng = np.random.default_rng(8)
@@ -116,7 +136,7 @@ def test_factored_results_do_not_depend_on_batch_composition():
     grid = _lattice(axes)
     perm = rng.permutation(len(grid))
     with context_for(m) as ctx:
-        ctx.set_path(ctx.PATH_FACTORED)
+        _force(ctx, kernel)
         a = ctx.loglik(grid)
         b = ctx.loglik(grid[perm])
         some = ctx.loglik(grid[100:140])
@@ -126,7 +146,8 @@ def test_factored_results_do_not_depend_on_batch_composition():
     assert one[0] == a[777]
 
 
-def test_factored_edge_rows_and_small_workspace(monkeypatch):
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_factored_edge_rows_and_small_workspace(monkeypatch, kernel):
     """NaN rows, empty copy ranges, and a profile workspace so small that the batch runs in many
     group ranges."""
     case = load_case('cfg2_repeats')
@@ -141,15 +162,16 @@ def test_factored_edge_rows_and_small_workspace(monkeypatch):
         want = ctx.loglik(grid)
     monkeypatch.setenv('COVEST_B200_PROFILE_MIB', '1')
     with context_for(m) as ctx:
-        ctx.set_path(ctx.PATH_FACTORED)
+        _force(ctx, kernel)
         got = ctx.loglik(grid)
     assert np.array_equal(np.isnan(got), np.isnan(want))
     assert math.isnan(got[5]) and math.isnan(got[9])
     assert rel_err_ll(got, want).max() <= PATH_RTOL
 
 
-def test_factored_with_a_tail_term():
-    """tail != 0 exercises the compensated mass sum of the GEMM epilogue (models.py:103-104)."""
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_factored_with_a_tail_term(kernel):
+    """tail != 0 exercises the compensated mass sum of the epilogues (models.py:103-104)."""
     case = load_case('cfg2_repeats_trim120')
     assert case['tail'] != 0
     m = _model(case)
@@ -158,6 +180,44 @@ def test_factored_with_a_tail_term():
     grid = _lattice(axes)
     want = m.loglik_batch(grid, threads=8)
     with context_for(m) as ctx:
-        ctx.set_path(ctx.PATH_FACTORED)
+        _force(ctx, kernel)
         got = ctx.loglik(grid)
     assert rel_err_ll(got, want).max() <= LL_RTOL
+
+
+def test_prefix_kernel_long_runs_and_many_runs():
+    """q-runs longer than a batch (512 points), more runs than a batch holds (4), tiles that end
+    inside a run, and the automatic choice between the two kernels."""
+    case = load_case('cfg3_repeats_dense1000')
+    hist = {j: h for j, h in case_hist(case).items() if j <= 400}
+    m = orc.Model('repeats', case['k'], case['r'], hist, case['tail'], max_error=8)
+    rng = np.random.default_rng(77)
+    rows = []
+    for c, e in [(25.0, .02), (40.0, .05)]:
+        for q, n in [(.5, 1500), (.3, 3), (.31, 1), (.32, 1), (.33, 1), (.34, 1), (.9, 700), (1.0, 40), (0.0, 40)]:
+            for _ in range(n):
+                rows.append([c, e, rng.uniform(.3, 1), rng.uniform(0, 1), q])
+    pts = np.array(rows)[rng.permutation(len(rows))]
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_FACTORED)
+        got = ctx.loglik(pts)
+        assert _ran(ctx, 'prefix') and ctx.last_path_info()['q_runs'] == 18
+        ctx.set_path(ctx.PATH_PER_POINT)
+        want = ctx.loglik(pts)
+        assert rel_err_ll(got, want).max() <= PATH_RTOL
+        # every point its own q: the GEMM is the better tool, and the automatic mode says so
+        solo = pts.copy()
+        solo[:, 4] = rng.uniform(.05, 1, len(solo))
+        ctx.set_path(ctx.PATH_FACTORED)
+        got = ctx.loglik(solo)
+        assert _ran(ctx, 'gemm')
+        _force(ctx, 'prefix')
+        alt = ctx.loglik(solo)
+        assert _ran(ctx, 'prefix')
+        assert rel_err_ll(got, alt).max() <= PATH_RTOL
+    pick = rng.choice(len(pts), 16, replace=False)
+    ref = m.loglik_batch(pts[pick], threads=8)
+    with context_for(m) as ctx:
+        _force(ctx, 'prefix')
+        sub = ctx.loglik(pts[pick])
+    assert rel_err_ll(sub, ref).max() <= LL_RTOL

@@ -12,5 +12,5 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_
 echo "reference rc=$?"; cat gpurun_out/${TAG}_bench_reference.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:cvf_gemm -s 3 -c 1 -o gpurun_out/${TAG}_prof_cvf_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_cvf_gemm.log 2>&1
-echo "ncu gemm rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cvf_prefix -s 3 -c 1 -o gpurun_out/${TAG}_prof_cvf_prefix -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_cvf_prefix.log 2>&1
+echo "ncu prefix rc=$?"

@@ -19,11 +19,18 @@ axes = workload.lattice_axes(cfg['theta'], n_c=40, n_e=25)
 pts = torch.from_numpy(workload.lattice_points(axes)).cuda()
 out = torch.empty(len(pts), dtype=torch.float64, device='cuda')
 ctx.set_timing(True)
-for i in range(4):
-    ctx.loglik(pts, out=out)
-    torch.cuda.synchronize()
-    info = ctx.last_path_info()
-    print('total %.3f ms' % ctx.last_kernel_ms()[0], {k: (round(v, 3) if isinstance(v, float) else v) for k, v in info.items()})
+res = {}
+for mode in (ctx.PATH_FACTORED_GEMM, ctx.PATH_FACTORED_PREFIX):
+    ctx.set_path(mode)
+    for i in range(4):
+        ctx.loglik(pts, out=out)
+        torch.cuda.synchronize()
+        info = ctx.last_path_info()
+        print('total %.3f ms' % ctx.last_kernel_ms()[0], {k: (round(v, 3) if isinstance(v, float) else v) for k, v in info.items()})
+    res[mode] = out.clone()
+a, b = res[ctx.PATH_FACTORED_GEMM], res[ctx.PATH_FACTORED_PREFIX]
+fin = torch.isfinite(a)
+print('kernels agree to', float(((a[fin] - b[fin]).abs() / a[fin].abs()).max()), 'non-finite equal', bool((torch.isfinite(b) == fin).all()))
 t0 = torch.cuda.Event(enable_timing=True)
 t1 = torch.cuda.Event(enable_timing=True)
 t0.record()
