@@ -202,6 +202,21 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def committed_traffic(kernel, workload_name, n_points):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture of this same command (profiles/, per launch) -- only when this run
+    launches the kernel on the batch the capture was taken on; else None."""
+    path = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
+    try:
+        with open(path) as f:
+            for row in json.load(f):
+                if row['kernel'] == kernel and row['workload'] == workload_name and row['points'] == n_points:
+                    return {'bytes': row['dram_bytes'], 'source': row['source']}
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def workload_config(name, world, n_bins, axes):
     lens = [len(a) for a in axes]
     return {'workload': '%s: repeats model k=21 r=100, lattice %s = %d points x %d bins, %d per rank' % (
@@ -354,7 +369,9 @@ def run_b200(args, rank, world, local_rank):
             'gpu_launches': (ctx.last_kernel_ms()[1] + 3) * 2 * args.steps,
             'clocks': clocks.summary(),
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak_tflops if peak_tflops else None, 'traffic': None,
+                         'frac': achieved / peak_tflops if peak_tflops else None,
+                         'traffic': (committed_traffic(dominant, args.workload, count) or {}).get('bytes'),
+                         'traffic_source': (committed_traffic(dominant, args.workload, count) or {}).get('source'),
                          'kernel': dominant, 'kernel_ms': dom_ms,
                          'flop_per_launch': flop_launch, 'mean_terms_per_point': float(terms.mean()),
                          'peak_source': 'register-resident DFMA chain measured in this run (cvb_fp64_peak); '
