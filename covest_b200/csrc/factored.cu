@@ -914,12 +914,35 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 #define CVF_PEW 33     /* doubles per row of that buffer (odd: conflict-free both ways) */
 #define CVF_PASS_SLOTS (CVF_PT * CVF_SL)
 
+struct __align__(16) CvfEvent {
+    double q1, two, many;
+    int info, need;
+};
+
+/* explicit shared-window accesses: the hot loop addresses its records, the logarithm table and the
+ * transpose buffer with 32-bit addresses kept in registers */
+__device__ __forceinline__ double2 cvf_lds128(unsigned int a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void cvf_lds_event(unsigned int a, double &many, int &info, int &need)
+{
+    asm volatile("ld.shared.f64 %0, [%3+16];\n\tld.shared.v2.s32 {%1, %2}, [%3+24];"
+                 : "=d"(many), "=r"(info), "=r"(need)
+                 : "r"(a));
+}
+__device__ __forceinline__ void cvf_sts64(unsigned int a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
 struct CvfPrefixSmem {
     double log_tab[2 * CV_LOG_N];
-    /* the points of the batch by ascending cut-off (the schedule): weights of copy 1, copy 2 and
-     * of the running sum; (batch position | run << 16, copies = O_thr - 1) */
-    double q1[CVF_PB], two[CVF_PB], many[CVF_PB];
-    int2 sched[CVF_PB + 1];
+    /* the points of the batch by ascending cut-off (the schedule), 32 bytes each: weights of
+     * copy 1, copy 2 and of the running sum; batch position | run << 16; copies = O_thr - 1 */
+    CvfEvent ev[CVF_PB + 1];
     int need[CVF_PB];  /* by batch position: copies of the point */
     double base[CVF_NQ];
     int seg[CVF_NQ + 1]; /* batch positions where its q-runs start */
@@ -946,28 +969,34 @@ __device__ __noinline__ double cvf_log_rare(double x)
     return (x <= 0.0) ? -INFINITY : log(x);
 }
 
-/* cv_log_tab (the same bits) for positive normal x with the index arithmetic on the high word;
- * everything else takes cvf_log_rare */
-__device__ __forceinline__ double cvf_safe_log(double x, const double *tab)
+/* cv_log_tab's algorithm for positive normal x with the index arithmetic on the high word and the
+ * table at the shared-window address `tab_s`; everything else takes cvf_log_rare.  The
+ * coefficients of r^5 .. r^7 and the high part of ln 2 are cut to 20 mantissa bits (they fit the
+ * immediate field of the FP64 instructions; errors below 2^-58 and none: k * ln2_hi stays exact);
+ * the polynomial in Estrin form, the last sum reordered: absolute error below 2.5e-16 (1 + |log x|)
+ * (cv_log_tab: 2e-16). */
+__device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
 {
     const int hi = __double2hiint(x);
     if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u)
         return cvf_log_rare(x);
     const int t = hi - (int)(CV_LOG_OFF >> 32);
-    const int i = (t >> 13) & (CV_LOG_N - 1);
     const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
-    const double2 c = *reinterpret_cast<const double2 *>(tab + 2 * i); /* (invc, logc) */
+    const double2 c = cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4))); /* (invc, logc) of interval (t >> 13) & 127 */
     const double r = cv_fma(z, c.x, -1.0);
     const double kd = (double)(t >> 20);
-    const double hi_part = cv_fma(kd, 0x1.62e42fefa3800p-1, c.y);
-    double p = cv_fma(r, 1.0 / 7.0, -1.0 / 6.0);
-    p = cv_fma(r, p, 1.0 / 5.0);
-    p = cv_fma(r, p, -1.0 / 4.0);
-    p = cv_fma(r, p, 1.0 / 3.0);
-    p = cv_fma(r, p, -0.5);
+    const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y); /* ln 2 to 20 bits */
+    /* log1p(r) - r = r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7), in three short dependent
+     * steps (Estrin) instead of five */
     const double r2 = cv_mul(r, r);
-    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.ef35793c76730p-45));
-    return cv_add(hi_part, cv_add(r, lo));
+    const double a = cv_fma(r, 1.0 / 3.0, -0.5);
+    const double b = cv_fma(r, 0x1.9999ap-3 /* 1/5 */, -0.25);
+    const double c2 = cv_fma(r, 0x1.24925p-3 /* 1/7 */, -0x1.55555p-3 /* 1/6 */);
+    const double r4 = cv_mul(r2, r2);
+    const double ab = cv_fma(r2, b, a);
+    const double p = cv_fma(r4, c2, ab);
+    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.fdf473de6af28p-22)); /* ln 2 - 0x1.62e42p-1 */
+    return cv_add(cv_add(hi_part, r), lo); /* hi_part + r does not wait for the polynomial */
 }
 
 /* number of entries of the ascending a[0..n) that are < x (strict) resp. <= x */
@@ -1006,6 +1035,9 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
     double *red_all = scratch + (size_t)blockIdx.x * (3 * CVF_PW * CVF_PB);
     double *red = red_all + warp * CVF_PB; /* plane stride CVF_PW * CVF_PB */
     const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
+    const unsigned int log_s = (unsigned int)__cvta_generic_to_shared(S.log_tab);
+    const unsigned int ev_s = (unsigned int)__cvta_generic_to_shared(S.ev);
+    const unsigned int tbuf_s = (unsigned int)__cvta_generic_to_shared(tbuf + lane); /* the lane's column */
     for (int i = tid; i < 2 * CV_LOG_N; i += CVF_PT)
         S.log_tab[i] = log_tab[i];
     const int nslots = nsteps * CVF_NS;
@@ -1095,14 +1127,21 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     for (int s = 0; s < CVF_NQ; s++)
                         if (s != mine && seg_end[s] > seg0[s])
                             rank += cvf_count_below(S.need + seg0[s], seg_end[s] - seg0[s], need, s < mine);
-                    S.sched[rank] = make_int2(t | (mine << 16), need);
-                    S.q1[rank] = pq1[j];
-                    S.two[rank] = ptwo[j];
-                    S.many[rank] = pmany[j];
+                    CvfEvent e;
+                    e.q1 = pq1[j];
+                    e.two = ptwo[j];
+                    e.many = pmany[j];
+                    e.info = t | (mine << 16);
+                    e.need = need;
+                    S.ev[rank] = e;
                 }
             }
-            if (tid == 0)
-                S.sched[npts] = make_int2(0, 0); /* read ahead by the loop below, never used */
+            if (tid == 0) { /* read ahead by the loop below, never used */
+                CvfEvent e;
+                e.q1 = e.two = e.many = 0.0;
+                e.info = e.need = 0;
+                S.ev[npts] = e;
+            }
             __syncthreads();
 
             /* ---- passes over the slots ---- */
@@ -1245,14 +1284,24 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     __syncwarp();
                 };
                 int o_done = 2;
-                int2 ev = S.sched[0];
-                double q1 = S.q1[0], two = S.two[0], many = S.many[0];
+                unsigned int ev_a = ev_s; /* the record of the point after the current one */
+                double q1, two, many;
+                int info, need;
+                {
+                    const double2 qt = cvf_lds128(ev_a);
+                    q1 = qt.x;
+                    two = qt.y;
+                    cvf_lds_event(ev_a, many, info, need);
+                }
+                unsigned int tb_a = tbuf_s; /* row `pending` of the transpose buffer */
                 for (int k = 0; k < npts; k++) {
                     /* the next point's record travels while this one is worked on */
-                    const int2 ev_next = S.sched[k + 1];
-                    const double q1_next = S.q1[min(k + 1, CVF_PB - 1)], two_next = S.two[min(k + 1, CVF_PB - 1)],
-                                 many_next = S.many[min(k + 1, CVF_PB - 1)];
-                    while (o_done < ev.y) { /* one more copy into the running sums (o_done >= 3) */
+                    ev_a += (unsigned int)sizeof(CvfEvent);
+                    const double2 qt_next = cvf_lds128(ev_a);
+                    double many_next;
+                    int info_next, need_next;
+                    cvf_lds_event(ev_a, many_next, info_next, need_next);
+                    while (o_done < need) { /* one more copy into the running sums (o_done >= 3) */
                         o_done++;
                         double x[CVF_SL];
                         take(x);
@@ -1267,12 +1316,12 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             }
                     }
                     /* the three-term combination for the thread's slots, models.py:235-241 */
-                    const int pt = ev.x & 0xffff;
+                    const int pt = info & 0xffff;
                     double p[CVF_SL];
 #pragma unroll
                     for (int i = 0; i < CVF_SL; i++)
                         p[i] = cv_fma(two, P2[i], cv_mul(q1, P1[i]));
-                    switch (ev.x >> 16) {
+                    switch (info >> 16) {
 #define CVF_CASE(s_)                                                                                   \
     case s_:                                                                                           \
         _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) p[i] = cv_fma(many, R[s_][i], p[i]);        \
@@ -1283,10 +1332,11 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         CVF_CASE(3)
 #undef CVF_CASE
                     }
-                    ev = ev_next;
-                    q1 = q1_next;
-                    two = two_next;
+                    q1 = qt_next.x;
+                    two = qt_next.y;
                     many = many_next;
+                    info = info_next;
+                    need = need_next;
                     /* models.py:100-107 for the thread's slots */
                     double sum = 0.0, mh = 0.0, ml = 0.0;
 #pragma unroll
@@ -1296,22 +1346,32 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         else
                             mh = cv_add(mh, p[i]);
                     }
+                    if (log_mask == 1) { /* the usual case: the warp's first half-line holds the bins with counts */
+                        double term = cv_mul(hcnt[0], cvf_safe_log(p[0], log_s)); /* utils.py:32-35 */
+                        if (hcnt[0] == 0.0) /* models.py:106 `if h` */
+                            term = 0.0;
+                        sum = term;
+                    } else if (log_mask) {
 #pragma unroll
-                    for (int i = 0; i < CVF_SL; i++)
-                        if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
-                            double term = cv_mul(hcnt[i], cvf_safe_log(p[i], S.log_tab)); /* utils.py:32-35 */
-                            if (hcnt[i] == 0.0) /* models.py:106 `if h` */
-                                term = 0.0;
-                            sum = cv_add(sum, term);
-                        }
-                    tbuf[pending * CVF_PEW + lane] = sum;
-                    tbuf[CVF_TBUF_DOUBLES + pending * CVF_PEW + lane] = mh;
+                        for (int i = 0; i < CVF_SL; i++)
+                            if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
+                                double term = cv_mul(hcnt[i], cvf_safe_log(p[i], log_s));
+                                if (hcnt[i] == 0.0)
+                                    term = 0.0;
+                                sum = cv_add(sum, term);
+                            }
+                    }
+                    cvf_sts64(tb_a, sum);
+                    cvf_sts64(tb_a + CVF_TBUF_DOUBLES * 8, mh);
                     if (MASS)
-                        tbuf[2 * CVF_TBUF_DOUBLES + pending * CVF_PEW + lane] = ml;
+                        cvf_sts64(tb_a + 2 * CVF_TBUF_DOUBLES * 8, ml);
+                    tb_a += CVF_PEW * 8;
                     if (lane == pending)
                         mypt = pt;
-                    if (++pending == CVF_PE)
+                    if (++pending == CVF_PE) {
                         flush();
+                        tb_a = tbuf_s;
+                    }
                 }
                 if (pending)
                     flush();
