@@ -324,26 +324,26 @@ def run_b200(args, rank, world, local_rank):
             torch.cuda.synchronize()
             kernel_ms.append(ctx.last_kernel_ms()[0])
             phases.append(ctx.last_path_info())
+        # ---- timed: end to end with host buffers ----
+        for _ in range(min(args.warmup, 2)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rows_host = step_host()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * count * n_bins * args.steps / float(t.item())
+
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = world * count * n_bins * args.steps / (total_ms * 1e-3)
-
-    # ---- timed: end to end with host buffers ----
-    for _ in range(min(args.warmup, 2)):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rows_host = step_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * count * n_bins * args.steps / float(t.item())
 
     best = rows if isinstance(rows, np.ndarray) else rows.cpu().numpy()
     if rank == 0:

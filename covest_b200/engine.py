@@ -39,12 +39,18 @@ def _ptr(x):
 CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle that names the default stream explicitly
 
 
-def _stream_ptr(stream):
-    """None -> NULL (the context's own stream).  A torch stream or a raw cudaStream_t value is
-    passed through; the default stream, whose raw value is 0, is named by cudaStreamLegacy so
-    that it is not mistaken for "no stream given"."""
+def _stream_ptr(stream, like=None):
+    """None -> NULL (the context's own stream, synchronised before a host-buffer call returns) --
+    unless `like` is a torch CUDA tensor: work on device buffers is only enqueued, so it goes to
+    torch's current stream of that device, where the caller's next torch operation is ordered
+    behind it.  A torch stream or a raw cudaStream_t value is passed through; the default stream,
+    whose raw value is 0, is named by cudaStreamLegacy so that it is not mistaken for "no stream
+    given"."""
     if stream is None:
-        return None
+        if like is None or not _is_torch_cuda(like):
+            return None
+        import torch
+        stream = torch.cuda.current_stream(like.device)
     value = stream.cuda_stream if hasattr(stream, 'cuda_stream') else int(stream)
     return ctypes.c_void_p(value if value else CUDA_STREAM_LEGACY)
 
@@ -125,7 +131,7 @@ class LikelihoodContext:
                 out = torch.empty(n, dtype=torch.float64, device=pts.device)
             else:
                 out = np.empty(n, dtype=np.float64)
-        self._check(self._lib.cvb_loglik_batch(self._ctx, n, _ptr(pts), _ptr(out), _stream_ptr(stream)),
+        self._check(self._lib.cvb_loglik_batch(self._ctx, n, _ptr(pts), _ptr(out), _stream_ptr(stream, pts)),
                     'cvb_loglik_batch')
         return out
 
@@ -141,7 +147,7 @@ class LikelihoodContext:
             out = np.zeros((n, self.n_bins), dtype=np.float64)
             ll = np.empty(n, dtype=np.float64) if with_loglik else None
         self._check(self._lib.cvb_probs_batch(self._ctx, n, _ptr(pts), int(bool(clip)), _ptr(out),
-                                              _ptr(ll), _stream_ptr(stream)), 'cvb_probs_batch')
+                                              _ptr(ll), _stream_ptr(stream, pts)), 'cvb_probs_batch')
         return (out, ll) if with_loglik else out
 
     def topk(self, ll, points, k_best, stream=None):
@@ -155,7 +161,7 @@ class LikelihoodContext:
             rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64)
             llb = np.ascontiguousarray(ll, dtype=np.float64)
         self._check(self._lib.cvb_topk(self._ctx, n, _ptr(llb), _ptr(pts), int(k_best), _ptr(rows),
-                                       _stream_ptr(stream)), 'cvb_topk')
+                                       _stream_ptr(stream, pts)), 'cvb_topk')
         return rows
 
     def loglik_topk(self, points, k_best, want_ll=True, stream=None):
@@ -169,7 +175,7 @@ class LikelihoodContext:
             ll = np.empty(n, dtype=np.float64) if want_ll else None
             rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64)
         self._check(self._lib.cvb_loglik_topk(self._ctx, n, _ptr(pts), _ptr(ll), int(k_best),
-                                              _ptr(rows), _stream_ptr(stream)), 'cvb_loglik_topk')
+                                              _ptr(rows), _stream_ptr(stream, pts)), 'cvb_loglik_topk')
         return ll, rows
 
     def lattice_eval(self, axes, first=0, stride=1, count=None, want_ll=True, k_best=0,
@@ -196,7 +202,7 @@ class LikelihoodContext:
         self._check(self._lib.cvb_lattice_eval(self._ctx, lens.ctypes.data_as(_capi.c_int32_p),
                                                vals.ctypes.data_as(_capi.c_double_p), int(first),
                                                int(stride), int(block), int(count), _ptr(ll), int(k_best),
-                                               _ptr(rows), _stream_ptr(stream)), 'cvb_lattice_eval')
+                                               _ptr(rows), _stream_ptr(stream, ll)), 'cvb_lattice_eval')
         return ll, rows
 
     # -- measurement -----------------------------------------------------------------------

@@ -26,17 +26,19 @@ def cfg3():
     pts = workload.lattice_points(axes)
     assert pts.shape == (1000000, 5) and len(hist) == 1000
     ctx = model.device_context
-    ll = ctx.loglik(pts)
-    info = ctx.last_path_info()
-    yield dict(cfg=cfg, hist=hist, model=model, axes=axes, pts=pts, ll=ll, info=info)
+    ll = ctx.loglik(pts)   # host buffers: copies and evaluation pipelined in slices
+    yield dict(cfg=cfg, hist=hist, model=model, axes=axes, pts=pts, ll=ll)
     model.close()
 
 
 def test_the_lattice_takes_the_prefix_kernel(cfg3):
-    info = cfg3['info']
+    import torch
+    ctx, ll = cfg3['model'].device_context, cfg3['ll']
+    dev = ctx.loglik(torch.from_numpy(cfg3['pts']).cuda())   # device buffers: one evaluation
+    info = ctx.last_path_info()
     assert info['path'] == 'factored' and info['kernel'] == 'cvf_prefix_kernel', info
     assert info['groups'] == 40 * 25 and info['q_runs'] == 40 * 25 * 10
-    ll = cfg3['ll']
+    assert np.array_equal(dev.cpu().numpy(), ll)
     assert not np.any(np.isnan(ll)) and not np.any(np.isposinf(ll)) and np.all(ll < 0)
 
 
