@@ -66,6 +66,8 @@ def load():
     L.cvb_last_kernel_ms.argtypes = [vp, c_double_p, ctypes.POINTER(ctypes.c_int)]
     L.cvb_set_path.restype = ctypes.c_int
     L.cvb_set_path.argtypes = [vp, ctypes.c_int]
+    L.cvb_merge_rows.restype = ctypes.c_int
+    L.cvb_merge_rows.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     L.cvb_last_path_info.restype = ctypes.c_int
     L.cvb_last_path_info.argtypes = [vp, c_double_p, ctypes.c_int]
     L.cvb_n_param.restype = ctypes.c_int
@@ -78,4 +80,4 @@ def load():
 
 EXPORTS = ('cvb_ctx_create', 'cvb_ctx_destroy', 'cvb_last_error', 'cvb_loglik_batch',
            'cvb_probs_batch', 'cvb_topk', 'cvb_loglik_topk', 'cvb_lattice_eval', 'cvb_fp64_peak', 'cvb_set_timing',
-           'cvb_last_kernel_ms', 'cvb_set_path', 'cvb_last_path_info', 'cvb_n_param', 'cvb_device_sm_count', 'cvb_version')
+           'cvb_last_kernel_ms', 'cvb_set_path', 'cvb_merge_rows', 'cvb_last_path_info', 'cvb_n_param', 'cvb_device_sm_count', 'cvb_version')

@@ -633,6 +633,17 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     return CVB_OK;
 }
 
+extern "C" int cvb_merge_rows(const double *rows, int n_rows, int n_cols, int k_best, double *out_rows,
+                              void *stream)
+{
+    if (!rows || !out_rows || n_rows < 0 || n_rows > 2048 || n_cols < 1 || k_best < 1)
+        return CVB_EINVAL;
+    if (!is_device_ptr(rows) || !is_device_ptr(out_rows))
+        return CVB_EINVAL;
+    cudaError_t e = cv_launch_merge_rows(rows, n_rows, n_cols, k_best, out_rows, (cudaStream_t)stream);
+    return e == cudaSuccess ? CVB_OK : CVB_ECUDA;
+}
+
 /* ---- path selection and facts about the last evaluation -------------------------------------- */
 extern "C" int cvb_set_path(cvb_ctx *ctx, int mode)
 {

@@ -38,6 +38,9 @@ cudaError_t cv_launch_topk(const double *ll, long long n_points, int K, double *
 /* K3 for large batches (topk.cu): the same selection by one stable descending radix sort of
  * order-preserving keys.  `scratch`: device, cv_topk_sort_bytes(n) bytes. */
 size_t cv_topk_sort_bytes(long long n);
+/* merge of best-row blocks of several ranks: n <= 2048 rows of c doubles -> the k best, device buffers */
+cudaError_t cv_launch_merge_rows(const double *rows, int n, int c, int k, double *out, cudaStream_t stream);
+
 cudaError_t cv_launch_topk_sort(const double *ll, long long n, int K, void *scratch, size_t scratch_bytes,
                                 double *out_ll, long long *out_idx, cudaStream_t stream);
 

@@ -82,3 +82,74 @@ cudaError_t cv_launch_topk_sort(const double *ll, long long n, int K, void *scra
     cv_topk_take<<<(K + 127) / 128, 128, 0, stream>>>(dk.Current(), dv.Current(), n, K, out_ll, out_idx);
     return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Merge of the best rows of several ranks (multi-GPU rounds): n rows of c doubles, column 0 the   */
+/* log-likelihood.  Total order: larger log-likelihood first (NaN as -inf), ties by the parameter */
+/* columns in ascending lexicographic order (NaN last) -- for a lattice with ascending axes the   */
+/* lattice index, so the result does not depend on how many ranks produced the rows.  One CTA,    */
+/* bitonic sort of row indices in shared memory; n <= CV_MERGE_MAX.                                */
+/* ------------------------------------------------------------------------------------------- */
+#define CV_MERGE_MAX 2048
+
+__device__ __forceinline__ bool cv_row_before(const double *__restrict__ rows, int c, int a, int b)
+{
+    if (a < 0 || b < 0)
+        return b < 0 && a >= 0; /* padding sorts last */
+    double x = rows[(size_t)a * c], y = rows[(size_t)b * c];
+    if (x != x)
+        x = -INFINITY;
+    if (y != y)
+        y = -INFINITY;
+    if (x != y)
+        return x > y;
+    for (int j = 1; j < c; j++) {
+        double u = rows[(size_t)a * c + j], v = rows[(size_t)b * c + j];
+        if (u != u)
+            u = INFINITY;
+        if (v != v)
+            v = INFINITY;
+        if (u != v)
+            return u < v;
+    }
+    return a < b; /* identical rows: stable */
+}
+
+__global__ void __launch_bounds__(1024)
+cv_merge_rows_kernel(const double *__restrict__ rows, int n, int c, int k, double *__restrict__ out)
+{
+    __shared__ int idx[CV_MERGE_MAX];
+    int m = 1;
+    while (m < n)
+        m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+        idx[i] = i < n ? i : -1;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool up = (i & size) == 0;
+                    const int a = idx[i], b = idx[j];
+                    if (cv_row_before(rows, c, b, a) == up) {
+                        idx[i] = b;
+                        idx[j] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int t = threadIdx.x; t < k * c; t += blockDim.x) {
+        const int r = t / c, j = t - r * c;
+        out[t] = (r < n) ? rows[(size_t)idx[r] * c + j] : (j == 0 ? -INFINITY : NAN);
+    }
+}
+
+cudaError_t cv_launch_merge_rows(const double *rows, int n, int c, int k, double *out, cudaStream_t stream)
+{
+    if (n < 0 || n > CV_MERGE_MAX || c < 1 || k < 1)
+        return cudaErrorInvalidValue;
+    cv_merge_rows_kernel<<<1, 1024, 0, stream>>>(rows, n, c, k, out);
+    return cudaGetLastError();
+}

@@ -75,6 +75,8 @@ def merge_topk(rows, k_best):
     import torch
     if not isinstance(rows, torch.Tensor):
         rows = torch.from_numpy(np.ascontiguousarray(rows))
+    if rows.is_cuda and rows.dtype == torch.float64 and rows.shape[0] <= 2048:
+        return _merge_topk_device(rows.contiguous(), k_best)
     order = torch.arange(rows.shape[0], device=rows.device)
     for col in range(rows.shape[1] - 1, 0, -1):  # least significant key first, stable sorts
         vals = rows[order, col]
@@ -84,6 +86,25 @@ def merge_topk(rows, k_best):
     key = torch.where(torch.isnan(key), torch.full_like(key, float('-inf')), key)
     order = order[torch.sort(key, descending=True, stable=True).indices]
     return rows[order[:k_best]]
+
+
+def _merge_topk_device(rows, k_best):
+    """merge_topk of a CUDA block in one launch (cvb_merge_rows, include/covest_b200.h): the same
+    order as the torch formulation above, which stays the CPU / gloo path."""
+    import ctypes
+
+    import torch
+
+    from . import _capi
+    lib = _capi.load()
+    out = torch.empty((k_best, rows.shape[1]), dtype=torch.float64, device=rows.device)
+    stream = torch.cuda.current_stream(rows.device).cuda_stream
+    with torch.cuda.device(rows.device):
+        rc = lib.cvb_merge_rows(ctypes.c_void_p(rows.data_ptr()), int(rows.shape[0]), int(rows.shape[1]),
+                                int(k_best), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream or 1))
+    if rc != 0:
+        raise RuntimeError('cvb_merge_rows failed (%d)' % rc)
+    return out[:min(int(k_best), int(rows.shape[0]))]
 
 
 def sharded_best_rows(evaluate_slice, total, k_best, block=1):

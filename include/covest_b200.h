@@ -94,6 +94,16 @@ CVB_API int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const dou
 CVB_API int cvb_loglik_topk(cvb_ctx *ctx, int64_t n_points, const double *params, double *out_ll,
                             int k_best, double *out_rows, void *stream);
 
+/* Merge of best-row blocks, the step after the all-gather of a multi-GPU round (the arg-max over
+ * the Pool.map results of covest/grid.py:61-69 when the candidates were split over ranks): `rows`
+ * holds n_rows <= 2048 rows of n_cols doubles (column 0 = log-likelihood), out_rows receives the
+ * k_best best, best first.  Order: larger log-likelihood first (NaN as -inf), ties by the other
+ * columns in ascending lexicographic order (NaN last), so the result does not depend on the number
+ * of ranks.  Device buffers only; the work is enqueued on `stream` (NULL = the legacy default
+ * stream).  Needs no context; returns 0 or a negative error code. */
+CVB_API int cvb_merge_rows(const double *rows, int n_rows, int n_cols, int k_best, double *out_rows,
+                           void *stream);
+
 /* A Cartesian lattice of candidate points generated on the device (no host->device parameter
  * traffic): n_param axes, axis a has axis_len[a] values stored consecutively in axis_values
  * (host), last axis fastest -- the order of itertools.product in covest/grid.py:33.  The call

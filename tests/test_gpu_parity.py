@@ -210,3 +210,23 @@ def test_error_reporting():
     with context_for(_model(case)) as ctx:
         assert len(ctx.loglik(np.zeros((0, 2)))) == 0
         assert math.isnan(ctx.loglik([[math.nan, .05]])[0])
+
+
+def test_device_merge_of_rank_blocks_equals_the_host_formulation():
+    """cvb_merge_rows (the merge after the all-gather of a multi-GPU round) against
+    parallel.merge_topk's torch formulation on CPU tensors: ties, NaN, -inf padding."""
+    import torch
+
+    from covest_b200 import parallel
+    rng = np.random.default_rng(21)
+    for n, k in ((128, 64), (512, 64), (100, 7), (5, 8)):
+        rows = rng.normal(size=(n, 6))
+        rows[:, 0] = np.round(rows[:, 0], 1)             # many ties on the log-likelihood
+        rows[rng.choice(n, n // 8, replace=False), 0] = -np.inf
+        rows[rng.choice(n, max(1, n // 16), replace=False), 0] = np.nan
+        rows[rng.choice(n, max(1, n // 16), replace=False), 3] = np.nan
+        rows[n // 2:n // 2 + n // 4] = rows[:n // 4]      # duplicated rows (the same point on two ranks)
+        want = parallel.merge_topk(torch.from_numpy(rows), k).numpy()
+        got = parallel.merge_topk(torch.from_numpy(rows).cuda(), k).cpu().numpy()
+        assert got.shape == want.shape
+        assert np.array_equal(got, want, equal_nan=True), (n, k)
