@@ -337,6 +337,27 @@ def run_b200(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = world * count * n_bins * args.steps / float(t.item())
+        # the same batch described by its axes (what grid.py's callers hand over): points generated
+        # on the device, only the values and the best rows cross the bus
+        lat_value = None
+        if not args.points:
+            def step_lattice():
+                ll, rows = ctx.lattice_eval(axes, first=rank, stride=world, count=count, block=block, k_best=K_BEST)
+                if world > 1:
+                    rows = parallel.merge_topk(parallel.allgather_rows(torch.from_numpy(rows).to(dev)), K_BEST)
+                return ll
+            ll_lat = step_lattice()   # warm-up, holding a result as the timed loop does (the pinned
+            ll_lat = step_lattice()   # output buffers are allocated once and then recycled)
+            ll_lat = step_lattice()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ll_lat = step_lattice()
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lat_value = world * count * n_bins * args.steps / float(t.item())
 
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -366,6 +387,9 @@ def run_b200(args, rank, world, local_rank):
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': int(count * 5 * 8),
                     'd2h_bytes_per_step': int(count * 8 + K_BEST * 6 * 8)},
+            'e2e_lattice': {'value': lat_value, 'unit': UNIT, 'h2d_bytes_per_step': int(8 * sum(len(a) for a in axes)),
+                            'd2h_bytes_per_step': int(count * 8 + K_BEST * 6 * 8),
+                            'note': 'cvb_lattice_eval: the batch handed over as its axes, values to a host buffer'},
             'gpu_launches': (ctx.last_kernel_ms()[1] + 3) * 2 * args.steps,
             'clocks': clocks.summary(),
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',

@@ -28,6 +28,8 @@ struct cvb_ctx {
     CvModelDesc desc;
     std::vector<void *> owned; /* device allocations that live as long as the context */
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; /* device -> host copy of the values while the top-K runs */
+    cudaEvent_t copy_ev = nullptr;
     /* growable staging */
     double *d_params = nullptr;
     size_t cap_params = 0; /* doubles */
@@ -157,6 +159,10 @@ extern "C" void cvb_ctx_destroy(cvb_ctx *ctx)
     for (cudaEvent_t e : ctx->ev)
         cudaEventDestroy(e);
     cvf_release(ctx->fw);
+    if (ctx->copy_ev)
+        cudaEventDestroy(ctx->copy_ev);
+    if (ctx->copy_stream)
+        cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -412,6 +418,7 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
     if (out_p && !q_dev)
         CU(grow(&ctx->d_probs, &ctx->cap_probs, (size_t)chunk * nb), "cudaMalloc(probs staging)");
 
+    bool side_copy = false;
     for (long long off = 0; off < n_points; off += chunk) {
         long long n = n_points - off < chunk ? n_points - off : chunk;
         const double *dp = params + off * np;
@@ -426,9 +433,22 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
         int rc = launch_loglik(ctx, lat, dp, n, clip, dl, dq, s);
         if (rc != CVB_OK)
             return rc;
-        if (out_ll && !l_dev)
-            CU(cudaMemcpyAsync(out_ll + off, dl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s),
+        if (out_ll && !l_dev) {
+            /* with a top-K to follow the values leave on a stream of their own, next to it */
+            cudaStream_t cs = s;
+            if (k_best > 0 && n >= (1 << 16)) {
+                if (!ctx->copy_stream)
+                    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+                if (!ctx->copy_ev)
+                    CU(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming), "cudaEventCreate");
+                CU(cudaEventRecord(ctx->copy_ev, s), "cudaEventRecord");
+                CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev, 0), "cudaStreamWaitEvent");
+                cs = ctx->copy_stream;
+                side_copy = true;
+            }
+            CU(cudaMemcpyAsync(out_ll + off, dl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, cs),
                "cudaMemcpyAsync(loglik)");
+        }
         if (out_p && !q_dev)
             CU(cudaMemcpyAsync(out_p + off * nb, dq, (size_t)n * nb * sizeof(double),
                                cudaMemcpyDeviceToHost, s),
@@ -443,6 +463,8 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
     }
     if (!all_dev)
         CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    if (side_copy)
+        CU(cudaStreamSynchronize(ctx->copy_stream), "cudaStreamSynchronize");
     return CVB_OK;
 }
 

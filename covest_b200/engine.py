@@ -28,6 +28,19 @@ def _is_torch_cuda(x):
     return hasattr(x, 'data_ptr') and hasattr(x, 'is_cuda') and x.is_cuda
 
 
+def _host_out(n, dtype=np.float64):
+    """A host output buffer of n values: page-locked when it is large and torch is at hand (the
+    device -> host copy of 10^6 values is 4x faster into pinned memory), else a plain array."""
+    if n >= (1 << 17):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty(int(n), dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.empty(n, dtype=dtype)
+
+
 def _ptr(x):
     if x is None:
         return None
@@ -130,7 +143,7 @@ class LikelihoodContext:
                 import torch
                 out = torch.empty(n, dtype=torch.float64, device=pts.device)
             else:
-                out = np.empty(n, dtype=np.float64)
+                out = _host_out(n)
         self._check(self._lib.cvb_loglik_batch(self._ctx, n, _ptr(pts), _ptr(out), _stream_ptr(stream, pts)),
                     'cvb_loglik_batch')
         return out
@@ -172,7 +185,7 @@ class LikelihoodContext:
             ll = torch.empty(n, dtype=torch.float64, device=pts.device) if want_ll else None
             rows = torch.empty((k_best, 1 + self.n_param), dtype=torch.float64, device=pts.device)
         else:
-            ll = np.empty(n, dtype=np.float64) if want_ll else None
+            ll = _host_out(n) if want_ll else None
             rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64)
         self._check(self._lib.cvb_loglik_topk(self._ctx, n, _ptr(pts), _ptr(ll), int(k_best),
                                               _ptr(rows), _stream_ptr(stream, pts)), 'cvb_loglik_topk')
@@ -197,7 +210,7 @@ class LikelihoodContext:
                 count -= (first + (mine - 1) * stride + 1) * block - total
         ll = out_ll
         if ll is None and want_ll:
-            ll = np.empty(count, dtype=np.float64)
+            ll = _host_out(count)
         rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64) if k_best > 0 else None
         self._check(self._lib.cvb_lattice_eval(self._ctx, lens.ctypes.data_as(_capi.c_int32_p),
                                                vals.ctypes.data_as(_capi.c_double_p), int(first),
