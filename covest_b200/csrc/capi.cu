@@ -523,7 +523,12 @@ static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, c
     int rc = ensure_topk(ctx, K);
     if (rc != CVB_OK)
         return rc;
-    if (n >= CVB_TOPK_SORT_MIN && n <= 0x7fffffffLL) { /* large batch: one radix sort (topk.cu) */
+    if (n >= CVB_TOPK_SORT_MIN && cv_topk_select_fits(n, K) && !getenv("COVEST_B200_TOPK_SORT")) {
+        /* large batch, few rows wanted: radix selection (topk.cu) */
+        CU(grow(&ctx->d_topk_scratch, &ctx->cap_topk_scratch, cv_topk_select_bytes()), "cudaMalloc(topk scratch)");
+        CU(cv_launch_topk_radix_select(d_ll, n, K, ctx->d_topk_scratch, ctx->n_sm, ctx->d_sel_ll, ctx->d_sel_idx, s),
+           "top-K selection");
+    } else if (n >= CVB_TOPK_SORT_MIN && n <= 0x7fffffffLL) { /* large batch: one radix sort (topk.cu) */
         const size_t need = cv_topk_sort_bytes(n);
         CU(grow(&ctx->d_topk_scratch, &ctx->cap_topk_scratch, need), "cudaMalloc(topk scratch)");
         CU(cv_launch_topk_sort(d_ll, n, K, ctx->d_topk_scratch, ctx->cap_topk_scratch, ctx->d_sel_ll,

@@ -41,6 +41,12 @@ size_t cv_topk_sort_bytes(long long n);
 /* merge of best-row blocks of several ranks: n <= 2048 rows of c doubles -> the k best, device buffers */
 cudaError_t cv_launch_merge_rows(const double *rows, int n, int c, int k, double *out, cudaStream_t stream);
 
+/* large n, K <= 1024: radix selection (topk.cu) */
+size_t cv_topk_select_bytes(void);
+bool cv_topk_select_fits(long long n, int K);
+cudaError_t cv_launch_topk_radix_select(const double *ll, long long n, int K, void *scratch, int n_sm,
+                                        double *out_ll, long long *out_idx, cudaStream_t stream);
+
 cudaError_t cv_launch_topk_sort(const double *ll, long long n, int K, void *scratch, size_t scratch_bytes,
                                 double *out_ll, long long *out_idx, cudaStream_t stream);
 
