@@ -528,12 +528,14 @@ static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, c
         CU(grow(&ctx->d_topk_scratch, &ctx->cap_topk_scratch, cv_topk_select_bytes()), "cudaMalloc(topk scratch)");
         CU(cv_launch_topk_radix_select(d_ll, n, K, ctx->d_topk_scratch, ctx->n_sm, ctx->d_sel_ll, ctx->d_sel_idx, s),
            "top-K selection");
+        ctx->last_launches += 1;
     } else if (n >= CVB_TOPK_SORT_MIN && n <= 0x7fffffffLL) { /* large batch: one radix sort (topk.cu) */
         const size_t need = cv_topk_sort_bytes(n);
         CU(grow(&ctx->d_topk_scratch, &ctx->cap_topk_scratch, need), "cudaMalloc(topk scratch)");
         CU(cv_launch_topk_sort(d_ll, n, K, ctx->d_topk_scratch, ctx->cap_topk_scratch, ctx->d_sel_ll,
                                ctx->d_sel_idx, s),
            "top-K sort");
+        ctx->last_launches += 12; /* keys, the passes of the radix sort, take */
     } else {
         int ctas = ctx->topk_ctas;
         if ((long long)ctas * 1024 > n) /* small inputs: fewer, fuller slices */
@@ -543,13 +545,14 @@ static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, c
         CU(cv_launch_topk(d_ll, n, K, ctx->d_cand_ll, ctx->d_cand_idx, ctas, ctx->d_sel_ll,
                           ctx->d_sel_idx, s),
            "cv_topk_select launch");
+        ctx->last_launches += 2;
     }
     const int np = ctx->desc.n_param;
     const bool r_dev = is_device_ptr(out_rows);
     double *dr = r_dev ? out_rows : ctx->d_rows;
     CU(cv_launch_gather_rows(lat, d_params, np, ctx->d_sel_ll, ctx->d_sel_idx, K, dr, s),
        "cv_gather_rows launch");
-    ctx->last_launches += 3;
+    ctx->last_launches += 1; /* the row gather */
     if (!r_dev) {
         CU(cudaMemcpyAsync(out_rows, dr, (size_t)K * (1 + np) * sizeof(double), cudaMemcpyDeviceToHost, s),
            "cudaMemcpyAsync(rows)");

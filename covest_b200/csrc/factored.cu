@@ -1580,7 +1580,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         CVF_CK(cudaGetLastError());
         CVF_CK(cudaMemcpyAsync(wk.h_header, pl.header, 6 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaStreamSynchronize(stream));
-        wk.launches += 12;
+        wk.launches += 28; /* K0, radix sort (10), heads, 6 scans (2 each), starts, counts, totals */
         return cudaSuccess;
     };
     /* ordering for the prefix kernel first: it also tells how many q-runs the batch has */

@@ -237,6 +237,12 @@ class LikelihoodContext:
                     'cvb_last_kernel_ms')
         return ms.value, n.value
 
+    def last_launches(self):
+        """Kernels launched by the most recent call (needs no timing)."""
+        n = ctypes.c_int()
+        self._check(self._lib.cvb_last_kernel_ms(self._ctx, None, ctypes.byref(n)), 'cvb_last_kernel_ms')
+        return n.value
+
     PATH_AUTO, PATH_PER_POINT, PATH_FACTORED, PATH_FACTORED_GEMM, PATH_FACTORED_PREFIX = 0, 1, 2, 3, 4
 
     def set_path(self, mode):
