@@ -921,6 +921,14 @@ struct __align__(16) CvfEvent {
 
 /* explicit shared-window accesses: the hot loop addresses its records, the logarithm table and the
  * transpose buffer with 32-bit addresses kept in registers */
+/* a shared-window address the compiler must keep in a register: without this it re-derives the
+ * window base (S2UR SR_CgaCtaId + ULEA) in front of every access of the hot loop */
+__device__ __forceinline__ unsigned int cvf_pin(unsigned int a)
+{
+    unsigned int r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
 __device__ __forceinline__ double2 cvf_lds128(unsigned int a)
 {
     double2 v;
@@ -1034,10 +1042,10 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                    warp * (CVF_PE * CVF_PEW); /* plane stride CVF_TBUF_DOUBLES */
     double *red_all = scratch + (size_t)blockIdx.x * (3 * CVF_PW * CVF_PB);
     double *red = red_all + warp * CVF_PB; /* plane stride CVF_PW * CVF_PB */
-    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
-    const unsigned int log_s = (unsigned int)__cvta_generic_to_shared(S.log_tab);
-    const unsigned int ev_s = (unsigned int)__cvta_generic_to_shared(S.ev);
-    const unsigned int tbuf_s = (unsigned int)__cvta_generic_to_shared(tbuf + lane); /* the lane's column */
+    const unsigned int ring_s = cvf_pin((unsigned int)__cvta_generic_to_shared(ring));
+    const unsigned int log_s = cvf_pin((unsigned int)__cvta_generic_to_shared(S.log_tab));
+    const unsigned int ev_s = cvf_pin((unsigned int)__cvta_generic_to_shared(S.ev));
+    const unsigned int tbuf_s = cvf_pin((unsigned int)__cvta_generic_to_shared(tbuf + lane)); /* the lane's column */
     for (int i = tid; i < 2 * CV_LOG_N; i += CVF_PT)
         S.log_tab[i] = log_tab[i];
     const int nslots = nsteps * CVF_NS;
@@ -1197,7 +1205,8 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     asm volatile("cp.async.wait_group %0;\n" ::"n"(CVF_PD - 1) : "memory");
 #pragma unroll
                     for (int i = 0; i < CVF_SL; i++) {
-                        const double v = ring[(slot_take * CVF_SL + i) * CVF_PT];
+                        double v;
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ring_s + (unsigned int)((slot_take * CVF_SL + i) * CVF_PT * 8)));
                         x[i] = live[i] ? v : 0.0;
                     }
                     slot_take = slot_take == CVF_PD - 1 ? 0 : slot_take + 1;
