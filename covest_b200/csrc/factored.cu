@@ -22,6 +22,9 @@
 
 #include "kdevice.h"
 
+#ifndef CVF_K1_NOSTORE
+#define CVF_K1_NOSTORE 0 /* development: 1 = K1 computes but does not write (timing experiment) */
+#endif
 #define CVF_M 128       /* points per tile of K2 */
 #define CVF_NS 64       /* bins (slots) per N-step of K2 */
 #define CVF_KC 16       /* copy numbers per K-chunk */
@@ -380,7 +383,8 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
         const double m0 = __ldg(slot_mult + s0), m1 = __ldg(slot_mult + s0 + 8);
         v.x = m0 != 0.0 ? cv_mul(v.x, m0) : 0.0;
         v.y = m1 != 0.0 ? cv_mul(v.y, m1) : 0.0;
-        *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
+        if (!CVF_K1_NOSTORE || v.x == 12345.678)
+            *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
     }
     __syncwarp();
 }
