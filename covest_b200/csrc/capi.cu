@@ -258,6 +258,16 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         }
         if ((e = upload(c, T.grp, &t.grp)) != cudaSuccess) break;
         if ((e = upload(c, T.slot_mult, &t.slot_mult)) != cudaSuccess) break;
+        {
+            std::vector<double> pr(T.slot_mult.size(), 0.0); /* the order of the profile kernel's stores */
+            for (size_t line = 0; line + 64 <= T.slot_mult.size(); line += 64)
+                for (int L = 0; L < 32; L++) {
+                    const size_t s0 = line + 16 * (L >> 3) + (L & 7);
+                    pr[line + 2 * L] = T.slot_mult[s0];
+                    pr[line + 2 * L + 1] = T.slot_mult[s0 + 8];
+                }
+            if ((e = upload(c, pr, &t.slot_mult_pair)) != cudaSuccess) break;
+        }
         if ((e = upload(c, T.slot_h, &t.slot_h)) != cudaSuccess) break;
         if ((e = upload(c, T.slot_bin, &t.slot_bin)) != cudaSuccess) break;
         if ((e = upload(c, T.copy_log_h, &t.copy_log_h)) != cudaSuccess) break;

@@ -57,6 +57,8 @@ struct CvTables {
     const double *grp;         /* CV_GD doubles per group */
     const double *slot_mult;   /* exp(-CV_SCALE_LOG) * (chain scale of the row) * j0! / (j0+i)!;
                                   0 marks a slot that is not in hist */
+    const double *slot_mult_pair; /* slot_mult as the profile kernel stores it: per 64-slot line the
+                                     32 pairs (slot 16 (L / 8) + L % 8, the same + 8), L = 0..31 */
     const double *slot_h;      /* count h_j */
     const int *slot_bin;       /* position of the bin in the caller's hist order, -1 = padding */
     const double *copy_log_h;  /* log(o), o = 0..max_bin, as a double-double (entry 0 unused) */

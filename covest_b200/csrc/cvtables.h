@@ -198,6 +198,7 @@ static inline CvTables cv_tables_view(const CvHostTables &T)
     CvTables v;
     v.grp = T.grp.data();
     v.slot_mult = T.slot_mult.data();
+    v.slot_mult_pair = nullptr; /* device only (capi.cu) */
     v.slot_h = T.slot_h.data();
     v.slot_bin = T.slot_bin.data();
     v.copy_log_h = T.copy_log_h.data();

@@ -356,7 +356,7 @@ __device__ __forceinline__ int cvf_find(const int *__restrict__ start, int n, in
  * groups swapped pairwise against bank conflicts) and leave as full 512-byte lines. */
 template <int NA>
 __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int nsteps,
-                                                  const double *__restrict__ slot_mult,
+                                                  const double *__restrict__ slot_mult /* pairs */,
                                                   double *__restrict__ Wg, double *stage, const double *acc)
 {
     const int r = lane >> 2, q = lane & 3;
@@ -379,10 +379,9 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
         double2 v = *reinterpret_cast<const double2 *>(stage + row * CV_W + 2 * chunk);
         /* the scale of the accumulators ends here: slot_mult of the pair's two slots (0 = the slot
          * is no bin of the histogram; its profile is an exact zero) */
-        const int s0 = (blk * (2 * NA) + ns) * CVF_NS + 16 * (lane >> 3) + (lane & 7);
-        const double m0 = __ldg(slot_mult + s0), m1 = __ldg(slot_mult + s0 + 8);
-        v.x = m0 != 0.0 ? cv_mul(v.x, m0) : 0.0;
-        v.y = m1 != 0.0 ? cv_mul(v.y, m1) : 0.0;
+        const double2 mm = __ldg(reinterpret_cast<const double2 *>(slot_mult) + (blk * (2 * NA) + ns) * 32 + lane);
+        v.x = cv_mul(v.x, mm.x); /* the accumulators are finite (that is what the scale is for): times 0 is 0 */
+        v.y = cv_mul(v.y, mm.y);
         if (!CVF_K1_NOSTORE || v.x == 12345.678)
             *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
     }
@@ -411,7 +410,7 @@ __device__ __forceinline__ void cvf_profile_item(int lane, const CvModelDesc &m,
                 for (int i = 0; i < 4 * NA; i++)
                     acc[i] = 0.0;
                 cv_w_fused<NA>(lane, G, cc * kpc, (cc + 1) * kpc, *M.fx, acc);
-                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, m.tab.slot_mult, Wg, stage, acc);
+                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, m.tab.slot_mult_pair, Wg, stage, acc);
             }
             __syncwarp();
         }
