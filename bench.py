@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 K_BEST = 64
 METRIC = 'loglik_point_bin_evals_per_sec'
 UNIT = 'point*bin/s'
-POINTS_PER_RANK = {'cfg3': 1000000, 'cfg5': 12500000}
+POINTS_PER_RANK = {'cfg3': 1000000, 'cfg4': 100000, 'cfg5': 12500000}
 
 
 def workload_axes(name, world):
@@ -47,6 +47,8 @@ def workload_axes(name, world):
     theta = workload.CONFIGS[name]['theta']
     if name == 'cfg3':
         return workload.lattice_axes(theta, n_c=40 * world, n_e=25)
+    if name == 'cfg4':  # k = 31, r = 150, 5000 bins, coverage 200: 10^5 points per rank
+        return workload.lattice_axes(theta, n_c=10 * world, n_e=10)
     return workload.lattice_axes(theta, n_c=25 * world, n_e=50, n_q1=10, n_q2=10, n_q=100)
 
 
@@ -219,8 +221,10 @@ def committed_traffic(kernel, workload_name, n_points):
 
 def workload_config(name, world, n_bins, axes):
     lens = [len(a) for a in axes]
-    return {'workload': '%s: repeats model k=21 r=100, lattice %s = %d points x %d bins, %d per rank' % (
-        name, 'x'.join(map(str, lens)), int(np.prod(lens)), n_bins, int(np.prod(lens)) // world),
+    from covest_b200 import workload
+    c = workload.CONFIGS[name]
+    return {'workload': '%s: repeats model k=%d r=%d, lattice %s = %d points x %d bins, %d per rank' % (
+        name, c['k'], c['r'], 'x'.join(map(str, lens)), int(np.prod(lens)), n_bins, int(np.prod(lens)) // world),
         'bins': n_bins, 'points_per_rank': int(np.prod(lens)) // world, 'lattice': lens,
         'max_error': 8, 'k_best': K_BEST,
         'sharding': 'whole (coverage, error_rate) groups of the lattice dealt round-robin: rank r takes groups r, r+N, ...',
@@ -402,7 +406,18 @@ def run_b200(args, rank, world, local_rank):
                          'flop_per_launch': flop_launch, 'mean_terms_per_point': float(terms.mean()),
                          'peak_source': 'register-resident DFMA chain measured in this run (cvb_fp64_peak); '
                                         'DMMA m8n8k4 chain: %.2f TFLOP/s' % peak_dmma,
-                         'kernel_share_of_step': dom_ms * args.steps / total_ms if world == 1 else None},
+                         'kernel_share_of_step': dom_ms * args.steps / total_ms if world == 1 else None,
+                         # SURVEY.md section 8(d) for comparison: the work of the reference's own
+                         # formulation of the same batch (an exp per mixture term and bin: 40 flop per
+                         # (term, bin) + 64 per bin -- "primary"; a recurrence, 4 flop per (term, bin)
+                         # + 64 per bin -- "secondary") over the time of the whole evaluation here
+                         'survey_accounting': {
+                             'primary_flop': float(n_bins * (40.0 * terms.sum() + 64.0 * len(terms))),
+                             'secondary_flop': float(n_bins * (4.0 * terms.sum() + 64.0 * len(terms))),
+                             'primary_equivalent_tflops': float(n_bins * (40.0 * terms.sum() + 64.0 * len(terms))) / (km * 1e-3) / 1e12,
+                             'secondary_equivalent_tflops': float(n_bins * (4.0 * terms.sum() + 64.0 * len(terms))) / (km * 1e-3) / 1e12,
+                             'gemm_formulation_flop': work['gemm_flop'] if factored else None,
+                             'note': 'equivalent rates exceed the FP64 peak because the factored formulations do less work for the same values'}},
             'phases': ({'path': 'factored', 'kernel': info['kernel'], 'groups': info['groups'],
                         'q_runs': info['q_runs'], 'tiles': info['tiles'],
                         'profile_workspace_bytes': 8 * info['profile_doubles'],
@@ -441,7 +456,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg5'])
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg4', 'cfg5'])
     ap.add_argument('--points', type=int, default=0, help='cap the points per rank (development)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--path', default='auto', choices=['auto', 'prefix', 'gemm', 'direct'],

@@ -1715,7 +1715,9 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
                 CVF_CK(cudaEventRecord(wk.ev[2], stream));
             int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;
             if (prefix) {
-                const int per_sm = std::max(1, std::min(4, (int)((size_t)smem_max / (kp_smem + 1024))));
+                int per_sm = std::max(1, std::min(4, (int)((size_t)smem_max / (kp_smem + 1024))));
+                if (const char *lim = getenv("COVEST_B200_PREFIX_CTAS")) /* development: CTAs per SM */
+                    per_sm = std::max(1, std::min(per_sm, atoi(lim)));
                 grid = tiles < per_sm * n_sm ? tiles : per_sm * n_sm;
                 kp<<<grid, CVF_PT, kp_smem, stream>>>(m, lat, params, clip, pl, tile0, tiles, wk.W, w0, slot_mh,
                                                        log_tab, nsteps, out_ll, wk.d_counters + 1, wk.d_scratch);
