@@ -153,13 +153,33 @@ def covest_end_to_end(cores):
                 return orc.ref_loglik_batch(m, pts, processes=min(cores, len(pts)))
             return m.loglik_batch(pts, mode=orc.FAITHFUL, threads=cores)
 
+    def flow_device(**kw):  # the reference's experiment invocations (tools/run_covest.py: -sp 16; -g)
+        import random
+        random.seed(7)
+        t0 = time.perf_counter()
+        h2, tail, sf, gc, ge = process_histogram(hist, g['k'], g['r'], sample_factor=1)
+        model = RepeatsModel(g['k'], g['r'], h2, tail, max_error=8)
+        guess = list(model.defaults)
+        guess[:2] = gc, ge
+        est = CoverageEstimator(model)
+        x, ok = est.compute_coverage(guess, **kw)
+        return time.perf_counter() - t0, float(x[0]), est.evaluations
+
     flow(RepeatsModel)  # warm-up: context creation, first launches
     dev_s, dev_x, dev_n = flow(RepeatsModel)
     cpu_s, cpu_x, cpu_n = flow(CpuRepeats)
+    extra = {}
+    try:
+        s16, c16, n16 = flow_device(starting_points=16)
+        sg, cg, ng = flow_device(starting_points=1, use_grid_search=True)
+        extra = {'device_multi_start_16': {'seconds': s16, 'coverage': c16, 'evaluations': n16},
+                 'device_grid_search': {'seconds': sg, 'coverage': cg, 'evaluations': ng}}
+    except Exception as exc:
+        extra = {'extra_error': repr(exc)}
     return {'workload': 'cfg2: repeats model k=21 r=100, %d bins, single start, L-BFGS-B' % len(hist),
             'device_s': dev_s, 'device_coverage': dev_x[0], 'device_evaluations': dev_n,
             'cpu_s': cpu_s, 'cpu_coverage': cpu_x[0], 'cpu_evaluations': cpu_n, 'cpu_cores': cores,
-            'cpu_kind': 'reference' if orc.ref_module() is not None else 'port'}
+            'cpu_kind': 'reference' if orc.ref_module() is not None else 'port', **extra}
 
 
 def reference_histogram(name):

@@ -108,3 +108,32 @@ def test_a_seeded_sample_against_the_oracle(cfg3):
     inside = np.isfinite(want)
     assert inside.sum() >= 30
     assert rel_err_ll(ll[pick][inside], want[inside]).max() <= LL_RTOL
+
+
+def test_cfg5_shape_two_full_passes():
+    """BASELINE.json configs[4] shape on one rank, reduced in points: 2000 dense bins (two full
+    passes of the prefix kernel over the bins), 20 q-runs per (coverage, error rate)."""
+    cfg = workload.CONFIGS['cfg5']
+    hist = workload.synthetic_histogram('cfg5')
+    assert len(hist) == 2000
+    model = RepeatsModel(cfg['k'], cfg['r'], hist, 0, max_error=8)
+    axes = [np.geomspace(15, 60, 4), np.geomspace(.01, .08, 3), np.linspace(.3, 1, 5), np.linspace(0, 1, 5),
+            np.linspace(.05, 1, 20)]
+    pts = workload.lattice_points(axes)
+    try:
+        ctx = model.device_context
+        ll = ctx.loglik(pts)
+        info = ctx.last_path_info()
+        assert info['kernel'] == 'cvf_prefix_kernel' and info['groups'] == 12 and info['q_runs'] == 240, info
+        ctx.set_path(ctx.PATH_PER_POINT)
+        direct = ctx.loglik(pts)
+        ctx.set_path(ctx.PATH_FACTORED_GEMM)
+        gemm = ctx.loglik(pts)
+    finally:
+        model.close()
+    assert rel_err_ll(ll, gemm).max() <= PATH_RTOL
+    assert rel_err_ll(ll, direct).max() <= PATH_RTOL
+    m = orc.Model('repeats', cfg['k'], cfg['r'], {int(j): int(v) for j, v in hist.items()}, 0, max_error=8)
+    pick = np.nonzero(pts[:, 4] >= 0.4)[0][::97][:12]
+    want = m.loglik_batch(pts[pick], threads=8)
+    assert rel_err_ll(ll[pick], want).max() <= LL_RTOL
