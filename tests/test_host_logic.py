@@ -303,3 +303,26 @@ def test_cli_flags_are_the_reference_flags():
     d = p.parse_args(['x.hist'])
     assert (d.model, d.kmer_size, d.read_length, d.starting_points, d.grid, d.trim, d.sample_factor) == \
         ('basic', 21, 100, 1, False, None, None)
+
+
+def test_workload_flop_accounting_of_the_factored_paths():
+    """bench.py's roofline numerators on a lattice small enough to count by
+    hand: copies per point from the cut-off, groups by (c, e), q-runs by (c, e, q)."""
+    from covest_b200 import workload
+    from covest_b200.models import RepeatsModel
+    hist = {j: 10 for j in range(1, 101)}
+    model = RepeatsModel(21, 100, hist, 0, max_error=8)
+    axes = [np.array([10.0, 20.0]), np.array([0.02]), np.array([0.5, 1.0]), np.array([0.0, 0.5]),
+            np.array([0.2, 0.6])]
+    pts = workload.lattice_points(axes)
+    assert pts.shape == (16, 5)
+    copies = np.maximum(workload.copy_cutoff(pts, max(hist), model.threshold) - 1, 0)
+    # q1 = 1 or q2 = 0 with ... : the cut-off follows models.py:185-191
+    assert copies[(pts[:, 2] == 1.0)].max() == 1            # b(2) = 0 <= threshold: only copy 1
+    w = workload.factored_flop(model, pts, n_bins=100, counted_bins=100)
+    assert w['groups'] == 2 and w['q_runs'] == 4
+    assert w['gemm_flop'] == float(np.sum(2.0 * 100 * copies + 64.0 * 100))
+    per_run_max = [copies[(pts[:, 0] == c) & (pts[:, 4] == q)].max() for c in (10.0, 20.0) for q in (0.2, 0.6)]
+    assert w['prefix_flop'] == 16 * (6.0 * 100 + 64.0 * 100) + 2.0 * 100 * sum(max(m - 2, 0) for m in per_run_max)
+    assert w['profile_flop'] == 2.0 * 8 * 100 * sum(copies[pts[:, 0] == c].max() for c in (10.0, 20.0))
+    model.close()
