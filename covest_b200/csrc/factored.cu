@@ -953,7 +953,7 @@ struct CvfPrefixSmem {
     double log_tab[2 * CV_LOG_N];
     /* the points of the batch by ascending cut-off (the schedule), 32 bytes each: weights of
      * copy 1, copy 2 and of the running sum; batch position | run << 16; copies = O_thr - 1 */
-    CvfEvent ev[CVF_PB + 1];
+    CvfEvent ev[CVF_PB + 2];
     int need[CVF_PB];  /* by batch position: copies of the point */
     double base[CVF_NQ];
     int seg[CVF_NQ + 1]; /* batch positions where its q-runs start */
@@ -1008,6 +1008,27 @@ __device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
     const double p = cv_fma(r4, c2, ab);
     const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.fdf473de6af28p-22)); /* ln 2 - 0x1.62e42p-1 */
     return cv_add(cv_add(hi_part, r), lo); /* hi_part + r does not wait for the polynomial */
+}
+
+/* the fast path of cvf_safe_log alone: x positive, normal, finite */
+__device__ __forceinline__ double cvf_log_fast(double x, unsigned int tab_s)
+{
+    const int hi = __double2hiint(x);
+    const int t = hi - (int)(CV_LOG_OFF >> 32);
+    const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
+    const double2 c = cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4)));
+    const double r = cv_fma(z, c.x, -1.0);
+    const double kd = (double)(t >> 20);
+    const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y);
+    const double r2 = cv_mul(r, r);
+    const double a = cv_fma(r, 1.0 / 3.0, -0.5);
+    const double b = cv_fma(r, 0x1.9999ap-3, -0.25);
+    const double c2 = cv_fma(r, 0x1.24925p-3, -0x1.55555p-3);
+    const double r4 = cv_mul(r2, r2);
+    const double ab = cv_fma(r2, b, a);
+    const double p = cv_fma(r4, c2, ab);
+    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.fdf473de6af28p-22));
+    return cv_add(cv_add(hi_part, r), lo);
 }
 
 /* number of entries of the ascending a[0..n) that are < x (strict) resp. <= x */
@@ -1147,12 +1168,18 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     S.ev[rank] = e;
                 }
             }
-            if (tid == 0) { /* read ahead by the loop below, never used */
+            if (tid < 2) { /* read ahead by the loop below, never used */
                 CvfEvent e;
                 e.q1 = e.two = e.many = 0.0;
                 e.info = e.need = 0;
-                S.ev[npts] = e;
+                S.ev[npts + tid] = e;
             }
+            __syncthreads();
+            /* a point whose successor in the schedule has the same cut-off can be finished together
+             * with it (no copy to add in between): bit 30 of its record */
+            for (int t = tid; t + 1 < npts; t += CVF_PT)
+                if (S.ev[t].need == S.ev[t + 1].need)
+                    S.ev[t].info |= 1 << 30;
             __syncthreads();
 
             /* ---- passes over the slots ---- */
@@ -1327,13 +1354,126 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                                 w[s] = cv_mul(w[s], base[s]);
                             }
                     }
+                    if (info & (1 << 30)) {
+                        /* two points of equal cut-off at once: their dependent chains (combination,
+                         * logarithm) run side by side, the bookkeeping is shared */
+                        double pa[CVF_SL], pb[CVF_SL];
+#pragma unroll
+                        for (int i = 0; i < CVF_SL; i++) {
+                            pa[i] = cv_fma(two, P2[i], cv_mul(q1, P1[i]));
+                            pb[i] = cv_fma(qt_next.y, P2[i], cv_mul(qt_next.x, P1[i]));
+                        }
+                        switch ((info >> 16) & 3) {
+#define CVF_CASE(s_)                                                                                   \
+    case s_:                                                                                           \
+        _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) pa[i] = cv_fma(many, R[s_][i], pa[i]);      \
+        break;
+                            CVF_CASE(0)
+                            CVF_CASE(1)
+                            CVF_CASE(2)
+                            CVF_CASE(3)
+#undef CVF_CASE
+                        }
+                        switch ((info_next >> 16) & 3) {
+#define CVF_CASE(s_)                                                                                   \
+    case s_:                                                                                           \
+        _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) pb[i] = cv_fma(many_next, R[s_][i], pb[i]); \
+        break;
+                            CVF_CASE(0)
+                            CVF_CASE(1)
+                            CVF_CASE(2)
+                            CVF_CASE(3)
+#undef CVF_CASE
+                        }
+                        const int pt_a = info & 0xffff, pt_b = info_next & 0xffff;
+                        /* the record after the pair becomes the current one */
+                        ev_a += (unsigned int)sizeof(CvfEvent);
+                        {
+                            const double2 qt = cvf_lds128(ev_a);
+                            q1 = qt.x;
+                            two = qt.y;
+                            cvf_lds_event(ev_a, many, info, need);
+                        }
+                        k++;
+                        double ma = 0.0, mb = 0.0, mla = 0.0, mlb = 0.0; /* models.py:103: the mass */
+#pragma unroll
+                        for (int i = 0; i < CVF_SL; i++) {
+                            if (MASS) {
+                                cvf_two_sum_acc(ma, mla, pa[i]);
+                                cvf_two_sum_acc(mb, mlb, pb[i]);
+                            } else {
+                                ma = cv_add(ma, pa[i]);
+                                mb = cv_add(mb, pb[i]);
+                            }
+                        }
+                        double sa = 0.0, sb = 0.0;
+                        if (log_mask == 1) { /* the usual case: only the warp's first half-line has counts */
+                            const unsigned int ca = (unsigned int)(__double2hiint(pa[0]) - 0x00100000),
+                                               cb = (unsigned int)(__double2hiint(pb[0]) - 0x00100000);
+                            double la, lb;
+                            if (ca < 0x7fe00000u && cb < 0x7fe00000u) { /* both positive, normal, finite */
+                                la = cvf_log_fast(pa[0], log_s);
+                                lb = cvf_log_fast(pb[0], log_s);
+                            } else {
+                                la = cvf_safe_log(pa[0], log_s);
+                                lb = cvf_safe_log(pb[0], log_s);
+                            }
+                            sa = cv_mul(hcnt[0], la);
+                            sb = cv_mul(hcnt[0], lb);
+                            if (hcnt[0] == 0.0) /* models.py:106 `if h` */
+                                sa = sb = 0.0;
+                        } else if (log_mask) {
+#pragma unroll
+                            for (int i = 0; i < CVF_SL; i++)
+                                if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
+                                    const unsigned int ca = (unsigned int)(__double2hiint(pa[i]) - 0x00100000),
+                                                       cb = (unsigned int)(__double2hiint(pb[i]) - 0x00100000);
+                                    double la, lb;
+                                    if (ca < 0x7fe00000u && cb < 0x7fe00000u) {
+                                        la = cvf_log_fast(pa[i], log_s);
+                                        lb = cvf_log_fast(pb[i], log_s);
+                                    } else {
+                                        la = cvf_safe_log(pa[i], log_s);
+                                        lb = cvf_safe_log(pb[i], log_s);
+                                    }
+                                    double ta = cv_mul(hcnt[i], la), tb = cv_mul(hcnt[i], lb);
+                                    if (hcnt[i] == 0.0)
+                                        ta = tb = 0.0;
+                                    sa = cv_add(sa, ta);
+                                    sb = cv_add(sb, tb);
+                                }
+                        }
+                        if (pending == CVF_PE - 1) { /* no room for two rows */
+                            flush();
+                            tb_a = tbuf_s;
+                        }
+                        cvf_sts64(tb_a, sa);
+                        cvf_sts64(tb_a + CVF_TBUF_DOUBLES * 8, ma);
+                        cvf_sts64(tb_a + CVF_PEW * 8, sb);
+                        cvf_sts64(tb_a + CVF_PEW * 8 + CVF_TBUF_DOUBLES * 8, mb);
+                        if (MASS) {
+                            cvf_sts64(tb_a + 2 * CVF_TBUF_DOUBLES * 8, mla);
+                            cvf_sts64(tb_a + CVF_PEW * 8 + 2 * CVF_TBUF_DOUBLES * 8, mlb);
+                        }
+                        tb_a += 2 * CVF_PEW * 8;
+                        if (lane == pending)
+                            mypt = pt_a;
+                        if (lane == pending + 1)
+                            mypt = pt_b;
+                        pending += 2;
+                        if (pending == CVF_PE) {
+                            flush();
+                            tb_a = tbuf_s;
+                        }
+                        continue;
+                    }
                     /* the three-term combination for the thread's slots, models.py:235-241 */
                     const int pt = info & 0xffff;
                     double p[CVF_SL];
 #pragma unroll
                     for (int i = 0; i < CVF_SL; i++)
                         p[i] = cv_fma(two, P2[i], cv_mul(q1, P1[i]));
-                    switch (info >> 16) {
+                    switch ((info >> 16) & 3) {
 #define CVF_CASE(s_)                                                                                   \
     case s_:                                                                                           \
         _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) p[i] = cv_fma(many, R[s_][i], p[i]);        \
