@@ -1175,12 +1175,6 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                 S.ev[npts + tid] = e;
             }
             __syncthreads();
-            /* a point whose successor in the schedule has the same cut-off can be finished together
-             * with it (no copy to add in between): bit 30 of its record */
-            for (int t = tid; t + 1 < npts; t += CVF_PT)
-                if (S.ev[t].need == S.ev[t + 1].need)
-                    S.ev[t].info |= 1 << 30;
-            __syncthreads();
 
             /* ---- passes over the slots ---- */
             for (int pass0 = 0; pass0 < nslots; pass0 += CVF_PASS_SLOTS) {
@@ -1333,6 +1327,20 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     cvf_lds_event(ev_a, many, info, need);
                 }
                 unsigned int tb_a = tbuf_s; /* row `pending` of the transpose buffer */
+                auto step = [&]() { /* one more copy into the running sums (o_done >= 3 afterwards) */
+                    o_done++;
+                    double x[CVF_SL];
+                    take(x);
+                    request();
+#pragma unroll
+                    for (int s = 0; s < CVF_NQ; s++)
+                        if (o_done <= last_need[s]) { /* runs whose points are all out need no more copies */
+#pragma unroll
+                            for (int i = 0; i < CVF_SL; i++)
+                                R[s][i] = cv_fma(w[s], x[i], R[s][i]);
+                            w[s] = cv_mul(w[s], base[s]);
+                        }
+                };
                 for (int k = 0; k < npts; k++) {
                     /* the next point's record travels while this one is worked on */
                     ev_a += (unsigned int)sizeof(CvfEvent);
@@ -1340,29 +1348,16 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     double many_next;
                     int info_next, need_next;
                     cvf_lds_event(ev_a, many_next, info_next, need_next);
-                    while (o_done < need) { /* one more copy into the running sums (o_done >= 3) */
-                        o_done++;
-                        double x[CVF_SL];
-                        take(x);
-                        request();
-#pragma unroll
-                        for (int s = 0; s < CVF_NQ; s++)
-                            if (o_done <= last_need[s]) { /* runs whose points are all out need no more copies */
-#pragma unroll
-                                for (int i = 0; i < CVF_SL; i++)
-                                    R[s][i] = cv_fma(w[s], x[i], R[s][i]);
-                                w[s] = cv_mul(w[s], base[s]);
-                            }
-                    }
-                    if (info & (1 << 30)) {
-                        /* two points of equal cut-off at once: their dependent chains (combination,
-                         * logarithm) run side by side, the bookkeeping is shared */
+                    while (o_done < need)
+                        step();
+                    if (k + 1 < npts) {
+                        /* two points at once: this one is combined now, the next one after the copies
+                         * it still needs; then their logarithms run side by side (two dependent
+                         * chains instead of one) and the bookkeeping is shared */
                         double pa[CVF_SL], pb[CVF_SL];
 #pragma unroll
-                        for (int i = 0; i < CVF_SL; i++) {
+                        for (int i = 0; i < CVF_SL; i++)
                             pa[i] = cv_fma(two, P2[i], cv_mul(q1, P1[i]));
-                            pb[i] = cv_fma(qt_next.y, P2[i], cv_mul(qt_next.x, P1[i]));
-                        }
                         switch ((info >> 16) & 3) {
 #define CVF_CASE(s_)                                                                                   \
     case s_:                                                                                           \
@@ -1374,6 +1369,11 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             CVF_CASE(3)
 #undef CVF_CASE
                         }
+                        while (o_done < need_next)
+                            step();
+#pragma unroll
+                        for (int i = 0; i < CVF_SL; i++)
+                            pb[i] = cv_fma(qt_next.y, P2[i], cv_mul(qt_next.x, P1[i]));
                         switch ((info_next >> 16) & 3) {
 #define CVF_CASE(s_)                                                                                   \
     case s_:                                                                                           \
