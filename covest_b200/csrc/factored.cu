@@ -327,16 +327,19 @@ __global__ void __launch_bounds__(128) cvf_tile_table(int n_groups, CvfPlan pl)
     }
 }
 
-/* largest g in [0, n) with start[g] <= x (start ascending, start[0] <= x) */
-__device__ __forceinline__ int cvf_find(const int *__restrict__ start, int n, int x)
+/* largest g in [0, n) with start[g] <= x (start ascending, start[0] <= x), for a whole warp at once:
+ * 32 probes per round, two or three dependent loads instead of log2(n) */
+__device__ __forceinline__ int cvf_find_warp(const int *__restrict__ start, int n, int x, int lane)
 {
     int lo = 0, hi = n;
     while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (start[mid] <= x)
-            lo = mid;
-        else
-            hi = mid;
+        const int step = (hi - lo + 31) >> 5;
+        const int p = lo + (lane + 1) * step;
+        const bool ok = p < hi && __ldg(start + p) <= x;
+        const int cnt = __popc(__ballot_sync(CV_FULL_MASK, ok)); /* probes ascend: the first cnt are <= x */
+        const int nlo = lo + cnt * step;
+        hi = min(nlo + step, hi);
+        lo = nlo;
     }
     return lo;
 }
@@ -449,7 +452,7 @@ cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
         if (it >= n_items)
             break;
         const int item = first_item + (int)it;
-        const int g = cvf_find(pl.item_start, n_groups, item);
+        const int g = cvf_find_warp(pl.item_start, n_groups, item, lane);
         const int kchunk = item - pl.item_start[g];
         const int a = pl.g_start[g];
         const int omax = pl.g_omax[g] - 1;
