@@ -160,6 +160,14 @@ def test_topk_of_a_large_batch_equals_the_selection_order():
         allbad = np.full(40000, np.nan)
         rows = ctx.topk(allbad, pts[:40000], 4)
         assert np.all(np.isneginf(rows[:, 0])) and np.array_equal(rows[:, 1:], pts[:4])
+        # the radix selection at its largest K, the radix sort beyond it, and a constant batch
+        # (every key equal: the index bits of the 96-bit keys decide)
+        for k in (1024, 2000):
+            rows = ctx.topk(ll, pts, k)
+            assert np.array_equal(rows[:, 0], key[order[:k]]) and np.array_equal(rows[:, 1:], pts[order[:k]])
+        same = np.full(70000, -3.5)
+        rows = ctx.topk(same, pts[:70000], 100)
+        assert np.all(rows[:, 0] == -3.5) and np.array_equal(rows[:, 1:], pts[:100])
 
 
 def test_full_size_properties_cfg3():
