@@ -53,28 +53,68 @@ def workload_axes(name, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons of one GPU while the timed region runs."""
+    """SM clock and throttle reasons of one GPU while the timed region runs: NVML every 5 ms
+    (pynvml), or nvidia-smi every 200 ms when NVML cannot be loaded."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.source = None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            bits = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                    'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                    'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                    'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+            get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.source = 'nvml'
+            while not self._stop.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(h))
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self._stop.wait(0.005)
+        finally:
+            nv.nvmlShutdown()
+
+    def _run_smi(self):
+        self.source = 'nvidia-smi'
         while not self._stop.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True,
                                      text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
+                r = [x.strip() for x in out.split(',')] if out else []
+                if r and r[0].replace('.', '').isdigit():
+                    self.sm.append(float(r[0]))
+                if len(r) > 1 and r[1].replace('.', '').isdigit():
+                    self.mx.append(float(r[1]))
+                for i, name in enumerate(self.NAMES):
+                    if len(r) > 3 + i and r[3 + i].lower().startswith('active'):
+                        self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(0.2)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            if not self.sm:
+                self._run_smi()
 
     def __enter__(self):
         self._t.start()
@@ -85,13 +125,10 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names)
-                   if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None,
+                'sm_max_mhz': max(self.mx) if self.mx else None,
+                'reasons': [n for n in self.NAMES if n in self.reasons], 'samples': len(self.sm),
+                'source': self.source}
 
 
 # ---------------------------------------------------------------------------------------------
