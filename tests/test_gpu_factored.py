@@ -221,3 +221,40 @@ def test_prefix_kernel_long_runs_and_many_runs():
         _force(ctx, 'prefix')
         sub = ctx.loglik(pts[pick])
     assert rel_err_ll(sub, ref).max() <= LL_RTOL
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_prefix_kernel_on_random_batch_structures(seed):
+    """Random numbers of (coverage, error rate) groups, q-runs per group and points per run
+    (singletons up to runs that span several batches and tiles), edge values of q1 / q2 / q mixed
+    in, rows shuffled: the prefix kernel against the per-point kernel on the same rows."""
+    case = load_case('cfg2_repeats' if seed % 2 else 'cfg3_repeats_dense1000')
+    hist = case_hist(case)
+    if seed % 2 == 0:
+        hist = {j: h for j, h in hist.items() if j <= 300 + 100 * seed}
+    m = orc.Model('repeats', case['k'], case['r'], hist, case['tail'] if seed % 3 else 7.0, max_error=8)
+    rng = np.random.default_rng(1000 + seed)
+    rows = []
+    for _ in range(int(rng.integers(1, 9))):
+        c, e = 30 * 3 ** rng.uniform(-1, 1), float(np.exp(rng.uniform(np.log(2e-3), np.log(.3))))
+        for _ in range(int(rng.integers(1, 13))):
+            q = float(rng.choice([0.0, 1.0, rng.uniform(.03, 1), rng.uniform(.2, 1)], p=[.05, .1, .35, .5]))
+            n = int(rng.choice([1, 2, 3, int(rng.integers(4, 80)), int(rng.integers(80, 700)),
+                                int(rng.integers(2000, 2600))], p=[.15, .1, .1, .4, .2, .05]))
+            q1 = rng.choice([1.0, .3], size=n, p=[.5, .5]) * (rng.uniform(0, 1, n) < .1) + \
+                rng.uniform(.3, 1, n) * 1.0
+            q1 = np.clip(q1, .3, 1.0)
+            q2 = np.where(rng.uniform(0, 1, n) < .1, rng.choice([0.0, 1.0], size=n), rng.uniform(0, 1, n))
+            rows.append(np.column_stack([np.full(n, c), np.full(n, e), q1, q2, np.full(n, q)]))
+    pts = np.vstack(rows)
+    pts = pts[rng.permutation(len(pts))]
+    with context_for(m) as ctx:
+        _force(ctx, 'prefix')
+        got = ctx.loglik(pts)
+        assert _ran(ctx, 'prefix')
+        ctx.set_path(ctx.PATH_PER_POINT)
+        want = ctx.loglik(pts)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    rel = rel_err_ll(got, want)
+    assert rel.max() <= PATH_RTOL, (seed, len(pts), int(rel.argmax()), pts[int(rel.argmax())],
+                                    got[int(rel.argmax())], want[int(rel.argmax())])
