@@ -2,7 +2,7 @@
  * factored.cu -- batched evaluation of the repeats model as profiles x copy weights (factored.h).
  *
  *   cvf_point_keys      K0: per point clip, cut-off O_thr, sort key
- *   cvf_heads / cvf_group_starts / cvf_group_counts / cvf_totals   group tables from the sorted keys
+ *   cvf_heads / cvf_group_starts / cvf_group_counts / cvf_group_scan   group tables from the sorted keys
  *   cvf_profile_kernel  K1: one warp per (group, 16 copy numbers): profiles over all bins
  *   cvf_gemm_kernel     K2: one CTA per tile of 128 points: FP64 tensor-core GEMM + epilogue
  *
@@ -14,6 +14,7 @@
 #include "factored.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -39,6 +40,7 @@ struct CvfPlan {
     const unsigned int *idx_sorted;
     int *othr;       /* by ORIGINAL point index */
     int *head, *gid; /* by sorted position */
+    unsigned long long *flags2; /* by sorted position: head | head2 << 32, then their running sums (gid | rid << 32) */
     int *head2, *rid; /* q-runs: points of a group that also share q (prefix path); rid = running count */
     int *g_omax;      /* [n + 1] per group: the largest O_thr of its points */
     int *r_start;     /* [n + 1] sorted position of the first point of a q-run */
@@ -191,6 +193,7 @@ cvf_heads(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLatti
     }
     pl.head[i] = h;
     pl.head2[i] = h2;
+    pl.flags2[i] = (unsigned long long)h | ((unsigned long long)h2 << 32);
 }
 
 __global__ void __launch_bounds__(256) cvf_group_starts(long long n, CvfPlan pl)
@@ -198,22 +201,25 @@ __global__ void __launch_bounds__(256) cvf_group_starts(long long n, CvfPlan pl)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
+    const unsigned long long both = pl.flags2[i]; /* running sums of head and head2 in one scan */
+    const int gid = (int)(both & 0xffffffffULL), rid = (int)(both >> 32);
+    pl.rid[i] = rid;
     if (pl.head[i]) {
-        pl.g_start[pl.gid[i] - 1] = (int)i;
-        pl.g_rfirst[pl.gid[i] - 1] = pl.rid[i] - 1;
+        pl.g_start[gid - 1] = (int)i;
+        pl.g_rfirst[gid - 1] = rid - 1;
     }
     if (pl.head2[i])
-        pl.r_start[pl.rid[i] - 1] = (int)i;
+        pl.r_start[rid - 1] = (int)i;
     if (i == n - 1) {
-        pl.header[0] = pl.gid[i];
-        pl.header[5] = pl.rid[i];
-        pl.g_start[pl.gid[i]] = (int)n;
-        pl.g_rfirst[pl.gid[i]] = pl.rid[i];
-        pl.r_start[pl.rid[i]] = (int)n;
+        pl.header[0] = gid;
+        pl.header[5] = rid;
+        pl.g_start[gid] = (int)n;
+        pl.g_rfirst[gid] = rid;
+        pl.r_start[rid] = (int)n;
     }
     /* cut-offs ascend inside a q-run: its last point holds the run's maximum */
     if (i == n - 1 || pl.head2[i + 1])
-        atomicMax(pl.g_omax + (pl.gid[i] - 1), pl.othr[pl.idx_sorted[i]]);
+        atomicMax(pl.g_omax + (gid - 1), pl.othr[pl.idx_sorted[i]]);
 }
 
 /* Tiles of the prefix kernel of group g: up to CVF_PNQ consecutive whole q-runs with at most
@@ -274,13 +280,47 @@ __global__ void __launch_bounds__(256) cvf_group_counts(long long n, int slots_p
     pl.a_start[g] = achunks;
 }
 
-__global__ void cvf_totals(CvfPlan pl)
+/* The exclusive prefix sums of the four per-group counts (tiles, items, profile doubles, weight
+ * chunks) over the n_groups + 1 entries that exist -- the host does not know n_groups yet, a scan
+ * per array over all n + 1 slots costs eight launches -- and the totals into the header.  One CTA,
+ * 1024 groups per round. */
+__global__ void __launch_bounds__(1024) cvf_group_scan(CvfPlan pl)
 {
-    const long long ng = pl.header[0];
-    pl.header[1] = pl.tile_start[ng];
-    pl.header[2] = pl.item_start[ng];
-    pl.header[3] = pl.w_off[ng];
-    pl.header[4] = pl.a_start[ng];
+    typedef cub::BlockScan<long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int ng = (int)pl.header[0];
+    long long run_t = 0, run_i = 0, run_w = 0, run_a = 0;
+    for (int g0 = 0; g0 <= ng; g0 += 1024) {
+        const int g = g0 + threadIdx.x;
+        const bool in = g <= ng;
+        const long long t = in ? pl.tile_start[g] : 0, it = in ? pl.item_start[g] : 0, w = in ? pl.w_off[g] : 0,
+                        a = in ? pl.a_start[g] : 0;
+        long long et, ei, ew, ea, tt, ti, tw, ta;
+        Scan(tmp).ExclusiveSum(t, et, tt);
+        __syncthreads();
+        Scan(tmp).ExclusiveSum(it, ei, ti);
+        __syncthreads();
+        Scan(tmp).ExclusiveSum(w, ew, tw);
+        __syncthreads();
+        Scan(tmp).ExclusiveSum(a, ea, ta);
+        __syncthreads();
+        if (in) {
+            pl.tile_start[g] = (int)(run_t + et);
+            pl.item_start[g] = (int)(run_i + ei);
+            pl.w_off[g] = run_w + ew;
+            pl.a_start[g] = (int)(run_a + ea);
+        }
+        run_t += tt;
+        run_i += ti;
+        run_w += tw;
+        run_a += ta;
+    }
+    if (threadIdx.x == 0) { /* entry ng of the counts is 0: the exclusive sums there are the totals */
+        pl.header[1] = run_t;
+        pl.header[2] = run_i;
+        pl.header[3] = run_w;
+        pl.header[4] = run_a;
+    }
 }
 
 /* one thread per group: the records of its tiles */
@@ -1611,7 +1651,8 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
                                     (unsigned int *)nullptr, (int)n, 0, 64, stream);
     cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp_t, (int *)nullptr, (int *)nullptr,
                                               (int *)nullptr, (int *)nullptr, (int)n, 0, 32, stream);
-    cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_i, (int *)nullptr, (int *)nullptr, (int)n + 1, stream);
+    cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_i, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                  (int)n + 1, stream);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_l, (long long *)nullptr, (long long *)nullptr,
                                   (int)n + 1, stream);
     const size_t tmp_bytes = std::max(std::max(sort_tmp, sort_tmp_t), std::max(scan_tmp_i, scan_tmp_l)) + 256;
@@ -1625,7 +1666,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     const size_t o_keys = take(n * 8), o_keys_alt = take(n * 8), o_idx = take(n * 4), o_idx_alt = take(n * 4);
     const size_t o_othr = take(n * 4), o_head = take(n * 4), o_gid = take(n * 4);
     const size_t o_head2 = take(n * 4), o_rid = take(n * 4), o_gomax = take(n1 * 4);
-    const size_t o_rstart = take(n1 * 4), o_grfirst = take(n1 * 4);
+    const size_t o_rstart = take(n1 * 4), o_grfirst = take(n1 * 4), o_flags2 = take(n * 8);
     const size_t o_gstart = take(n1 * 4), o_tile = take(n1 * 4), o_item = take(n1 * 4), o_woff = take(n1 * 8);
     const size_t o_astart = take(n1 * 4);
     size_t o_t[9];
@@ -1663,6 +1704,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     pl.head2 = (int *)(base + o_head2);
     pl.rid = (int *)(base + o_rid);
     pl.g_omax = (int *)(base + o_gomax);
+    pl.flags2 = (unsigned long long *)(base + o_flags2);
     pl.r_start = (int *)(base + o_rstart);
     pl.g_rfirst = (int *)(base + o_grfirst);
     pl.g_start = (int *)(base + o_gstart);
@@ -1712,30 +1754,18 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         CVF_CK(cudaGetLastError());
         {
             size_t tb_ = tmp_bytes;
-            CVF_CK(cub::DeviceScan::InclusiveSum(tmp, tb_, pl.head, pl.gid, (int)n, stream));
-            tb_ = tmp_bytes;
-            CVF_CK(cub::DeviceScan::InclusiveSum(tmp, tb_, pl.head2, pl.rid, (int)n, stream));
+            CVF_CK(cub::DeviceScan::InclusiveSum(tmp, tb_, pl.flags2, pl.flags2, (int)n, stream));
         }
         CVF_CK(cudaMemsetAsync(pl.g_omax, 0, n1 * sizeof(int), stream));
         cvf_group_starts<<<nb, tb, 0, stream>>>(n, pl);
         CVF_CK(cudaGetLastError());
         cvf_group_counts<<<nb1, tb, 0, stream>>>(n, slots_padded, pl);
         CVF_CK(cudaGetLastError());
-        {
-            size_t tb_ = tmp_bytes;
-            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.tile_start, pl.tile_start, (int)n + 1, stream));
-            tb_ = tmp_bytes;
-            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.item_start, pl.item_start, (int)n + 1, stream));
-            tb_ = tmp_bytes;
-            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.w_off, pl.w_off, (int)n + 1, stream));
-            tb_ = tmp_bytes;
-            CVF_CK(cub::DeviceScan::ExclusiveSum(tmp, tb_, pl.a_start, pl.a_start, (int)n + 1, stream));
-        }
-        cvf_totals<<<1, 1, 0, stream>>>(pl);
+        cvf_group_scan<<<1, 1024, 0, stream>>>(pl);
         CVF_CK(cudaGetLastError());
         CVF_CK(cudaMemcpyAsync(wk.h_header, pl.header, 6 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaStreamSynchronize(stream));
-        wk.launches += 28; /* K0, radix sort (10), heads, 6 scans (2 each), starts, counts, totals */
+        wk.launches += 17; /* K0, radix sort (10), heads, one scan (2), starts, counts, group scan */
         return cudaSuccess;
     };
     /* ordering for the prefix kernel first: it also tells how many q-runs the batch has */
