@@ -1409,7 +1409,11 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             CVF_CASE(0)
                             CVF_CASE(1)
                             CVF_CASE(2)
-                            CVF_CASE(3)
+#if CVF_PNQ > 3
+    #if CVF_PNQ > 3
+                        CVF_CASE(3)
+#endif
+#endif
 #undef CVF_CASE
                         }
                         while (o_done < need_next)
@@ -1425,7 +1429,11 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             CVF_CASE(0)
                             CVF_CASE(1)
                             CVF_CASE(2)
-                            CVF_CASE(3)
+#if CVF_PNQ > 3
+    #if CVF_PNQ > 3
+                        CVF_CASE(3)
+#endif
+#endif
 #undef CVF_CASE
                         }
                         const int pt_a = info & 0xffff, pt_b = info_next & 0xffff;
@@ -1524,7 +1532,9 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         CVF_CASE(0)
                         CVF_CASE(1)
                         CVF_CASE(2)
+#if CVF_PNQ > 3
                         CVF_CASE(3)
+#endif
 #undef CVF_CASE
                     }
                     q1 = qt_next.x;
