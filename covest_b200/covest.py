@@ -106,7 +106,7 @@ class CoverageEstimator:
 
     # -- objective --------------------------------------------------------------------------
     def _model_rows(self, points):
-        rows = np.array([[float(v) for v in p] for p in points], dtype=np.float64)
+        rows = np.array(points, dtype=np.float64)  # a copy: fix / err_scale are applied in place
         rows = rows.reshape(len(points), self.model.param_count)
         if self.fix is not None:
             for i, v in enumerate(self.fix):

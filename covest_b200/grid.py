@@ -21,8 +21,9 @@ from .utils import verbose_print
 
 def evaluate_all(fn, points):
     """Objective values of `points`, through fn.batch when the objective offers it."""
-    points = list(points)
-    if not points:
+    if not isinstance(points, np.ndarray):
+        points = list(points)
+    if len(points) == 0:
         return []
     batch = getattr(fn, 'batch', None)
     if batch is not None:
@@ -49,10 +50,10 @@ def _inside(value, bounds, i):
     return (lo is None or value >= lo) and (hi is None or value <= hi)
 
 
-def grid_candidates(center, step, depth, bounds=None, fix=None):
-    """Cartesian product of center_i * step**d, d in -depth..depth without 0, kept inside the
-    bounds; a fixed coordinate contributes its fixed value only (grid.py:20-43).  The centre
-    itself is never a candidate and a zero coordinate stays zero."""
+def grid_axes(center, step, depth, bounds=None, fix=None):
+    """Per coordinate the candidate values center_i * step**d, d in -depth..depth without 0, kept
+    inside the bounds; a fixed coordinate contributes its fixed value only (grid.py:20-43).  The
+    centre itself is never a candidate and a zero coordinate stays zero."""
     axes = []
     for i, var in enumerate(center):
         if fix is not None and fix[i] is not None:
@@ -60,7 +61,20 @@ def grid_candidates(center, step, depth, bounds=None, fix=None):
             continue
         axes.append([v for v in (var * step ** d for d in range(-depth, depth + 1) if d != 0)
                      if _inside(v, bounds, i)])
-    return list(itertools.product(*axes))
+    return axes
+
+
+def grid_candidates(center, step, depth, bounds=None, fix=None):
+    """Cartesian product of grid_axes, in the order of itertools.product (grid.py:33)."""
+    return list(itertools.product(*grid_axes(center, step, depth, bounds, fix)))
+
+
+def _product_rows(axes):
+    """The rows of itertools.product(*axes) as one float64 array (last axis fastest)."""
+    if any(len(a) == 0 for a in axes):
+        return np.empty((0, len(axes)))
+    mesh = np.meshgrid(*[np.asarray(a, dtype=np.float64) for a in axes], indexing='ij')
+    return np.ascontiguousarray(np.stack([m.ravel() for m in mesh], axis=1))
 
 
 @running_time_decorator
@@ -82,16 +96,32 @@ def optimize_grid(fn, initial_guess, bounds=None, maximize=False, fix=None,
         while diff > 0.1 or step > 1.001:
             rounds += 1
             diff = 0.0
-            grid = grid_candidates(best_args, step, depth, bounds, fix)
-            verbose_print('Iter : {}, Grid size: {}'.format(rounds, len(grid)))
-            with running_time('grid iteration'):
-                values = evaluate_all(fn, grid)
-            # same sequential bookkeeping as grid.py:65-69, including its use of the raw value
-            for args, val in zip(grid, values):
-                if sign * val < best_val:
-                    diff += best_val - val
-                    best_val = sign * val
-                    best_args = args
+            batch = getattr(fn, 'batch', None)
+            if batch is not None:
+                # the whole round as one array and one launch; the bookkeeping of grid.py:65-69
+                # (strict improvements in candidate order, its use of the raw value included) on
+                # the running minimum
+                grid = _product_rows(grid_axes(best_args, step, depth, bounds, fix))
+                verbose_print('Iter : {}, Grid size: {}'.format(rounds, len(grid)))
+                with running_time('grid iteration'):
+                    values = np.asarray(batch(grid), dtype=np.float64) if len(grid) else np.empty(0)
+                signed = sign * values
+                before = np.fmin.accumulate(np.concatenate(([best_val], signed)))[:-1]
+                for i in np.nonzero(signed < before)[0]:
+                    diff += float(before[i]) - float(values[i])
+                    best_val = float(signed[i])
+                    best_args = tuple(float(v) for v in grid[i])
+            else:
+                grid = grid_candidates(best_args, step, depth, bounds, fix)
+                verbose_print('Iter : {}, Grid size: {}'.format(rounds, len(grid)))
+                with running_time('grid iteration'):
+                    values = evaluate_all(fn, grid)
+                # same sequential bookkeeping as grid.py:65-69, including its use of the raw value
+                for args, val in zip(grid, values):
+                    if sign * val < best_val:
+                        diff += best_val - val
+                        best_val = sign * val
+                        best_args = args
             if diff < 1.0:
                 step = 1 + (step - 1) * 0.75
             verbose_print('d:{} s:{}'.format(diff, step))
