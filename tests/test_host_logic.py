@@ -326,3 +326,16 @@ def test_workload_flop_accounting_of_the_factored_paths():
     assert w['prefix_flop'] == 16 * (6.0 * 100 + 64.0 * 100) + 2.0 * 100 * sum(max(m - 2, 0) for m in per_run_max)
     assert w['profile_flop'] == 2.0 * 8 * 100 * sum(copies[pts[:, 0] == c].max() for c in (10.0, 20.0))
     model.close()
+
+
+def test_grid_rounds_as_arrays_keep_the_order_of_itertools_product():
+    import itertools
+    from covest_b200 import grid
+    axes = grid.grid_axes([10.0, 0.05, 0.5, 0.0, 0.9], 1.1, 3, bounds=((0.01, None), (0, .5), (.3, 1), (0, 1), (0, 1)))
+    assert [len(a) for a in axes] == [6, 6, 6, 6, 4]   # 0.0 stays 0.0 six times; 0.9 * 1.1^d cut at 1
+    rows = grid._product_rows(axes)
+    assert rows.shape == (6 * 6 * 6 * 6 * 4, 5)
+    assert [tuple(r) for r in rows[:50]] == list(itertools.product(*axes))[:50]
+    assert tuple(rows[-1]) == list(itertools.product(*axes))[-1]
+    assert grid._product_rows([[1.0], [], [2.0]]).shape == (0, 3)
+    assert grid.grid_candidates([10.0, 0.05], 1.1, 1) == list(itertools.product(*grid.grid_axes([10.0, 0.05], 1.1, 1)))
