@@ -57,6 +57,7 @@ struct cvb_ctx {
     CvFactorWork fw;
     const double2 *d_slot_mh = nullptr;
     const int *d_step_mask = nullptr;
+    bool counts_first = false; /* cvf_counts_first(slot_h) */
     const double *d_log_tab = nullptr;
     int path_mode = 0;         /* 0 auto, 1 per-point kernel only, 2 factored whenever supported */
     size_t w_limit = (size_t)2 << 30; /* doubles: 16 GiB of profiles per group range */
@@ -281,6 +282,7 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
                 mh[i] = make_double2(T.slot_mult[i], T.slot_h[i]);
             if ((e = upload(c, mh, &c->d_slot_mh)) != cudaSuccess) break;
             if ((e = upload(c, cvf_step_masks(T.slot_h), &c->d_step_mask)) != cudaSuccess) break;
+            c->counts_first = cvf_counts_first(T.slot_h);
             std::vector<double> lt(2 * CV_LOG_N);
             cv_log_table(lt.data());
             if ((e = upload(c, lt, &c->d_log_tab)) != cudaSuccess) break;
@@ -359,7 +361,7 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
         CU(cvf_eval(ctx->desc, lat, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->d_step_mask,
                     ctx->d_log_tab, ctx->fw, ctx->n_sm,
                     ctx->smem_max, ctx->w_limit, forced ? 0.0 : ctx->min_group, ctx->min_run,
-                    ctx->path_mode == 3 ? 1 : ctx->path_mode == 4 ? 2 : 0, s, &used),
+                    ctx->path_mode == 3 ? 1 : ctx->path_mode == 4 ? 2 : 0, ctx->counts_first, s, &used),
            "factored evaluation");
         ctx->last_launches += ctx->fw.launches;
     }

@@ -1092,8 +1092,11 @@ __device__ __forceinline__ int cvf_count_below(const int *a, int n, int x, bool 
 /* MASS: the histogram has a tail (models.py:103-104): the mass sum_j p_j enters the result through
  * 1 - mass and is summed compensated (the reference uses fsum); without a tail it only has to
  * tell whether it is below 1 (models.py:104), a plain sum.
- * FULL: the slots are a multiple of CVF_PASS_SLOTS, no thread ever idles in a pass. */
-template <bool MASS, bool FULL>
+ * FULL: the slots are a multiple of CVF_PASS_SLOTS, no thread ever idles in a pass.
+ * ONE: the bins with counts all lie in the first of a thread's CVF_SL slots (histograms whose
+ * counted bins are the first quarter of every pass): the code for the other slots' logarithms is
+ * not even compiled in. */
+template <bool MASS, bool FULL, bool ONE>
 __global__ void __launch_bounds__(CVF_PT, 2)
 cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                   const double *__restrict__ params, int clip, CvfPlan pl, int first_tile, int n_tiles,
@@ -1458,7 +1461,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             }
                         }
                         double sa = 0.0, sb = 0.0;
-                        if (log_mask == 1) { /* the usual case: only the warp's first half-line has counts */
+                        if (ONE ? log_mask != 0 : log_mask == 1) { /* the usual case: only the warp's first half-line has counts */
                             const unsigned int ca = (unsigned int)(__double2hiint(pa[0]) - 0x00100000),
                                                cb = (unsigned int)(__double2hiint(pb[0]) - 0x00100000);
                             double la, lb;
@@ -1473,7 +1476,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             sb = cv_mul(hcnt[0], lb);
                             if (hcnt[0] == 0.0) /* models.py:106 `if h` */
                                 sa = sb = 0.0;
-                        } else if (log_mask) {
+                        } else if (!ONE && log_mask) {
 #pragma unroll
                             for (int i = 0; i < CVF_SL; i++)
                                 if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
@@ -1551,12 +1554,12 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         else
                             mh = cv_add(mh, p[i]);
                     }
-                    if (log_mask == 1) { /* the usual case: the warp's first half-line holds the bins with counts */
+                    if (ONE ? log_mask != 0 : log_mask == 1) { /* the usual case: the warp's first half-line holds the bins with counts */
                         double term = cv_mul(hcnt[0], cvf_safe_log(p[0], log_s)); /* utils.py:32-35 */
                         if (hcnt[0] == 0.0) /* models.py:106 `if h` */
                             term = 0.0;
                         sum = term;
-                    } else if (log_mask) {
+                    } else if (!ONE && log_mask) {
 #pragma unroll
                         for (int i = 0; i < CVF_SL; i++)
                             if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
@@ -1645,7 +1648,8 @@ static size_t cvf_align(size_t x) { return (x + 255) & ~(size_t)255; }
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
                      int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
-                     double min_group, double min_run, int kernel_mode, cudaStream_t stream, int *used)
+                     double min_group, double min_run, int kernel_mode, bool counts_first, cudaStream_t stream,
+                     int *used)
 {
     *used = 0;
     wk.launches = 0;
@@ -1858,8 +1862,10 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
     CVF_CK(cudaFuncSetAttribute(cvf_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
     CVF_CK(cudaFuncSetAttribute(cvf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(CvfSmem)));
-    auto kp = want_mass ? (full_passes ? cvf_prefix_kernel<true, true> : cvf_prefix_kernel<true, false>)
-                        : (full_passes ? cvf_prefix_kernel<false, true> : cvf_prefix_kernel<false, false>);
+    auto kp = want_mass ? (full_passes ? (counts_first ? cvf_prefix_kernel<true, true, true> : cvf_prefix_kernel<true, true, false>)
+                                       : (counts_first ? cvf_prefix_kernel<true, false, true> : cvf_prefix_kernel<true, false, false>))
+                        : (full_passes ? (counts_first ? cvf_prefix_kernel<false, true, true> : cvf_prefix_kernel<false, true, false>)
+                                       : (counts_first ? cvf_prefix_kernel<false, false, true> : cvf_prefix_kernel<false, false, false>));
     CVF_CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kp_smem));
     if (wk.timed)
         CVF_CK(cudaEventRecord(wk.ev[1], stream));

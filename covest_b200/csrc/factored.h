@@ -49,7 +49,7 @@ bool cvf_supported(const CvModelDesc &m);
 
 /* Evaluates n points.  *used = 0 when the batch does not group well enough (nothing written to
  * out_ll; the caller runs the per-point kernel), 1 when K2 (the GEMM) ran, 2 when the prefix kernel
- * ran.  kernel_mode: 0 = prefix kernel when the batch has at least min_run points per q-run (points
+ * ran.  counts_first: cvf_counts_first(slot_h).  kernel_mode: 0 = prefix kernel when the batch has at least min_run points per q-run (points
  * of a group that also share q), else the GEMM; 1 = GEMM; 2 = prefix kernel.  Device tables: `slot_mh` = (slot_mult, slot_h)
  * pairs; `step_mask` = per 32 slots, bit 2 nt + c set when one of the slots 8 nt + 2 q + c, q < 4,
  * has a count (cvf_step_masks); `log_tab` = cv_log_table.  w_limit = largest profile workspace in
@@ -57,7 +57,8 @@ bool cvf_supported(const CvModelDesc &m);
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
                      int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
-                     double min_group, double min_run, int kernel_mode, cudaStream_t stream, int *used);
+                     double min_group, double min_run, int kernel_mode, bool counts_first, cudaStream_t stream,
+                     int *used);
 
 /* host: the step masks of a slot_h table (length a multiple of 32) */
 #include <vector>
@@ -70,6 +71,17 @@ static inline std::vector<int> cvf_step_masks(const std::vector<double> &slot_h)
             out[s / 32] |= 1 << (2 * nt + c);
         }
     return out;
+}
+
+/* host: do all slots with counts lie in the first of the four slots a thread of the prefix kernel
+ * owns per pass?  (slot -> half-line u = 2 * (slot / 64) + (slot % 64) / 32; a pass has 32
+ * half-lines, a thread's slot i is half-line (u % 32) / 8.) */
+static inline bool cvf_counts_first(const std::vector<double> &slot_h)
+{
+    for (size_t s = 0; s < slot_h.size(); s++)
+        if (slot_h[s] != 0.0 && (((2 * (s / 64) + (s % 64) / 32) % 32) >> 3) != 0)
+            return false;
+    return true;
 }
 
 void cvf_release(CvFactorWork &wk);
