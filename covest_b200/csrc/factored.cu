@@ -1,10 +1,16 @@
 /*
  * factored.cu -- batched evaluation of the repeats model as profiles x copy weights (factored.h).
  *
- *   cvf_point_keys      K0: per point clip, cut-off O_thr, sort key
- *   cvf_heads / cvf_group_starts / cvf_group_counts / cvf_group_scan   group tables from the sorted keys
+ *   cvf_point_keys      K0: per point clip, cut-off O_thr, sort key ((c, e) hash | q | O_thr)
+ *   cvf_heads / cvf_group_starts / cvf_group_counts / cvf_group_scan / cvf_tile_table
+ *                       groups (equal (c, e)), q-runs (equal q inside a group) and tiles from the
+ *                       sorted keys
  *   cvf_profile_kernel  K1: one warp per (group, 16 copy numbers): profiles over all bins
- *   cvf_gemm_kernel     K2: one CTA per tile of 128 points: FP64 tensor-core GEMM + epilogue
+ *   cvf_prefix_kernel   K2p: one CTA per tile of up to four q-runs: running sums over the copy
+ *                       numbers, per point the three-term combination + epilogue (the default for
+ *                       batches whose points share q, as lattices do)
+ *   cvf_weights_kernel, cvf_gemm_kernel   K1b, K2: one CTA per tile of 128 points: copy weights and
+ *                       FP64 tensor-core GEMM + epilogue (batches that share (c, e) but not q)
  *
  * cub's device radix sort and prefix sums order the keys and lay out the group tables (plumbing);
  * every likelihood flop is in the hand-written kernels of this file and of cvpoint.h.
