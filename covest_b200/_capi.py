@@ -8,6 +8,7 @@ from . import build as _build
 _lib = None
 
 CVB_OK = 0
+ABI_VERSION = 2  # CVB_ABI_VERSION of include/covest_b200.h this binding was written against
 MODEL_BASIC, MODEL_REPEATS = 0, 1
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -34,7 +35,18 @@ def load():
                     'libcovest_b200.so is not built and could not be built (%s). Run '
                     '`python -m covest_b200.build` on a machine with nvcc; there is no CPU '
                     'implementation to fall back to.' % exc)
+            import warnings
+            warnings.warn('libcovest_b200.so is older than its sources and could not be rebuilt (%s); '
+                          'using the existing binary if its ABI version matches' % exc)
     L = ctypes.CDLL(path)
+    try:
+        L.cvb_abi_version.restype = ctypes.c_int
+        have = L.cvb_abi_version()
+    except AttributeError:
+        have = 1
+    if have != ABI_VERSION:
+        raise LibraryMissing('libcovest_b200.so has ABI version %d, this binding needs %d: rebuild it '
+                             'with `python -m covest_b200.build --force`' % (have, ABI_VERSION))
     vp = ctypes.c_void_p
     i64 = ctypes.c_int64
     L.cvb_version.restype = ctypes.c_char_p
@@ -80,4 +92,5 @@ def load():
 
 EXPORTS = ('cvb_ctx_create', 'cvb_ctx_destroy', 'cvb_last_error', 'cvb_loglik_batch',
            'cvb_probs_batch', 'cvb_topk', 'cvb_loglik_topk', 'cvb_lattice_eval', 'cvb_fp64_peak', 'cvb_set_timing',
-           'cvb_last_kernel_ms', 'cvb_set_path', 'cvb_merge_rows', 'cvb_last_path_info', 'cvb_n_param', 'cvb_device_sm_count', 'cvb_version')
+           'cvb_last_kernel_ms', 'cvb_set_path', 'cvb_merge_rows', 'cvb_last_path_info', 'cvb_n_param', 'cvb_device_sm_count', 'cvb_version',
+           'cvb_abi_version')

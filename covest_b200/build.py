@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libcovest_b200.so')
 SOURCES = ['kernels.cu', 'factored.cu', 'topk.cu', 'capi.cu']
-NVCC_FLAGS = (['-DCVF_K1_NOSTORE=1'] if os.environ.get('CVF_K1_NOSTORE') else []) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xcompiler', '-ffp-contract=off',
               '--fmad=false']
 

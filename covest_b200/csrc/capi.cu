@@ -133,7 +133,9 @@ static cudaError_t upload(cvb_ctx *ctx, const std::vector<T> &v, const T **out)
     return e;
 }
 
-extern "C" const char *cvb_version(void) { return "covest_b200 0.1 (sm_100a)"; }
+extern "C" const char *cvb_version(void) { return "covest_b200 0.2 (sm_100a)"; }
+
+extern "C" int cvb_abi_version(void) { return CVB_ABI_VERSION; }
 
 extern "C" const char *cvb_last_error(const cvb_ctx *ctx)
 {

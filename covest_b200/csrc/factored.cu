@@ -29,9 +29,6 @@
 
 #include "kdevice.h"
 
-#ifndef CVF_K1_NOSTORE
-#define CVF_K1_NOSTORE 0 /* development: 1 = K1 computes but does not write (timing experiment) */
-#endif
 #define CVF_M 128       /* points per tile of K2 */
 #define CVF_NS 64       /* bins (slots) per N-step of K2 */
 #define CVF_KC 16       /* copy numbers per K-chunk */
@@ -431,8 +428,7 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
         const double2 mm = __ldg(reinterpret_cast<const double2 *>(slot_mult) + (blk * (2 * NA) + ns) * 32 + lane);
         v.x = cv_mul(v.x, mm.x); /* the accumulators are finite (that is what the scale is for): times 0 is 0 */
         v.y = cv_mul(v.y, mm.y);
-        if (!CVF_K1_NOSTORE || v.x == 12345.678)
-            *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
+        *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
     }
     __syncwarp();
 }
@@ -719,7 +715,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
                 const double *__restrict__ W, long long w_base, const double *__restrict__ A,
                 long long a_base, const double2 *__restrict__ slot_mh, const int *__restrict__ step_mask,
                 const double *__restrict__ log_tab, int nsteps, double *__restrict__ out_ll,
-                unsigned long long *counter, int dbg)
+                unsigned long long *counter)
 {
     extern __shared__ __align__(16) unsigned char cvf_smem_raw[];
     CvfSmem &S = *reinterpret_cast<CvfSmem *>(cvf_smem_raw);
@@ -779,7 +775,6 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
         int ld_kc = 0, ld_ns = 0, ld_buf = 0; /* the next (profile, weight) tile pair to request */
         auto issue = [&]() {
             if (ld_ns < nsteps) {
-                if (!(dbg & 4)) {
                 const double2 *src = reinterpret_cast<const double2 *>(
                     Wg + ((long long)ld_kc * nsteps + ld_ns) * CVF_TILE_DOUBLES);
                 double2 *dst = S.Bs[ld_buf];
@@ -790,7 +785,6 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     cvf_cp_async16(adst + tid + j * CVF_THREADS, asrc + tid + j * CVF_THREADS);
-                }
                 if (++ld_kc == nkc) {
                     ld_kc = 0;
                     ld_ns++;
@@ -818,7 +812,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
                 __syncthreads(); /* this chunk's tiles landed, the previous chunk is consumed */
                 issue();
                 const int k0 = kc * CVF_KC;
-                if (k0 >= kend_hi || (dbg & 1))
+                if (k0 >= kend_hi)
                     continue;
                 const double2 *as2 = S.As[cons_buf] + (wm * 4) * 2 * 32 + apos;
                 const double2 *bs2 = S.Bs[cons_buf] + (wn * 4) * 2 * 32 + lane;
@@ -865,7 +859,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
              * tiles and slots 64 ns + 32 wn + 8 nt + 2 q + c; bit 2 nt + c of the step mask says
              * whether any of those four slots has a count */
             const int mask = want_mass ? 0xff : __ldg(step_mask + 2 * ns + wn);
-            if (mask && !(dbg & 2)) {
+            if (mask) {
 #pragma unroll
                 for (int nt = 0; nt < 4; nt++)
 #pragma unroll
@@ -1919,7 +1913,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
             } else {
                 cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(
                     m, pl, tile0, tiles, wk.W, w0, A, a0, slot_mh, step_mask, log_tab, nsteps, out_ll,
-                    wk.d_counters + 1, getenv("COVEST_B200_DBG") ? atoi(getenv("COVEST_B200_DBG")) : 0);
+                    wk.d_counters + 1);
             }
             CVF_CK(cudaGetLastError());
             wk.launches += 2;

@@ -98,7 +98,10 @@ class BasicModel:
 
     # -- device context ---------------------------------------------------------------------
     def _state_key(self):
-        return (id(self.hist), len(self.hist), self.tail, self.max_error, self.bounds,
+        # the reference reads self.hist on every call (models.py:92, :235): counts changed in place
+        # must reach the device copy, so the items themselves are part of the key (a few hundred to
+        # a few thousand bins)
+        return (hash(tuple(self.hist.items())), self.tail, self.max_error, self.bounds,
                 self.threshold, self.k, self.r)
 
     @property

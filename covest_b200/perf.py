@@ -1,74 +1,52 @@
-"""Wall-clock timers that report to stderr in the reference's format
-("... took {time} seconds.", covest/perf.py)."""
+"""Nested wall-clock timers reporting to stderr.
+
+Only the message text is a contract with the reference ("<what> took <seconds> seconds.", and
+"Function <name> (<module>) took ..." for decorated functions; covest/perf.py:52-68): tools that
+scrape covest's stderr keep working.  The mechanism is this package's own: one `Timer` per region,
+the nesting depth kept in a thread-local counter (the multi-start refinement runs regions in
+threads), monotonic clock, and the message is emitted even when the region raises.
+"""
+import functools
 import sys
+import threading
 import time
-from contextlib import contextmanager
 
-stack = []
-messages = []
+_depth = threading.local()
 
 
-def indent():
-    if len(stack) < 2:
-        return ''
-    return '| ' * (len(stack) - 2) + '+'
+class Timer:
+    """Context manager: prints '<label> took <seconds> seconds.' on exit, indented by nesting."""
+
+    def __init__(self, label, out=None):
+        self.label = label
+        self.out = out
+        self.seconds = None
+
+    def __enter__(self):
+        self.level = getattr(_depth, 'n', 0)
+        _depth.n = self.level + 1
+        self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *exc):
+        self.seconds = time.perf_counter() - self.t0
+        _depth.n = self.level
+        prefix = '' if self.level == 0 else '| ' * (self.level - 1) + '+'
+        (self.out or sys.stderr).write('%s%s took %s seconds.\n' % (prefix, self.label, self.seconds))
+        return False
 
 
-def push(cnt=1):
-    for _ in range(cnt):
-        stack.append(time.time())
-
-
-def pop(cnt=1):
-    last = None
-    for _ in range(cnt):
-        last = stack.pop()
-    return last
-
-
-def replace():
-    pop()
-    push()
-
-
-def get_time(back=0):
-    n = len(stack)
-    if back >= n or back == -1:
-        back = n - 1
-    return stack[n - back - 1]
-
-
-def print_all():
-    global messages
-    for m in messages:
-        sys.stderr.write(m + '\n')
-    messages = []
-
-
-def msg(message, back=0):
-    elapsed = time.time() - get_time(back)
-    messages.append(indent() + message.format(time=elapsed))
-    print_all()
+def running_time(text):
+    """`with running_time('First optimization'): ...` (covest/covest.py:54, :65; grid.py:62)."""
+    return Timer(text)
 
 
 def running_time_decorator(fn):
-    def wrapped(*args, **kwargs):
-        push(2)
-        try:
+    """Times every call of `fn` (covest/covest.py:99, grid.py:17)."""
+    label = 'Function %s (%s)' % (fn.__name__, fn.__module__)
+
+    @functools.wraps(fn)
+    def timed(*args, **kwargs):
+        with Timer(label):
             return fn(*args, **kwargs)
-        finally:
-            msg('Function ' + fn.__name__ + ' (' + fn.__module__ + ') took {time} seconds.', 1)
-            pop(2)
-    wrapped.__name__ = fn.__name__
-    wrapped.__doc__ = fn.__doc__
-    return wrapped
-
-
-@contextmanager
-def running_time(text):
-    push(2)
-    try:
-        yield
-    finally:
-        msg(text + ' took {time} seconds.', 1)
-        pop(2)
+    return timed

@@ -156,6 +156,11 @@ CVB_API int cvb_n_param(const cvb_ctx *ctx);
 CVB_API int cvb_device_sm_count(const cvb_ctx *ctx);
 CVB_API const char *cvb_version(void);
 
+/* Bumped whenever a signature or the meaning of an argument changes; a binding compares it with
+ * the version it was written against before it calls anything else (covest_b200/_capi.py). */
+#define CVB_ABI_VERSION 2
+CVB_API int cvb_abi_version(void);
+
 #ifdef __cplusplus
 }
 #endif
