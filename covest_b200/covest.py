@@ -10,11 +10,23 @@ YAML report.  What changes is scheduling only:
     `workers` map hook and evaluated as one launch (the reference: n+1 sequential objective calls);
   * the starts of a multi-start run live in threads whose evaluations are merged into common
     launches by a LaunchBatcher (the reference: one forked process per start, covest.py:67-68);
-  * grid-search rounds are one launch each (grid.py).
+  * grid-search rounds are one launch each (grid.py); for a device-resident model the round is
+    handed over as its axes and only the best candidate comes back (cvb_lattice_eval, k_best = 1).
+
+Additions (not in the reference):
+
+  * `optimizer='lockstep'` (CLI `--optimizer lockstep`): the multi-start refinement as a lock-step
+    projected Newton iteration, all starts per launch (optimizer.py), instead of scipy in threads;
+  * under torch.distributed (one process per GPU, torchrun) the starts of a multi-start run are
+    dealt round-robin to the ranks, refined there, and the refined optima are all-gathered
+    (`refine_starts`); `compute_coverage_from_lattice` first evaluates a sharded candidate lattice
+    and takes the global best rows as starts (SURVEY.md section 8(e));
+  * `polish` (CLI `--polish`): Newton iteration on central differences.
 
 `-T / n_threads` is accepted and ignored.
 """
 import argparse
+import os
 import threading
 from pathlib import Path
 
@@ -23,7 +35,9 @@ from scipy.optimize import minimize
 
 from . import constants, version_string
 from .data import load_histogram, parse_data, print_output, save_histogram
-from .grid import initial_grid, optimize_grid
+from . import parallel
+from .grid import initial_grid, lattice_search, optimize_grid
+from .optimizer import lockstep_minimize
 from .histogram import process_histogram
 from .models import models, select_model
 from .perf import running_time, running_time_decorator
@@ -93,12 +107,23 @@ class _Objective:
     def batch(self, points):
         return self._est.likelihood_batch(points)
 
+    def lattice_best(self, axes):
+        """(objective, point) of the best candidate of the Cartesian lattice of `axes` (optimiser
+        coordinates, last axis fastest; ties to the first candidate in itertools.product order) --
+        or None when the model has no device lattice evaluator.  One grid-search round
+        (grid.py:56-69) without the candidates or their values crossing the bus."""
+        return self._est.lattice_best(axes)
+
 
 class CoverageEstimator:
-    def __init__(self, model, err_scale=1, fix=None):
+    def __init__(self, model, err_scale=1, fix=None, optimizer=None):
         self.model = model
         self.fix = fix
         self.err_scale = err_scale
+        # 'scipy': L-BFGS-B per start, as the reference; 'lockstep': optimizer.py (multi-start only)
+        self.optimizer = optimizer or os.environ.get('COVEST_B200_OPTIMIZER', 'scipy')
+        if self.optimizer not in ('scipy', 'lockstep'):
+            raise ValueError('optimizer must be scipy or lockstep')
         self.bounds = list(self.model.bounds)
         self.bounds[1] = self.bounds[1][0], self.bounds[1][1] * self.err_scale
         self.launches = 0
@@ -127,6 +152,33 @@ class CoverageEstimator:
     @property
     def likelihood_f(self):
         return _Objective(self)
+
+    def lattice_best(self, axes):
+        """See _Objective.lattice_best.  Needs a model whose evaluator is the device context
+        (a subclass that overrides loglikelihood_batch is evaluated through `batch` instead)."""
+        from .models import BasicModel
+        if type(self.model).loglikelihood_batch is not BasicModel.loglikelihood_batch:
+            return None
+        axes = [np.asarray(a, dtype=np.float64).ravel() for a in axes]
+        if any(len(a) == 0 for a in axes):
+            return None
+        model_axes = [a.copy() for a in axes]
+        if self.fix is not None:
+            for i, v in enumerate(self.fix):
+                if v is not None:
+                    model_axes[i] = np.full(len(axes[i]), float(v))
+        model_axes[1] = model_axes[1] / self.err_scale
+        _, rows = self.model.device_context.lattice_eval(model_axes, want_ll=False, k_best=1)
+        self.launches += 1
+        self.evaluations += int(np.prod([len(a) for a in axes]))
+        if not np.isfinite(rows[0, 0]) and not np.isneginf(rows[0, 0]):
+            return None
+        # back to optimiser coordinates: the row holds the model-side axis values bit for bit
+        point = []
+        for a, ma, v in zip(axes, model_axes, rows[0, 1:]):
+            hit = np.flatnonzero(ma == v)
+            point.append(float(a[hit[0]]) if len(hit) else float(v))
+        return -float(rows[0, 0]), tuple(point)
 
     # -- optimisation -----------------------------------------------------------------------
     def _optimize(self, r, evaluate=None):
@@ -186,6 +238,11 @@ class CoverageEstimator:
                         verbose_print('Optimization unsuccessful.\n'
                                       'Initial params:{}\nResult{}'.format(r, res))
                     r = res.x
+            elif starting_points > 1 and (self.optimizer == 'lockstep' or parallel.world()[1] > 1):
+                params = initial_grid(r, count=starting_points, bounds=self.bounds, fix=self.fix)
+                params = parallel.broadcast_rows(np.array(params, dtype=np.float64), self._comm_device())
+                with running_time('Initial grid optimization'):
+                    r, _, success, _ = self.refine_starts(params)
             elif starting_points > 1:
                 params = initial_grid(r, count=starting_points, bounds=self.bounds, fix=self.fix)
                 with running_time('Initial grid optimization'):
@@ -210,6 +267,68 @@ class CoverageEstimator:
         r = list(r)
         r[1] /= self.err_scale
         return r, success
+
+    # -- multi-start refinement, sharded over the ranks (new) ---------------------------------
+    def _comm_device(self):
+        """Where the small tensors of the collectives live: the model's GPU under NCCL, the host
+        under gloo."""
+        rank, world = parallel.world()
+        if world > 1:
+            import torch.distributed as dist
+            if dist.get_backend() == 'nccl':
+                import torch
+                return torch.device('cuda', self.model.device_context.device)
+        return None
+
+    def refine_starts(self, starts):
+        """Refine every row of `starts` (optimiser coordinates) and return the best result:
+        (x, objective, success, table) with table = one row (objective, success, x...) per start.
+        Start i belongs to rank i % W (parallel.split_starts); every rank refines its share -- all
+        of them per launch with the lock-step optimiser, or scipy L-BFGS-B in threads -- and the
+        refined optima are all-gathered, so every rank returns the same answer.  The reference's
+        counterpart is Pool.map(self._optimize, params) and the arg-min over it (covest.py:63-78)."""
+        starts = np.asarray(starts, dtype=np.float64).reshape(-1, self.model.param_count)
+        rank, world = parallel.world()
+        mine = parallel.split_starts(starts, rank, world)
+        n = self.model.param_count
+        per_rank = (len(starts) + world - 1) // world
+        table = np.full((per_rank, 2 + n), np.nan)
+        table[:, 0] = np.inf
+        table[:, 1] = 0.0
+        if len(mine):
+            if self.optimizer == 'lockstep':
+                fixed = [self.fix is not None and self.fix[i] is not None for i in range(n)]
+                results, launches = lockstep_minimize(self.likelihood_batch, mine, self.bounds, fixed=fixed)
+            else:
+                results = self._optimize_many([list(s) for s in mine])
+            for j, res in enumerate(results):
+                table[j, 0] = res.fun if np.isfinite(res.fun) else np.inf
+                table[j, 1] = 1.0 if res.success else 0.0
+                table[j, 2:] = res.x
+        if world > 1:
+            gathered = parallel.allgather_rows(parallel.to_comm(table, self._comm_device()))
+            table = gathered.cpu().numpy().reshape(world, per_rank, 2 + n)
+            table = table.transpose(1, 0, 2).reshape(-1, 2 + n)[:len(starts)]  # back to start order
+        else:
+            table = table[:len(starts)]
+        best = int(np.argmin(table[:, 0]))  # ties: the earliest start, as the reference's strict `>`
+        return table[best, 2:].copy(), float(table[best, 0]), bool(table[best, 1]), table
+
+    def compute_coverage_from_lattice(self, axes, k_best=64):
+        """evaluate the candidate lattice of `axes` (model coordinates)
+        sharded over the ranks, all-gather every rank's k_best best rows, refine the global best
+        rows as starts (dealt round-robin), all-gather the refined optima.
+        Returns (parameters, success, rows) like compute_coverage plus the global best rows."""
+        rows = lattice_search(self.model, axes, k_best=k_best)
+        keep = np.isfinite(rows[:, 0])
+        starts = rows[keep, 1:].copy()
+        if len(starts) == 0:
+            raise ValueError('no lattice point has a finite log-likelihood')
+        starts[:, 1] *= self.err_scale
+        x, fun, success, _ = self.refine_starts(starts)
+        x = list(x)
+        x[1] /= self.err_scale
+        return x, success, rows
 
     # -- polish (new) -----------------------------------------------------------------------
     def polish(self, x, iterations=40, rel_step=1e-4, tol=1e-11):
@@ -347,7 +466,8 @@ def main(args):
             raise SystemExit(1)
         verbose_print('Initial guess: {} ll:{}'.format(guess, guess_ll))
 
-        estimator = CoverageEstimator(model, err_scale=err_scale, fix=fix)
+        estimator = CoverageEstimator(model, err_scale=err_scale, fix=fix,
+                                      optimizer=getattr(args, 'optimizer', None))
         res, success = estimator.compute_coverage(
             guess, starting_points=args.starting_points, use_grid_search=args.grid,
             n_threads=args.thread_count)
@@ -410,6 +530,9 @@ def build_parser():
     # additions (not in the reference)
     p.add_argument('--polish', action='store_true',
                    help='Newton-polish the optimum on central differences after L-BFGS-B')
+    p.add_argument('--optimizer', choices=['scipy', 'lockstep'], default=None,
+                   help='Multi-start refinement: scipy L-BFGS-B per start (the reference\'s optimiser, '
+                        'default) or the lock-step Newton iteration with all starts per launch')
     p.add_argument('--seed', type=int, default=None,
                    help='Seed Python\'s random (multi-start points, histogram sampling)')
     return p

@@ -30,6 +30,12 @@ struct cvb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; /* device -> host copy of the values while the top-K runs */
     cudaEvent_t copy_ev = nullptr;
+    cudaEvent_t copy_done = nullptr; /* the side copy has finished: the main stream waits for it */
+    /* calls of one context share its scratch (work counters, plan, profiles, staging): a call on a
+     * different stream than the previous one first waits for the previous call's work */
+    cudaEvent_t order_ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool order_valid = false;
     /* growable staging */
     double *d_params = nullptr;
     size_t cap_params = 0; /* doubles */
@@ -164,6 +170,10 @@ extern "C" void cvb_ctx_destroy(cvb_ctx *ctx)
     cvf_release(ctx->fw);
     if (ctx->copy_ev)
         cudaEventDestroy(ctx->copy_ev);
+    if (ctx->copy_done)
+        cudaEventDestroy(ctx->copy_done);
+    if (ctx->order_ev)
+        cudaEventDestroy(ctx->order_ev);
     if (ctx->copy_stream)
         cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream)
@@ -348,8 +358,9 @@ extern "C" int cvb_last_kernel_ms(cvb_ctx *ctx, double *out_ms, int *out_launche
 /* one evaluation of n points on the device, optionally bracketed by events: the factored path
  * when the batch is large and groups well (never when per-bin probabilities are wanted), else the
  * per-point kernel */
-static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_params, long long n,
-                         int clip, double *d_ll, double *d_probs, cudaStream_t s)
+static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *const *lat_axes_host,
+                         const double *d_params, long long n, int clip, double *d_ll, double *d_probs,
+                         cudaStream_t s)
 {
     bool timed = ctx->timing && ctx->timed_chunks < CVB_MAX_TIMED_CHUNKS;
     if (timed)
@@ -360,7 +371,7 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
                               (forced || n >= ctx->min_points);
     if (try_factored) {
         ctx->fw.timed = ctx->timing;
-        CU(cvf_eval(ctx->desc, lat, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->d_step_mask,
+        CU(cvf_eval(ctx->desc, lat, lat_axes_host, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->d_step_mask,
                     ctx->d_log_tab, ctx->fw, ctx->n_sm,
                     ctx->smem_max, ctx->w_limit, forced ? 0.0 : ctx->min_group, ctx->min_run,
                     ctx->path_mode == 3 ? 1 : ctx->path_mode == 4 ? 2 : 0, ctx->counts_first, s, &used),
@@ -384,6 +395,24 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *d_par
 static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, const double *d_params,
                        long long n, int K, double *out_rows, cudaStream_t s);
 
+/* stream ordering between the calls of one context (see cvb_ctx::order_ev) */
+static int order_enter(cvb_ctx *ctx, cudaStream_t s)
+{
+    if (ctx->order_valid && ctx->last_stream != s)
+        CU(cudaStreamWaitEvent(s, ctx->order_ev, 0), "cudaStreamWaitEvent");
+    return CVB_OK;
+}
+
+static int order_leave(cvb_ctx *ctx, cudaStream_t s)
+{
+    if (!ctx->order_ev)
+        CU(cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming), "cudaEventCreate");
+    CU(cudaEventRecord(ctx->order_ev, s), "cudaEventRecord");
+    ctx->last_stream = s;
+    ctx->order_valid = true;
+    return CVB_OK;
+}
+
 static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int clip, double *out_p,
                       double *out_ll, int k_best, double *out_rows, void *stream)
 {
@@ -401,6 +430,8 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
     ctx->last_launches = 0;
     if (n_points == 0 && k_best <= 0)
         return CVB_OK;
+    if (int rc = order_enter(ctx, s))
+        return rc;
     const int np = ctx->desc.n_param;
     const long long nb = ctx->desc.n_bins;
     const bool p_dev = is_device_ptr(params);
@@ -444,7 +475,7 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
         }
         double *dl = (out_ll && l_dev) ? out_ll + off : ctx->d_ll;
         double *dq = out_p ? (q_dev ? out_p + off * nb : ctx->d_probs) : nullptr;
-        int rc = launch_loglik(ctx, lat, dp, n, clip, dl, dq, s);
+        int rc = launch_loglik(ctx, lat, nullptr, dp, n, clip, dl, dq, s);
         if (rc != CVB_OK)
             return rc;
         if (out_ll && !l_dev) {
@@ -455,6 +486,8 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
                     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
                 if (!ctx->copy_ev)
                     CU(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming), "cudaEventCreate");
+                if (!ctx->copy_done)
+                    CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming), "cudaEventCreate");
                 CU(cudaEventRecord(ctx->copy_ev, s), "cudaEventRecord");
                 CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev, 0), "cudaStreamWaitEvent");
                 cs = ctx->copy_stream;
@@ -462,6 +495,8 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
             }
             CU(cudaMemcpyAsync(out_ll + off, dl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, cs),
                "cudaMemcpyAsync(loglik)");
+            if (cs != s)
+                CU(cudaEventRecord(ctx->copy_done, cs), "cudaEventRecord");
         }
         if (out_p && !q_dev)
             CU(cudaMemcpyAsync(out_p + off * nb, dq, (size_t)n * nb * sizeof(double),
@@ -470,15 +505,19 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
         if (!all_dev && off + chunk < n_points)
             CU(cudaStreamSynchronize(s), "cudaStreamSynchronize"); /* staging is reused */
     }
+    bool rows_to_host = false;
     if (k_best > 0) {
         int rc = topk_device(ctx, lat, dl_all, dp_all, n_points, k_best, out_rows, s);
         if (rc != CVB_OK)
             return rc;
+        rows_to_host = !is_device_ptr(out_rows);
     }
-    if (!all_dev)
+    if (side_copy) /* the values left on the side stream: the main stream ends after them */
+        CU(cudaStreamWaitEvent(s, ctx->copy_done, 0), "cudaStreamWaitEvent");
+    if (int rc = order_leave(ctx, s))
+        return rc;
+    if (!all_dev || rows_to_host) /* one synchronisation per call, and only when something went to host memory */
         CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-    if (side_copy)
-        CU(cudaStreamSynchronize(ctx->copy_stream), "cudaStreamSynchronize");
     return CVB_OK;
 }
 
@@ -567,11 +606,9 @@ static int topk_device(cvb_ctx *ctx, const CvLattice &lat, const double *d_ll, c
     CU(cv_launch_gather_rows(lat, d_params, np, ctx->d_sel_ll, ctx->d_sel_idx, K, dr, s),
        "cv_gather_rows launch");
     ctx->last_launches += 1; /* the row gather */
-    if (!r_dev) {
+    if (!r_dev) /* the caller synchronises the stream before it returns */
         CU(cudaMemcpyAsync(out_rows, dr, (size_t)K * (1 + np) * sizeof(double), cudaMemcpyDeviceToHost, s),
            "cudaMemcpyAsync(rows)");
-        CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-    }
     return CVB_OK;
 }
 
@@ -586,6 +623,8 @@ extern "C" int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const 
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     const int np = ctx->desc.n_param;
     ctx->last_launches = 0;
+    if (int rc = order_enter(ctx, s))
+        return rc;
     const double *dl = ll, *dp = params;
     if (n_points > 0 && !is_device_ptr(ll)) {
         CU(grow(&ctx->d_ll, &ctx->cap_ll, (size_t)n_points), "cudaMalloc(loglik staging)");
@@ -602,7 +641,13 @@ extern "C" int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const 
     }
     CvLattice lat;
     memset(&lat, 0, sizeof(lat));
-    return topk_device(ctx, lat, dl, dp, n_points, k_best, out_rows, s);
+    if (int rc = topk_device(ctx, lat, dl, dp, n_points, k_best, out_rows, s))
+        return rc;
+    if (int rc = order_leave(ctx, s))
+        return rc;
+    if (!is_device_ptr(out_rows))
+        CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    return CVB_OK;
 }
 
 /* ---- lattice ------------------------------------------------------------------------------ */
@@ -621,6 +666,8 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     const int np = ctx->desc.n_param;
     ctx->timed_chunks = 0;
     ctx->last_launches = 0;
+    if (int rc = order_enter(ctx, s))
+        return rc;
     size_t total_vals = 0;
     double total_pts = 1.0;
     for (int a = 0; a < np; a++) {
@@ -650,6 +697,12 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     lat.first = first;
     lat.stride = stride;
     lat.block = block;
+    const double *axes_host[CV_MAX_PARAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    at = 0;
+    for (int a = 0; a < np; a++) {
+        axes_host[a] = axis_values + at;
+        at += (size_t)axis_len[a];
+    }
     const bool l_dev = out_ll && is_device_ptr(out_ll);
     double *dl = l_dev ? out_ll : nullptr;
     if (!dl) {
@@ -657,21 +710,41 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
         dl = ctx->d_ll;
     }
     if (count > 0) {
-        int rc = launch_loglik(ctx, lat, nullptr, count, 1, dl, nullptr, s);
+        int rc = launch_loglik(ctx, lat, axes_host, nullptr, count, 1, dl, nullptr, s);
         if (rc != CVB_OK)
             return rc;
     }
-    bool need_sync = false;
+    bool need_sync = false, side_copy = false;
     if (out_ll && !l_dev && count > 0) {
-        CU(cudaMemcpyAsync(out_ll, dl, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, s),
+        cudaStream_t cs = s;
+        if (k_best > 0 && count >= (1 << 16)) { /* the values leave next to the top-K, on a stream of their own */
+            if (!ctx->copy_stream)
+                CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            if (!ctx->copy_ev)
+                CU(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming), "cudaEventCreate");
+            if (!ctx->copy_done)
+                CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming), "cudaEventCreate");
+            CU(cudaEventRecord(ctx->copy_ev, s), "cudaEventRecord");
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev, 0), "cudaStreamWaitEvent");
+            cs = ctx->copy_stream;
+            side_copy = true;
+        }
+        CU(cudaMemcpyAsync(out_ll, dl, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, cs),
            "cudaMemcpyAsync(loglik)");
+        if (side_copy)
+            CU(cudaEventRecord(ctx->copy_done, cs), "cudaEventRecord");
         need_sync = true;
     }
     if (k_best > 0) {
         int rc = topk_device(ctx, lat, dl, nullptr, count, k_best, out_rows, s);
         if (rc != CVB_OK)
             return rc;
+        need_sync = need_sync || !is_device_ptr(out_rows);
     }
+    if (side_copy)
+        CU(cudaStreamWaitEvent(s, ctx->copy_done, 0), "cudaStreamWaitEvent");
+    if (int rc = order_leave(ctx, s))
+        return rc;
     if (need_sync)
         CU(cudaStreamSynchronize(s), "cudaStreamSynchronize");
     return CVB_OK;

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "kdevice.h"
@@ -97,7 +98,7 @@ __device__ __forceinline__ double cvf_clipped(const CvModelDesc &m, const double
 /* models.py:185-191: the first o in [1, max(hist)) with b(o) <= threshold, else max(hist).  The
  * geometric tail b(o) = many * base^(o-3) is searched from a closed-form estimate with the exact
  * predicate; anything unusual (base outside (0, 1), non-positive threshold) is scanned. */
-__device__ int cvf_cutoff(const CvModelDesc &m, double q1, double two, double many, double base)
+__host__ __device__ inline int cvf_cutoff(const CvModelDesc &m, double q1, double two, double many, double base)
 {
     const double thr = m.threshold;
     const int top = m.max_bin;
@@ -368,6 +369,81 @@ __global__ void __launch_bounds__(128) cvf_tile_table(int n_groups, CvfPlan pl)
         pl.t_order[tile] = tile;
         aoff += nkc;
     }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* The plan of a lattice, from its axes                                                          */
+/* ------------------------------------------------------------------------------------------- */
+/* A Cartesian lattice handed over as axes (cvb_lattice_eval; what grid.py's rounds and initial
+ * boxes are) needs no sort: its groups are the (c, e) index pairs, its q-runs the values of the q
+ * axis, and the cut-off O_thr (models.py:185-191) depends on (q1, q2, q) only -- |q1| |q2| |q|
+ * values for the whole batch instead of one per point.  The host evaluates those once per set of
+ * axes (the *template* of a group: its points by (q ascending, O_thr ascending, lattice order),
+ * their cut-offs, its tiles and their order by cost), the template travels to the device (a few
+ * KB, only when the axes changed), and one kernel writes the same tables the sort-based plan
+ * produces.  Every size is known on the host: no device -> host round trip, nothing blocks. */
+struct CvfLatticeDev { /* device copies of the template */
+    const int *perm;   /* [M] lattice offset inside the group of the point at sorted offset t */
+    const int *othr;   /* [M] its cut-off */
+    const int *tt_first, *tt_cnt, *tt_kmax, *tt_order; /* [nT] tiles of a group; by descending cost */
+};
+
+__global__ void __launch_bounds__(256)
+cvf_lattice_fill(CvfPlan pl, CvfLatticeDev T, int G, int M, int R, int nq, int nT, int omax, int items,
+                 long long wpg)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)G * M;
+    if (p < n) {
+        const int g = (int)(p / M), t = (int)(p - (long long)g * M);
+        const unsigned int idx = (unsigned int)((long long)g * M + T.perm[t]);
+        pl.idx[p] = idx;
+        pl.othr[idx] = T.othr[t];
+        const int run = t / R;
+        pl.head[p] = t == 0;
+        pl.head2[p] = t - run * R == 0;
+        pl.rid[p] = g * nq + run + 1;
+    }
+    if (p <= G) { /* per group; entry G closes the prefix tables */
+        pl.g_start[p] = (int)(p * M);
+        pl.g_rfirst[p] = (int)(p * nq);
+        pl.g_omax[p] = p < G ? omax + 1 : 0;
+        pl.item_start[p] = (int)(p * items);
+        pl.w_off[p] = p * wpg;
+        pl.tile_start[p] = (int)(p * nT);
+        pl.a_start[p] = 0;
+    }
+    if (p <= (long long)G * nq)
+        pl.r_start[p] = (int)(p * R);
+    if (p < (long long)G * nT) {
+        const int g = (int)(p / nT), tt = (int)(p - (long long)g * nT);
+        const int kmax = T.tt_kmax[tt];
+        pl.t_first[p] = g * M + T.tt_first[tt];
+        pl.t_cnt[p] = T.tt_cnt[tt];
+        pl.t_nkc[p] = (kmax + CVF_KC - 1) / CVF_KC;
+        pl.t_aoff[p] = 0;
+        pl.t_group[p] = g;
+    }
+    if (p == 0) {
+        pl.header[0] = G;
+        pl.header[1] = (long long)G * nT;
+        pl.header[2] = (long long)G * items;
+        pl.header[3] = (long long)G * wpg;
+        pl.header[4] = 0;
+        pl.header[5] = (long long)G * nq;
+    }
+}
+
+/* tiles of the groups g0 .. g1 - 1 by descending cost: every group has the same tiles */
+__global__ void __launch_bounds__(256)
+cvf_lattice_order(CvfLatticeDev T, int g0, int g1, int nT, int *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ng = g1 - g0;
+    if (i >= (long long)ng * nT)
+        return;
+    const int k = (int)(i / ng), g = g0 + (int)(i - (long long)k * ng);
+    out[i] = g * nT + T.tt_order[k];
 }
 
 /* largest g in [0, n) with start[g] <= x (start ascending, start[0] <= x), for a whole warp at once:
@@ -1624,6 +1700,13 @@ void cvf_release(CvFactorWork &wk)
     if (wk.d_scratch)
         cudaFree(wk.d_scratch);
     wk.d_scratch = nullptr;
+    if (wk.lattice.dev)
+        cudaFree(wk.lattice.dev);
+    if (wk.lattice.pinned)
+        cudaFreeHost(wk.lattice.pinned);
+    if (wk.lattice.uploaded)
+        cudaEventDestroy(wk.lattice.uploaded);
+    wk.lattice = CvfLatticeCache();
     for (cudaEvent_t &e : wk.ev)
         if (e) {
             cudaEventDestroy(e);
@@ -1645,7 +1728,113 @@ static size_t cvf_align(size_t x) { return (x + 255) & ~(size_t)255; }
             return e_;            \
     } while (0)
 
-cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
+/* ---- the template of a lattice's groups, on the host ---- */
+static double cvf_host_clip(const CvModelDesc &m, double v, int clip, int a)
+{
+    return clip ? cv_clip(v, m.lo[a], m.hi[a]) : v;
+}
+
+static void cvf_lattice_template(const CvModelDesc &m, int clip, const double *q1v, int n1, const double *q2v,
+                                 int n2, const double *qv, int nq, CvfLatticeCache &T)
+{
+    const int R = n1 * n2, M = R * nq;
+    T.M = M;
+    T.R = R;
+    T.nq = nq;
+    /* runs in ascending order of the clipped q (NaN first), as the sort key of the general plan
+     * orders them: neighbours then need about the same number of copies */
+    std::vector<int> qorder(nq);
+    std::vector<double> qc(nq);
+    for (int i = 0; i < nq; i++) {
+        qorder[i] = i;
+        const double v = cvf_host_clip(m, qv[i], clip, 4);
+        qc[i] = v > 0.0 ? (v < 1.0 ? v : 1.0) : 0.0;
+    }
+    std::stable_sort(qorder.begin(), qorder.end(), [&](int a, int b) { return qc[a] < qc[b]; });
+    std::vector<int> perm(M), othr(M);
+    std::vector<std::pair<int, int>> run(R); /* (cut-off, lattice offset) */
+    int omax = 0;
+    for (int r = 0; r < nq; r++) {
+        const int iq = qorder[r];
+        const double q = cvf_host_clip(m, qv[iq], clip, 4);
+        const double base = cv_sub(1.0, q);
+        for (int i1 = 0; i1 < n1; i1++) {
+            const double q1 = cvf_host_clip(m, q1v[i1], clip, 2);
+            for (int i2 = 0; i2 < n2; i2++) {
+                const double q2 = cvf_host_clip(m, q2v[i2], clip, 3);
+                const double two = cv_mul(cv_sub(1.0, q1), q2);                          /* models.py:195 */
+                const double many = cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), q); /* models.py:196 */
+                run[i1 * n2 + i2] = std::make_pair(cvf_cutoff(m, q1, two, many, base), (i1 * n2 + i2) * nq + iq);
+            }
+        }
+        std::stable_sort(run.begin(), run.end(),
+                         [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first < b.first; });
+        for (int t = 0; t < R; t++) {
+            othr[r * R + t] = run[t].first;
+            perm[r * R + t] = run[t].second;
+            omax = std::max(omax, run[t].first - 1);
+        }
+    }
+    T.omax = omax;
+    /* tiles: cvf_prefix_tiles over runs of R points each */
+    std::vector<int> tf, tc, tk;
+    for (int r = 0; r < nq;) {
+        const int first = r * R, rfirst = r;
+        int end = first, runs = 0;
+        while (r < nq && runs < CVF_PNQ) {
+            const int re = (r + 1) * R;
+            if (runs > 0 && re - first > CVF_PPB)
+                break;
+            end = re;
+            r++;
+            runs++;
+        }
+        for (int p = first; p < end; p += CVF_PSPLIT) {
+            const int cnt = std::min(CVF_PSPLIT, end - p);
+            int kmax = 0;
+            for (int rr = rfirst; rr < rfirst + runs; rr++) {
+                const int last = std::min((rr + 1) * R, p + cnt) - 1;
+                if (last >= p && last >= rr * R)
+                    kmax = std::max(kmax, othr[last] - 1);
+            }
+            tf.push_back(p);
+            tc.push_back(cnt);
+            tk.push_back(kmax);
+        }
+    }
+    const int nT = (int)tf.size();
+    T.nT = nT;
+    std::vector<int> order(nT);
+    for (int i = 0; i < nT; i++)
+        order[i] = i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return 4 * tc[a] + 3 * tk[a] > 4 * tc[b] + 3 * tk[b]; });
+    T.host.clear();
+    T.host.insert(T.host.end(), perm.begin(), perm.end());
+    T.host.insert(T.host.end(), othr.begin(), othr.end());
+    T.host.insert(T.host.end(), tf.begin(), tf.end());
+    T.host.insert(T.host.end(), tc.begin(), tc.end());
+    T.host.insert(T.host.end(), tk.begin(), tk.end());
+    T.host.insert(T.host.end(), order.begin(), order.end());
+}
+
+/* Can the batch be planned from its axes?  Points i of a group must be consecutive lattice indices
+ * starting at a multiple of M = |q1| |q2| |q|. */
+static bool cvf_lattice_aligned(const CvModelDesc &m, const CvLattice &lat, long long n, long long *M_out)
+{
+    if (!lat.enabled || lat.n_axes != 5 || m.n_param != 5)
+        return false;
+    const long long M = (long long)lat.len[2] * lat.len[3] * lat.len[4];
+    *M_out = M;
+    if (M <= 0 || M > 0x7fffffffLL || n % M)
+        return false;
+    if (lat.block % M == 0)
+        return true;
+    return lat.block == 1 && lat.stride == 1 && lat.first % M == 0;
+}
+
+cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *const *lat_axes_host,
+                     const double *params, long long n,
                      int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
                      double min_group, double min_run, int kernel_mode, bool counts_first, cudaStream_t stream,
@@ -1782,26 +1971,109 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         wk.launches += 17; /* K0, radix sort (10), heads, one scan (2), starts, counts, group scan */
         return cudaSuccess;
     };
-    /* ordering for the prefix kernel first: it also tells how many q-runs the batch has */
+    /* ---- a lattice handed over as axes: the plan follows from the axes (no sort, no sync) ---- */
     int prefix = kernel_mode != 1;
-    CVF_CK(build_plan(prefix));
-    wk.n_groups = wk.h_header[0];
-    wk.n_runs = wk.h_header[5];
-    if (wk.n_groups <= 0 || (double)n < min_group * (double)wk.n_groups)
-        return cudaSuccess; /* too little sharing: the per-point kernel is the better tool */
-    if (prefix && kernel_mode == 0 && (double)n < min_run * (double)wk.n_runs) {
-        prefix = 0; /* few points per q-run: the GEMM shares the profiles between all points of a group */
-        CVF_CK(build_plan(0));
+    long long latM = 0;
+    bool analytic = false;
+    CvfLatticeDev TD;
+    memset(&TD, 0, sizeof(TD));
+    long long n_groups = 0, n_tiles = 0, n_items = 0, w_total = 0, a_total = 0;
+    if (prefix && lat_axes_host && cvf_lattice_aligned(m, lat, n, &latM) && (double)latM >= min_group &&
+        (double)(lat.len[2] * (long long)lat.len[3]) >= (kernel_mode == 0 ? min_run : 1.0)) {
+        CvfLatticeCache &T = wk.lattice;
+        const int n1 = lat.len[2], n2 = lat.len[3], nq = lat.len[4];
+        std::vector<double> key;
+        key.reserve(4 + n1 + n2 + nq);
+        key.push_back((double)clip);
+        key.push_back((double)n1);
+        key.push_back((double)n2);
+        key.push_back((double)nq);
+        key.insert(key.end(), lat_axes_host[2], lat_axes_host[2] + n1);
+        key.insert(key.end(), lat_axes_host[3], lat_axes_host[3] + n2);
+        key.insert(key.end(), lat_axes_host[4], lat_axes_host[4] + nq);
+        const bool same = key.size() == T.key.size() && T.dev &&
+                          memcmp(key.data(), T.key.data(), key.size() * sizeof(double)) == 0;
+        if (!same) {
+            cvf_lattice_template(m, clip, lat_axes_host[2], n1, lat_axes_host[3], n2, lat_axes_host[4], nq, T);
+            const size_t ints = T.host.size();
+            if (ints > T.dev_cap) {
+                if (T.dev)
+                    cudaFree(T.dev);
+                T.dev = nullptr;
+                T.dev_cap = 0;
+                CVF_CK(cudaMalloc((void **)&T.dev, ints * sizeof(int)));
+                T.dev_cap = ints;
+            }
+            if (!T.uploaded)
+                CVF_CK(cudaEventCreateWithFlags(&T.uploaded, cudaEventDisableTiming));
+            else
+                CVF_CK(cudaEventSynchronize(T.uploaded)); /* the staging buffer is free again */
+            if (ints > T.pinned_cap) {
+                if (T.pinned)
+                    cudaFreeHost(T.pinned);
+                T.pinned = nullptr;
+                T.pinned_cap = 0;
+                CVF_CK(cudaMallocHost((void **)&T.pinned, ints * sizeof(int)));
+                T.pinned_cap = ints;
+            }
+            memcpy(T.pinned, T.host.data(), ints * sizeof(int));
+            T.key.clear(); /* not valid until the copy is enqueued */
+            CVF_CK(cudaMemcpyAsync(T.dev, T.pinned, ints * sizeof(int), cudaMemcpyHostToDevice, stream));
+            CVF_CK(cudaEventRecord(T.uploaded, stream));
+            T.key = key;
+        }
+        const int M = T.M, nT = T.nT;
+        const int G = (int)(n / M);
+        const int items = (T.omax + CVF_KC - 1) / CVF_KC;
+        const long long wpg = (long long)items * CVF_KC * slots_padded;
+        TD.perm = T.dev;
+        TD.othr = T.dev + M;
+        TD.tt_first = T.dev + 2 * (size_t)M;
+        TD.tt_cnt = TD.tt_first + nT;
+        TD.tt_kmax = TD.tt_cnt + nT;
+        TD.tt_order = TD.tt_kmax + nT;
+        pl.prefix = 1;
+        pl.tile_points = CVF_M;
+        pl.idx_sorted = pl.idx;
+        const long long work = std::max<long long>(n, (long long)G * T.nq + 1);
+        cvf_lattice_fill<<<(unsigned int)((work + tb - 1) / tb), tb, 0, stream>>>(pl, TD, G, M, T.R, T.nq, nT, T.omax,
+                                                                                items, wpg);
+        CVF_CK(cudaGetLastError());
+        wk.launches += 1;
+        analytic = true;
+        n_groups = G;
+        n_tiles = (long long)G * nT;
+        n_items = (long long)G * items;
+        w_total = (long long)G * wpg;
+        a_total = 0;
+        wk.n_groups = G;
+        wk.n_runs = (long long)G * T.nq;
     }
-    const long long n_groups = wk.h_header[0], n_tiles = wk.h_header[1], n_items = wk.h_header[2];
-    const long long w_total = wk.h_header[3], a_total = wk.h_header[4];
+    wk.analytic = analytic ? 1 : 0;
+    if (!analytic) {
+        /* ordering for the prefix kernel first: it also tells how many q-runs the batch has */
+        CVF_CK(build_plan(prefix));
+        wk.n_groups = wk.h_header[0];
+        wk.n_runs = wk.h_header[5];
+        if (wk.n_groups <= 0 || (double)n < min_group * (double)wk.n_groups)
+            return cudaSuccess; /* too little sharing: the per-point kernel is the better tool */
+        if (prefix && kernel_mode == 0 && (double)n < min_run * (double)wk.n_runs) {
+            prefix = 0; /* few points per q-run: the GEMM shares the profiles between all points of a group */
+            CVF_CK(build_plan(0));
+        }
+        n_groups = wk.h_header[0];
+        n_tiles = wk.h_header[1];
+        n_items = wk.h_header[2];
+        w_total = wk.h_header[3];
+        a_total = wk.h_header[4];
+        cvf_tile_table<<<(unsigned int)((n_groups + 127) / 128), 128, 0, stream>>>((int)n_groups, pl);
+        CVF_CK(cudaGetLastError());
+        wk.launches++;
+    }
     wk.n_tiles = n_tiles;
     wk.n_items = n_items;
     wk.w_doubles = w_total;
     wk.prefix = prefix;
-    cvf_tile_table<<<(unsigned int)((n_groups + 127) / 128), 128, 0, stream>>>((int)n_groups, pl);
-    CVF_CK(cudaGetLastError());
-    wk.launches++;
 
     /* ---- group ranges whose profiles fit the workspace ---- */
     std::vector<int> cut; /* group boundaries */
@@ -1813,11 +2085,20 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
         h_item.resize(n_groups + 1);
         h_achunk.resize(n_groups + 1);
         h_woff.resize(n_groups + 1);
+        if (analytic) { /* every group has the same tiles, items and profile size */
+            for (long long g = 0; g <= n_groups; g++) {
+                h_tile[g] = (int)(g * (n_tiles / n_groups));
+                h_item[g] = (int)(g * (n_items / n_groups));
+                h_achunk[g] = 0;
+                h_woff[g] = g * (w_total / n_groups);
+            }
+        } else {
         CVF_CK(cudaMemcpyAsync(h_tile.data(), pl.tile_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaMemcpyAsync(h_item.data(), pl.item_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaMemcpyAsync(h_achunk.data(), pl.a_start, (n_groups + 1) * 4, cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaMemcpyAsync(h_woff.data(), pl.w_off, (n_groups + 1) * 8, cudaMemcpyDeviceToHost, stream));
         CVF_CK(cudaStreamSynchronize(stream));
+        }
         int g0 = 0;
         while (g0 < n_groups) {
             int g1 = g0 + 1;
@@ -1895,11 +2176,18 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *p
                 wk.launches++;
             }
             /* tiles of the range by descending cost: the long ones start first */
-            cub::DoubleBuffer<int> dk(pl.t_key + tile0, pl.t_key_alt + tile0);
-            cub::DoubleBuffer<int> dv(pl.t_order + tile0, pl.t_order_alt + tile0);
-            size_t tb_ = tmp_bytes;
-            CVF_CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb_, dk, dv, tiles, 0, 32, stream));
-            pl.t_sorted = dv.Current();
+            if (analytic) {
+                cvf_lattice_order<<<(unsigned int)((tiles + tb - 1) / tb), tb, 0, stream>>>(
+                    TD, g0, g1, (int)(n_tiles / n_groups), pl.t_order_alt + tile0);
+                CVF_CK(cudaGetLastError());
+                pl.t_sorted = pl.t_order_alt + tile0;
+            } else {
+                cub::DoubleBuffer<int> dk(pl.t_key + tile0, pl.t_key_alt + tile0);
+                cub::DoubleBuffer<int> dv(pl.t_order + tile0, pl.t_order_alt + tile0);
+                size_t tb_ = tmp_bytes;
+                CVF_CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb_, dk, dv, tiles, 0, 32, stream));
+                pl.t_sorted = dv.Current();
+            }
             if (wk.timed && i + 2 == cut.size())
                 CVF_CK(cudaEventRecord(wk.ev[2], stream));
             int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;

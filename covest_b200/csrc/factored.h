@@ -23,7 +23,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "kernels.h"
+
+/* The template of a lattice's groups (factored.cu, "The plan of a lattice"): computed on the host
+ * from the (q1, q2, q) axes, kept until the axes change, mirrored on the device. */
+struct CvfLatticeCache {
+    std::vector<double> key; /* clip flag, axis lengths and values the template was made from */
+    std::vector<int> host;   /* perm[M], othr[M], then tt_first, tt_cnt, tt_kmax, tt_order [nT each] */
+    int M = 0, R = 0, nq = 0, nT = 0, omax = 0;
+    int *dev = nullptr;
+    size_t dev_cap = 0;      /* ints */
+    int *pinned = nullptr;   /* staging of the upload */
+    size_t pinned_cap = 0;
+    cudaEvent_t uploaded = nullptr; /* the last upload has left the staging buffer */
+};
 
 struct CvFactorWork {
     void *plan = nullptr; /* sort keys, indices, group tables, cub scratch */
@@ -41,6 +56,8 @@ struct CvFactorWork {
     long long n_groups = 0, n_tiles = 0, n_items = 0, w_doubles = 0, n_runs = 0;
     int prefix = 0; /* 1: the prefix kernel ran, 0: the GEMM */
     int launches = 0;
+    int analytic = 0; /* 1: the plan came from the lattice axes (no sort, no host synchronisation) */
+    CvfLatticeCache lattice;
     double gemm_fma = 0.0; /* FMAs the tiles of K2 issue (128 rows x padded copies x padded slots) */
 };
 
@@ -54,14 +71,15 @@ bool cvf_supported(const CvModelDesc &m);
  * pairs; `step_mask` = per 32 slots, bit 2 nt + c set when one of the slots 8 nt + 2 q + c, q < 4,
  * has a count (cvf_step_masks); `log_tab` = cv_log_table.  w_limit = largest profile workspace in
  * doubles; larger batches run in several group ranges. */
-cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
+/* lat_axes_host: the lattice axes in host memory (n_param pointers) when lat.enabled, else NULL */
+cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *const *lat_axes_host,
+                     const double *params, long long n,
                      int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
                      double min_group, double min_run, int kernel_mode, bool counts_first, cudaStream_t stream,
                      int *used);
 
 /* host: the step masks of a slot_h table (length a multiple of 32) */
-#include <vector>
 static inline std::vector<int> cvf_step_masks(const std::vector<double> &slot_h)
 {
     std::vector<int> out(slot_h.size() / 32, 0);

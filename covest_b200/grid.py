@@ -97,7 +97,26 @@ def optimize_grid(fn, initial_guess, bounds=None, maximize=False, fix=None,
             rounds += 1
             diff = 0.0
             batch = getattr(fn, 'batch', None)
-            if batch is not None:
+            lattice_best = getattr(fn, 'lattice_best', None) if not maximize else None
+            found = None
+            if lattice_best is not None:
+                # the round stays on the device: candidates generated there from the axes, the
+                # arg-min taken there, one row comes back.  The sequential bookkeeping of
+                # grid.py:65-69 adds up the strict improvements in candidate order, which
+                # telescopes to (best before the round) - (best of the round), and keeps the FIRST
+                # candidate that attains the minimum -- the tie-break of the device's top-K.
+                axes = grid_axes(best_args, step, depth, bounds, fix)
+                size = int(np.prod([len(a) for a in axes]))
+                verbose_print('Iter : {}, Grid size: {}'.format(rounds, size))
+                with running_time('grid iteration'):
+                    found = lattice_best(axes) if size else (float('inf'), None)
+            if found is not None:
+                value, point = found
+                if point is not None and value < best_val:
+                    diff += best_val - value
+                    best_val = value
+                    best_args = point
+            elif batch is not None:
                 # the whole round as one array and one launch; the bookkeeping of grid.py:65-69
                 # (strict improvements in candidate order, its use of the raw value included) on
                 # the running minimum

@@ -67,6 +67,26 @@ def allgather_rows(rows):
     return out
 
 
+def to_comm(array, device=None):
+    """A numpy block as a tensor where the collectives of the current backend want it (`device`:
+    a CUDA device under NCCL, None = host under gloo or without a process group)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64))
+    return t.to(device) if device is not None else t
+
+
+def broadcast_rows(array, device=None, src=0):
+    """Rank `src`'s float64 block on every rank (same shape everywhere); a no-op without a process
+    group.  Used for the random multi-start points, which every rank draws from its own unseeded
+    `random` (covest/grid.py:95-110)."""
+    rank, w = world()
+    if w == 1:
+        return np.asarray(array, dtype=np.float64)
+    t = to_comm(array, device)
+    _dist().broadcast(t, src=src)
+    return t.cpu().numpy()
+
+
 def merge_topk(rows, k_best):
     """The k_best best rows (column 0 = log-likelihood, larger is better) of a stacked block,
     best first.  NaN and padding (-inf) sort last.  Ties are broken by the parameter columns in

@@ -47,10 +47,22 @@ def main():
     mine = parallel.split_starts(rows)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine.numpy().tolist())
+
+    # the refinement after the all-gather (CoverageEstimator.refine_starts): every rank refines its
+    # share of the global best rows with the lock-step optimiser, the optima are all-gathered
+    from covest_b200.covest import CoverageEstimator
+    from tests.test_host_logic import ORepeats
+    est = CoverageEstimator(ORepeats(21, 100, case_hist(case), 0, max_error=8), optimizer='lockstep')
+    x, fun, ok, table = est.refine_starts(rows.numpy()[:4, 1:])
+    tables = [None] * world
+    dist.all_gather_object(tables, table.tolist())
+    drawn = parallel.broadcast_rows(np.full((2, 3), float(rank + 5)))
     if rank == 0:
         with open(out_path, 'w') as f:
             json.dump({'world': world, 'rows': rows.numpy().tolist(), 'starts': gathered,
-                       'slice': list(parallel.shard_blocked(total, block, rank, world))}, f)
+                       'slice': list(parallel.shard_blocked(total, block, rank, world)),
+                       'refined_x': [float(v) for v in x], 'refined_fun': fun, 'refined_ok': ok,
+                       'tables': tables, 'broadcast': drawn.tolist(), 'launches': est.launches}, f)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -339,3 +339,68 @@ def test_grid_rounds_as_arrays_keep_the_order_of_itertools_product():
     assert tuple(rows[-1]) == list(itertools.product(*axes))[-1]
     assert grid._product_rows([[1.0], [], [2.0]]).shape == (0, 3)
     assert grid.grid_candidates([10.0, 0.05], 1.1, 1) == list(itertools.product(*grid.grid_axes([10.0, 0.05], 1.1, 1)))
+
+
+# ---- lock-step multi-start, device grid rounds (additions) -----------------------------------
+def test_lockstep_optimizer_reaches_the_polished_optimum_from_every_start():
+    """c = 10.018595075, e = 0.0499913066, f = 3678682.5783989 on the
+    reference's fixture; all starts advance per launch."""
+    from covest_b200.optimizer import lockstep_minimize
+    hist = fixture('e05')
+    ce = CoverageEstimator(OBasic(21, 100, hist, 0, max_error=8))
+    random.seed(7)
+    starts = grid.initial_grid([8.77, 0.0469], count=8, bounds=ce.bounds)
+    results, launches = lockstep_minimize(ce.likelihood_batch, starts, ce.bounds)
+    assert launches <= 2 * 15 + 1
+    for r in results:
+        assert r.success
+        assert r.x[0] == pytest.approx(10.018595075, rel=2e-7) and r.x[1] == pytest.approx(0.0499913066, rel=2e-7)
+        assert r.fun == pytest.approx(3678682.5783989, rel=1e-12)
+    # a fixed coordinate stays, bounds hold
+    results, _ = lockstep_minimize(ce.likelihood_batch, [[9.0, 0.04]], ce.bounds, fixed=[False, True])
+    assert results[0].x[1] == 0.04 and results[0].fun > 3678682.58
+    results, _ = lockstep_minimize(ce.likelihood_batch, [[9.0, 0.04]], [(0.01, 9.5), (0, .5)])
+    assert results[0].x[0] == 9.5
+
+
+def test_refine_starts_and_lockstep_compute_coverage():
+    hist = fixture('e05')
+    model = ORepeats(21, 100, hist, 0, max_error=8)
+    ce = CoverageEstimator(model, optimizer='lockstep')
+    random.seed(3)
+    x, ok = ce.compute_coverage([8.77, 0.0469, .65, .5, .5], starting_points=4)
+    assert ok and ce.launches < 200
+    # at least as good as the stock single-start run of the reference (SURVEY.md section 8(c))
+    assert ce.likelihood_f(x) <= 3678677.5264701946 + 1e-3
+    xs, fun, ok2, table = ce.refine_starts([[10.0, .05, .9, .5, .5], [9.0, .04, .5, .5, .5]])
+    assert table.shape == (2, 7) and fun == table[:, 0].min() and list(xs) == list(table[np.argmin(table[:, 0]), 2:])
+
+
+def test_grid_round_through_lattice_best_equals_the_sequential_bookkeeping():
+    """optimize_grid with an objective that offers lattice_best (the device path: only the best
+    candidate of a round comes back) walks the same centres as the reference's bookkeeping."""
+    g = HOST['optimize_grid_toy']
+
+    def toy(x):
+        return (x[0] - 7.3) ** 2 + 40 * (x[1] - 0.031) ** 2 + 0.5 * (x[0] - 7.3) * (x[1] - 0.031)
+
+    rounds = []
+
+    class OnDevice:
+        def __call__(self, x):
+            return toy(x)
+
+        def batch(self, pts):
+            return [toy(p) for p in pts]
+
+        def lattice_best(self, axes):
+            import itertools
+            cands = list(itertools.product(*axes))
+            vals = [toy(c) for c in cands]
+            i = int(np.argmin(vals))  # first minimum
+            rounds.append(len(cands))
+            return vals[i], tuple(cands[i])
+
+    bounds = [tuple(b) for b in g['bounds']]
+    assert list(grid.optimize_grid(OnDevice(), g['start'], bounds=bounds)) == g['result']
+    assert len(rounds) >= 17 and max(rounds) == 36

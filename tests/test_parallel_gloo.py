@@ -51,7 +51,7 @@ def test_world_size_two_equals_single_process(tmp_path):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
            '--master-addr', '127.0.0.1', '--master-port', '29533',
            os.path.join(ROOT, 'tests', 'dist_worker.py'), out]
-    subprocess.run(cmd, check=True, env=env, timeout=300, cwd=ROOT,
+    subprocess.run(cmd, check=True, env=env, timeout=600, cwd=ROOT,
                    stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     with open(out) as f:
         res = json.load(f)
@@ -70,3 +70,13 @@ def test_world_size_two_equals_single_process(tmp_path):
     # the refinement starts are dealt round-robin and cover the best rows exactly once
     starts = [np.array(s) for s in res['starts']]
     assert np.array_equal(starts[0], rows[0::2]) and np.array_equal(starts[1], rows[1::2])
+    # refinement of the best rows, sharded: the same optima as one process refining all of them
+    from covest_b200.covest import CoverageEstimator
+    from tests.test_host_logic import ORepeats
+    est = CoverageEstimator(ORepeats(21, 100, case_hist(case), 0, max_error=8), optimizer='lockstep')
+    x, fun, ok, table = est.refine_starts(rows[:4, 1:])
+    assert res['tables'][0] == res['tables'][1]                  # every rank holds the same table
+    assert np.array_equal(np.array(res['tables'][0]), table)    # ... and it is the single-process one
+    assert res['refined_x'] == [float(v) for v in x] and res['refined_fun'] == fun and res['refined_ok'] == ok
+    assert fun <= -rows[0, 0]                                    # refinement improves on the best lattice point
+    assert res['broadcast'] == [[5.0] * 3] * 2                   # rank 0's block
