@@ -8,13 +8,16 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/covest_b200.h"
 #include "cvtables.h"
 #include "factored.h"
+#include "faithful.h"
 #include "kernels.h"
 
 #define CVB_CHUNK_POINTS (1LL << 22) /* staging granularity for host-resident batches */
@@ -71,6 +74,9 @@ struct cvb_ctx {
     long long min_points = 2048; /* auto: batches below this go straight to the per-point kernel */
     int last_path = 0;         /* 1 per-point, 2 factored (GEMM), 3 factored (prefix kernel) */
     double min_run = 4.0;      /* auto: points per q-run below which the GEMM runs instead of the prefix kernel */
+    /* re-evaluation of marked points (faithful.h) */
+    CvFaithTables faith = {nullptr, nullptr, 0, nullptr};
+    unsigned long long *d_fixed = nullptr; /* marked points of the most recent call */
     std::string err;
 };
 
@@ -301,10 +307,33 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         }
         if (const char *pm = getenv("COVEST_B200_PATH"))
             c->path_mode = !strcmp(pm, "direct") ? 1 : !strcmp(pm, "factored") ? 2 : !strcmp(pm, "gemm") ? 3
-                           : !strcmp(pm, "prefix") ? 4 : 0;
+                           : !strcmp(pm, "prefix") ? 4 : !strcmp(pm, "faithful") ? 5 : 0;
         if (const char *wl = getenv("COVEST_B200_PROFILE_MIB"))
             if (atoll(wl) > 0)
                 c->w_limit = (size_t)atoll(wl) * (1 << 20) / sizeof(double);
+        {
+            std::vector<std::pair<int, double>> kv(n_bins);
+            for (int b = 0; b < n_bins; b++)
+                kv[b] = std::make_pair((int)bin_j[b], bin_h[b]);
+            std::sort(kv.begin(), kv.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) {
+                return a.first < b.first;
+            });
+            std::vector<int> fk(n_bins);
+            std::vector<double> fc(n_bins);
+            for (int b = 0; b < n_bins; b++) {
+                fk[b] = kv[b].first;
+                fc[b] = kv[b].second;
+            }
+            if ((e = upload(c, fk, &c->faith.key)) != cudaSuccess) break;
+            if ((e = upload(c, fc, &c->faith.cnt)) != cudaSuccess) break;
+            c->faith.n = n_bins;
+            void *scr = nullptr;
+            if ((e = cudaMalloc(&scr, (size_t)cv_faithful_warps(c->n_sm) * (n_bins > 0 ? n_bins : 1) * sizeof(double))) != cudaSuccess) break;
+            c->owned.push_back(scr);
+            c->faith.scratch = (double *)scr;
+            if ((e = cudaMalloc((void **)&c->d_fixed, sizeof(unsigned long long))) != cudaSuccess) break;
+            c->owned.push_back(c->d_fixed);
+        }
         if ((e = cudaMalloc((void **)&c->d_counter, sizeof(unsigned long long))) != cudaSuccess) break;
         if ((e = cudaMalloc((void **)&c->d_sink, 64)) != cudaSuccess) break;
     } while (0);
@@ -367,8 +396,14 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *const
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks], s), "cudaEventRecord");
     int used = 0;
     const bool forced = ctx->path_mode >= 2;
-    const bool try_factored = !d_probs && ctx->path_mode != 1 && cvf_supported(ctx->desc) &&
+    const bool faithful_only = ctx->path_mode == 5 && !d_probs;
+    const bool try_factored = !d_probs && ctx->path_mode != 1 && !faithful_only && cvf_supported(ctx->desc) &&
                               (forced || n >= ctx->min_points);
+    if (faithful_only) {
+        CU(cv_launch_mark_all(d_ll, n, s), "cv_mark_all_kernel launch");
+        ctx->last_launches++;
+        used = 3;
+    }
     if (try_factored) {
         ctx->fw.timed = ctx->timing;
         CU(cvf_eval(ctx->desc, lat, lat_axes_host, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->d_step_mask,
@@ -385,6 +420,10 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *const
         ctx->last_launches++;
     }
     ctx->last_path = used ? 1 + used : 1;
+    /* points whose value hinges on the reference's subnormal roundings: again, term by term */
+    CU(cv_launch_faithful(ctx->desc, lat, d_params, n, clip, d_ll, ctx->faith, ctx->n_sm, ctx->d_fixed, s),
+       "cv_faithful_kernel launch");
+    ctx->last_launches++;
     if (timed) {
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks + 1], s), "cudaEventRecord");
         ctx->timed_chunks++;
@@ -400,6 +439,12 @@ static int order_enter(cvb_ctx *ctx, cudaStream_t s)
 {
     if (ctx->order_valid && ctx->last_stream != s)
         CU(cudaStreamWaitEvent(s, ctx->order_ev, 0), "cudaStreamWaitEvent");
+    return CVB_OK;
+}
+
+static int reset_fixed(cvb_ctx *ctx, cudaStream_t s)
+{
+    CU(cudaMemsetAsync(ctx->d_fixed, 0, sizeof(unsigned long long), s), "cudaMemsetAsync");
     return CVB_OK;
 }
 
@@ -431,6 +476,8 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
     if (n_points == 0 && k_best <= 0)
         return CVB_OK;
     if (int rc = order_enter(ctx, s))
+        return rc;
+    if (int rc = reset_fixed(ctx, s))
         return rc;
     const int np = ctx->desc.n_param;
     const long long nb = ctx->desc.n_bins;
@@ -668,6 +715,8 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     ctx->last_launches = 0;
     if (int rc = order_enter(ctx, s))
         return rc;
+    if (int rc = reset_fixed(ctx, s))
+        return rc;
     size_t total_vals = 0;
     double total_pts = 1.0;
     for (int a = 0; a < np; a++) {
@@ -766,9 +815,9 @@ extern "C" int cvb_set_path(cvb_ctx *ctx, int mode)
 {
     if (!ctx)
         return CVB_EINVAL;
-    if (mode < 0 || mode > 4)
-        return fail(ctx, CVB_EINVAL, "path mode must be 0 (auto), 1 (per-point), 2 (factored), 3 (factored, GEMM) "
-                                     "or 4 (factored, prefix kernel)");
+    if (mode < 0 || mode > 5)
+        return fail(ctx, CVB_EINVAL, "path mode must be 0 (auto), 1 (per-point), 2 (factored), 3 (factored, GEMM), "
+                                     "4 (factored, prefix kernel) or 5 (term by term)");
     ctx->path_mode = mode;
     return CVB_OK;
 }
@@ -780,7 +829,13 @@ extern "C" int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out)
     CU(cudaSetDevice(ctx->device), "cudaSetDevice");
     double v[CVB_PATH_INFO_LEN] = {0};
     v[0] = ctx->last_path;
+    {
+        unsigned long long fixed = 0; /* waits for the work queued on the device */
+        CU(cudaMemcpy(&fixed, ctx->d_fixed, sizeof(fixed), cudaMemcpyDeviceToHost), "cudaMemcpy");
+        v[9] = (double)fixed;
+    }
     if (ctx->last_path >= 2) {
+        v[10] = (double)ctx->fw.analytic;
         const CvFactorWork &w = ctx->fw;
         v[1] = (double)w.n_groups;
         v[2] = (double)w.n_tiles;

@@ -259,14 +259,15 @@ CV_HD cv_dd cv_log_dd(double x)
 #define CV_LOG_N 128
 #define CV_LOG_OFF 0x3fe6000000000000ULL
 
-CV_HD double cv_log_tab(double x, const double *tab)
+/* kshift: log(x * 2^-kshift) -- exact, the shift joins the exponent */
+CV_HD double cv_log_tab(double x, const double *tab, int kshift = 0)
 {
     if (!(x >= 0x1p-1022) || !(x < INFINITY))
-        return log(x);
+        return cv_sub(log(x), cv_mul((double)kshift, 0x1.62e42fefa39efp-1));
     const uint64_t ix = cv_bits(x);
     const uint64_t tmp = ix - CV_LOG_OFF;
     const int i = (int)((tmp >> 45) & (CV_LOG_N - 1));
-    const int k = (int)((int64_t)tmp >> 52);
+    const int k = (int)((int64_t)tmp >> 52) - kshift;
     const double z = cv_from_bits(ix - (tmp & 0xfff0000000000000ULL));
     const double invc = tab[2 * i], logc = tab[2 * i + 1];
     const double r = cv_fma(z, invc, -1.0);

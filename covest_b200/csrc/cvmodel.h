@@ -27,6 +27,30 @@
  * out again.  420 leaves room both ways for chains of up to 64 bins and rates up to the
  * reference's own overflow limit (~11 360). */
 #define CV_SCALE_LOG 420.0
+
+/* Probabilities leave the accumulators scaled by 2^128 (slot_mult carries the factor): they stay
+ * normal numbers down to p = 2^-1150, so a kernel can tell three classes of a bin with a count:
+ *
+ *   p >= 2^-1000   every intermediate of the reference's evaluation (c:33 rounds each term to a
+ *                  double, models.py:236-239 each product) that matters is a normal number: the
+ *                  fast arithmetic of the kernels agrees with it to ~1e-12
+ *   p <  2^-1088   the reference's value is exactly 0 (a non-zero result needs a product that
+ *                  rounds to at least one unit 2^-1074 of the subnormal grid, which takes a true
+ *                  value of at least 2^-1077): log-likelihood -inf
+ *   in between     the reference's per-term roundings to the subnormal grid decide the value
+ *                  (one unit is ln 2 in log p): the bin contributes the sentinel CV_BAND_LOG, which
+ *                  makes the point's value < CV_BAND_LL, and such points are re-evaluated term by
+ *                  term, rounding where the reference rounds (faithful.cu).  They are far-off
+ *                  points (log-likelihood ~ 700 x their count below any plausible one), about one
+ *                  in 10^4 of a wide lattice. */
+#define CV_PSCALE 0x1p128
+#define CV_PUNSCALE 0x1p-128
+#define CV_PSCALE_EXP 128
+#define CV_PSCALE_LOG 0x1.62e42fefa39efp+6 /* 128 ln 2 */
+#define CV_P_ZERO 0x1p-960  /* scaled: p < 2^-1088 */
+#define CV_P_BAND 0x1p-872  /* scaled: p < 2^-1000 */
+#define CV_BAND_LOG (-1.0e280)
+#define CV_BAND_LL (-1.0e270)
 #define CV_DEAD_TERM (-1.0e30)
 #define CV_MAX_ERR 64
 
@@ -156,6 +180,16 @@ CV_HD double cv_seed(double j0, double head_h, double head_l, double lh, double 
     double el = cv_sub(lo, cv_sub(eh, s2.hi));
     double u = exp(eh);
     return cv_mul(cv_fma(u, el, u), f);
+}
+
+/* utils.py:32-35 safe_log of a probability that arrives scaled by 2^128, with the classes above */
+CV_HD double cv_log_scaled(double ps)
+{
+    if (ps >= CV_P_BAND)
+        return cv_sub(log(ps), CV_PSCALE_LOG);
+    if (ps != ps)
+        return ps;
+    return ps >= CV_P_ZERO ? CV_BAND_LOG : -INFINITY;
 }
 
 /* models.py:103-107 for the last step: total mass, tail term */

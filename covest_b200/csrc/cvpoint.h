@@ -559,7 +559,7 @@ CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, int ngroups_bl
                 h[u] = cnt[e];
                 p[u] = cv_mul(F.u.spill[cv_spill_index<NA>(e)], mu);
                 if (out_probs && mu != 0.0)
-                    out_probs[bin[e]] = p[u];
+                    out_probs[bin[e]] = cv_mul(p[u], CV_PUNSCALE); /* p[] stays scaled by 2^128 */
             }
             if (mu == 0.0) { /* a bin that is not in hist (p may be NaN * 0) */
                 p[u] = 0.0;
@@ -575,7 +575,7 @@ CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, int ngroups_bl
         for (int u = 0; u < U; u++) {
             const bool counted = h[u] != 0.0; /* models.py:106 `if h` */
             if (CV_WARP_ANY(counted)) {
-                double lg = (p[u] <= 0.0) ? -INFINITY : log(p[u]); /* utils.py:32-35 safe_log */
+                double lg = cv_log_scaled(p[u]); /* utils.py:32-35 safe_log */
                 if (counted)
                     sum[u] = cv_add(sum[u], cv_mul(h[u], lg));
             }
@@ -587,7 +587,8 @@ CV_HD void cv_w_epilogue(int lane, const CvModelDesc &m, int blk, int ngroups_bl
 /* models.py:103-107 */
 CV_HD double cv_point_finish(const CvModelDesc &m, const CvPartial &part)
 {
-    double mass = cv_add(part.mass_h, part.mass_l);
+    /* the partial sums are sums of probabilities scaled by 2^128 */
+    double mass = cv_add(cv_mul(part.mass_h, CV_PUNSCALE), cv_mul(part.mass_l, CV_PUNSCALE));
     if (!(mass < 1.0))
         mass = 1.0; /* min(1, fsum(...)): keeps the 1 unless the sum is smaller (also for NaN) */
     return cv_finish_loglik(part.sum, mass, m.tail);

@@ -158,7 +158,8 @@ static inline std::string cv_build_tables(int n_bins, const int *bin_j, const do
             int mrow = d / CV_W, i = d % CV_W;
             long double run = cv_rising(heads[g] + (long)CV_W * mrow, i);
             size_t slot = ((size_t)g * na + mrow) * CV_W + i;
-            T.slot_mult[slot] = (double)(unscale * row_scale[(size_t)g * na + mrow] / run);
+            /* times 2^128: see CV_PSCALE (cvmodel.h) */
+            T.slot_mult[slot] = (double)(unscale * row_scale[(size_t)g * na + mrow] / run * (long double)CV_PSCALE);
             T.slot_h[slot] = bin_h ? bin_h[keys[b].second] : 0.0;
             T.slot_bin[slot] = keys[b].second;
         }

@@ -78,59 +78,6 @@ bool cvf_supported(const CvModelDesc &m)
     return m.model_kind == 1 && m.n_err <= 32 && m.max_bin < (1 << CVF_OBITS) - CV_COPY_PAD;
 }
 
-__device__ __forceinline__ void cvf_raw_row(const CvModelDesc &m, const CvLattice &lat,
-                                            const double *__restrict__ params, long long i, double *row)
-{
-    if (lat.enabled) {
-        cv_lattice_point(lat, i, row);
-    } else {
-#pragma unroll
-        for (int a = 0; a < CV_MAX_PARAMS; a++)
-            row[a] = a < m.n_param ? params[i * m.n_param + a] : 0.0;
-    }
-}
-
-__device__ __forceinline__ double cvf_clipped(const CvModelDesc &m, const double *row, int clip, int a)
-{
-    return clip ? cv_clip(row[a], m.lo[a], m.hi[a]) : row[a];
-}
-
-/* models.py:185-191: the first o in [1, max(hist)) with b(o) <= threshold, else max(hist).  The
- * geometric tail b(o) = many * base^(o-3) is searched from a closed-form estimate with the exact
- * predicate; anything unusual (base outside (0, 1), non-positive threshold) is scanned. */
-__host__ __device__ inline int cvf_cutoff(const CvModelDesc &m, double q1, double two, double many, double base)
-{
-    const double thr = m.threshold;
-    const int top = m.max_bin;
-    if (!(thr == thr))
-        return top;
-    if (1 < top && q1 <= thr)
-        return 1;
-    if (2 < top && two <= thr)
-        return 2;
-    if (top <= 3)
-        return top;
-    if (many <= thr)
-        return 3;
-    if (!(many == many) || !(base == base))
-        return top; /* every comparison is false */
-    if (base > 0.0 && base < 1.0 && thr > 0.0 && many - many == 0.0) {
-        double est = 3.0 + log(thr / many) / log(base);
-        int o = est < (double)top ? (int)est - 1 : top - 1;
-        if (o < 3)
-            o = 3;
-        while (o < top && !(cv_copy_weight(o, q1, two, many, base) <= thr))
-            o++;
-        while (o > 3 && cv_copy_weight(o - 1, q1, two, many, base) <= thr)
-            o--;
-        return o < top ? o : top;
-    }
-    for (int o = 4; o < top; o++)
-        if (cv_copy_weight(o, q1, two, many, base) <= thr)
-            return o;
-    return top;
-}
-
 __device__ __forceinline__ unsigned int cvf_hash(double c, double e)
 {
     unsigned long long x = (unsigned long long)__double_as_longlong(c) * 0x9E3779B97F4A7C15ULL;
@@ -466,10 +413,12 @@ __device__ __forceinline__ int cvf_find_warp(const int *__restrict__ start, int 
 /* ------------------------------------------------------------------------------------------- */
 /* K1: profiles                                                                                 */
 /* ------------------------------------------------------------------------------------------- */
-/* Layout of the profiles of a group in HBM: tiles of 16 copies x 64 slots, [K-chunk][N-step];
- * inside a tile [copy][pair L][2] where pair L = 8 * (row of the N-step) + column % 8 holds the
- * slots with columns c and c + 8 of that row -- 512 contiguous bytes per copy, which K1 writes
- * with one warp-wide store and K2 scatters into its fragment order while loading. */
+/* Layout of the profiles of a group in HBM: one ROW per copy number, [copy][line][pair L][2]: a
+ * row holds all (padded) slots of the histogram in lines of 64 slots (one N-step of K2), and inside
+ * a line pair L = 8 * (row of the N-step) + column % 8 holds the slots with columns c and c + 8 of
+ * that row.  K1 writes 512 contiguous bytes per (copy, line) with one warp-wide store; the prefix
+ * kernel fetches whole rows (a pass of 1024 slots = 8 KB contiguous) with bulk copies; K2 scatters
+ * 16 rows x one line into its fragment order while loading. */
 #define CVF_STAGE_DOUBLES (CV_GB * CV_NA_MAX * CV_W)
 
 /* The accumulators of a lane after the slices of ONE copy are its share of the profile of that
@@ -491,9 +440,8 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
                 make_double2(acc[4 * mt + c], acc[4 * mt + 2 + c]);
         }
     __syncwarp();
-    const int k = o - 1;
-    double *tile0 = Wg + ((long long)(k >> 4) * nsteps + (long long)blk * (2 * NA)) * CVF_TILE_DOUBLES +
-                    ((k & 15) * 32 + lane) * 2;
+    /* row o - 1 of the group's profiles, 64-slot line blk * 2 NA + ns, pair `lane` */
+    double *tile0 = Wg + (long long)(o - 1) * nsteps * CVF_NS + (long long)blk * (2 * NA) * CVF_NS + lane * 2;
 #pragma unroll
     for (int ns = 0; ns < 2 * NA; ns++) {
         const int row = 4 * ns + (lane >> 3);
@@ -504,7 +452,7 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
         const double2 mm = __ldg(reinterpret_cast<const double2 *>(slot_mult) + (blk * (2 * NA) + ns) * 32 + lane);
         v.x = cv_mul(v.x, mm.x); /* the accumulators are finite (that is what the scale is for): times 0 is 0 */
         v.y = cv_mul(v.y, mm.y);
-        *reinterpret_cast<double2 *>(tile0 + (long long)ns * CVF_TILE_DOUBLES) = v;
+        *reinterpret_cast<double2 *>(tile0 + ns * CVF_NS) = v;
     }
     __syncwarp();
 }
@@ -804,11 +752,13 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
     /* loader role: 16-byte chunks tid and tid + 256 of a profile tile ([copy][pair]) go to the
      * fragment order [N half][K slice][n-tile pair][lane = (column % 8) * 4 + copy % 4] */
     int b_dst[2];
+    long long b_src[2]; /* double2 units from the first row of the K-chunk */
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         const int i = tid + j * CVF_THREADS;
         const int oc = i >> 5, L = i & 31, row = L >> 3, rr = L & 7;
         b_dst[j] = (((row >> 1) * 4 + (oc >> 2)) * 2 + (row & 1)) * 32 + rr * 4 + (oc & 3);
+        b_src[j] = (long long)oc * nsteps * (CVF_NS / 2) + L;
     }
     const bool want_mass = m.tail != 0.0;
 
@@ -851,11 +801,13 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
         int ld_kc = 0, ld_ns = 0, ld_buf = 0; /* the next (profile, weight) tile pair to request */
         auto issue = [&]() {
             if (ld_ns < nsteps) {
+                /* 16 rows (copies) x one line of 64 slots: 16-byte chunk i = tid + 256 j is pair
+                 * i % 32 of row i / 32 */
                 const double2 *src = reinterpret_cast<const double2 *>(
-                    Wg + ((long long)ld_kc * nsteps + ld_ns) * CVF_TILE_DOUBLES);
+                    Wg + ((long long)ld_kc * CVF_KC * nsteps + ld_ns) * CVF_NS);
                 double2 *dst = S.Bs[ld_buf];
-                cvf_cp_async16(dst + b_dst[0], src + tid);
-                cvf_cp_async16(dst + b_dst[1], src + tid + CVF_THREADS);
+                cvf_cp_async16(dst + b_dst[0], src + b_src[0]);
+                cvf_cp_async16(dst + b_dst[1], src + b_src[1]);
                 const double2 *asrc = Ag + (long long)ld_kc * (CVF_M * CVF_KC / 2);
                 double2 *adst = S.As[ld_buf];
 #pragma unroll
@@ -959,7 +911,8 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 #pragma unroll
                             for (int mt = 0; mt < 4; mt++) {
                                 /* utils.py:32-35 safe_log */
-                                double lg = (p[mt] <= 0.0) ? -INFINITY : cv_log_tab(p[mt], S.log_tab);
+                                double lg = p[mt] >= CV_P_BAND ? cv_log_tab(p[mt], S.log_tab, CV_PSCALE_EXP)
+                                                               : cv_log_scaled(p[mt]);
                                 if (counted)
                                     sum[mt] = cv_add(sum[mt], cv_mul(mh.y, lg));
                             }
@@ -1093,11 +1046,16 @@ static size_t cvf_prefix_smem_bytes(bool mass)
     return sizeof(CvfPrefixSmem) + CVF_RING_BYTES + planes * CVF_TBUF_DOUBLES * sizeof(double);
 }
 
-/* safe_log (utils.py:32-35) off the fast path: zero, negative, subnormal, infinite, NaN */
+/* safe_log (utils.py:32-35) off the fast path: below the band limit (cvmodel.h CV_PSCALE), zero,
+ * negative, infinite, NaN */
 __device__ __noinline__ double cvf_log_rare(double x)
 {
-    return (x <= 0.0) ? -INFINITY : log(x);
+    return cv_log_scaled(x);
 }
+
+/* fast path of the logarithms: scaled probability in [2^-872, inf), i.e. p >= 2^-1000 */
+#define CVF_FAST_LO ((1023 - 872) << 20)
+#define CVF_FAST_SPAN (0x7ff00000u - (unsigned int)CVF_FAST_LO)
 
 /* cv_log_tab's algorithm for positive normal x with the index arithmetic on the high word and the
  * table at the shared-window address `tab_s`; everything else takes cvf_log_rare.  The
@@ -1108,13 +1066,13 @@ __device__ __noinline__ double cvf_log_rare(double x)
 __device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
 {
     const int hi = __double2hiint(x);
-    if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u)
+    if ((unsigned int)(hi - CVF_FAST_LO) >= CVF_FAST_SPAN)
         return cvf_log_rare(x);
     const int t = hi - (int)(CV_LOG_OFF >> 32);
     const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
     const double2 c = cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4))); /* (invc, logc) of interval (t >> 13) & 127 */
     const double r = cv_fma(z, c.x, -1.0);
-    const double kd = (double)(t >> 20);
+    const double kd = (double)((t >> 20) - CV_PSCALE_EXP); /* log(x 2^-128) */
     const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y); /* ln 2 to 20 bits */
     /* log1p(r) - r = r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7), in three short dependent
      * steps (Estrin) instead of five */
@@ -1137,7 +1095,7 @@ __device__ __forceinline__ double cvf_log_fast(double x, unsigned int tab_s)
     const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
     const double2 c = cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4)));
     const double r = cv_fma(z, c.x, -1.0);
-    const double kd = (double)(t >> 20);
+    const double kd = (double)((t >> 20) - CV_PSCALE_EXP); /* log(x 2^-128) */
     const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y);
     const double r2 = cv_mul(r, r);
     const double a = cv_fma(r, 1.0 / 3.0, -0.5);
@@ -1195,7 +1153,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
     for (int i = tid; i < 2 * CV_LOG_N; i += CVF_PT)
         S.log_tab[i] = log_tab[i];
     const int nslots = nsteps * CVF_NS;
-    const long long chunk_stride = (long long)nsteps * CVF_TILE_DOUBLES;
+    const long long row_stride = (long long)nslots; /* doubles between the rows of consecutive copies */
 
     for (;;) {
         __syncthreads();
@@ -1302,8 +1260,8 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
             for (int pass0 = 0; pass0 < nslots; pass0 += CVF_PASS_SLOTS) {
                 /* the thread's slots: double `lane` of the half-lines u = pass0 / 32 + i * CVF_PW + warp */
                 const int u0 = (pass0 >> 5) + warp;
-                const double *src0 = Wg + (long long)(u0 >> 1) * CVF_TILE_DOUBLES + (u0 & 1) * 32 + lane;
-                constexpr long long SRC_STEP = (long long)(CVF_PW / 2) * CVF_TILE_DOUBLES; /* doubles between i and i + 1 */
+                const double *src0 = Wg + u0 * 32 + lane; /* row 0 (copy 1) */
+                constexpr long long SRC_STEP = (long long)CVF_PW * 32; /* doubles between i and i + 1 */
                 double hcnt[CVF_SL];
                 int log_mask = 0;
                 bool live[CVF_SL];
@@ -1323,7 +1281,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                 int o_req = 1;                 /* the next copy to request */
                 unsigned int dst_req = ring_s; /* its place in the ring */
                 const double *src_req = src0;  /* its first slot */
-                const double *src_far = src0 + (long long)(CVF_PL2 >> 4) * chunk_stride + (CVF_PL2 & 15) * 64;
+                const double *src_far = src0 + (long long)CVF_PL2 * row_stride;
                 const bool far_lane = (lane & 15) == 0; /* one request per 128-byte line */
                 auto request = [&]() { /* one commit group per call, also when there is nothing left to load */
                     if (o_req <= omax_b) {
@@ -1341,8 +1299,8 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         }
                     }
                     cvf_cp_commit();
-                    src_req += ((o_req & 15) == 0) ? chunk_stride - 15 * 64 : 64;
-                    src_far += (((o_req + CVF_PL2) & 15) == 0) ? chunk_stride - 15 * 64 : 64;
+                    src_req += row_stride;
+                    src_far += row_stride;
                     dst_req = (o_req % CVF_PD == 0) ? ring_s : dst_req + CVF_SL * CVF_PT * 8;
                     o_req++;
                 };
@@ -1538,10 +1496,10 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         }
                         double sa = 0.0, sb = 0.0;
                         if (ONE ? log_mask != 0 : log_mask == 1) { /* the usual case: only the warp's first half-line has counts */
-                            const unsigned int ca = (unsigned int)(__double2hiint(pa[0]) - 0x00100000),
-                                               cb = (unsigned int)(__double2hiint(pb[0]) - 0x00100000);
+                            const unsigned int ca = (unsigned int)(__double2hiint(pa[0]) - CVF_FAST_LO),
+                                               cb = (unsigned int)(__double2hiint(pb[0]) - CVF_FAST_LO);
                             double la, lb;
-                            if (ca < 0x7fe00000u && cb < 0x7fe00000u) { /* both positive, normal, finite */
+                            if (ca < CVF_FAST_SPAN && cb < CVF_FAST_SPAN) { /* both on the fast path */
                                 la = cvf_log_fast(pa[0], log_s);
                                 lb = cvf_log_fast(pb[0], log_s);
                             } else {
@@ -1556,10 +1514,10 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
 #pragma unroll
                             for (int i = 0; i < CVF_SL; i++)
                                 if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
-                                    const unsigned int ca = (unsigned int)(__double2hiint(pa[i]) - 0x00100000),
-                                                       cb = (unsigned int)(__double2hiint(pb[i]) - 0x00100000);
+                                    const unsigned int ca = (unsigned int)(__double2hiint(pa[i]) - CVF_FAST_LO),
+                                                       cb = (unsigned int)(__double2hiint(pb[i]) - CVF_FAST_LO);
                                     double la, lb;
-                                    if (ca < 0x7fe00000u && cb < 0x7fe00000u) {
+                                    if (ca < CVF_FAST_SPAN && cb < CVF_FAST_SPAN) {
                                         la = cvf_log_fast(pa[i], log_s);
                                         lb = cvf_log_fast(pb[i], log_s);
                                     } else {

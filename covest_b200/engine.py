@@ -244,6 +244,7 @@ class LikelihoodContext:
         return n.value
 
     PATH_AUTO, PATH_PER_POINT, PATH_FACTORED, PATH_FACTORED_GEMM, PATH_FACTORED_PREFIX = 0, 1, 2, 3, 4
+    PATH_TERM_BY_TERM = 5  # every point through the reference-order evaluation of faithful.cu (slow; a check)
 
     def set_path(self, mode):
         """Evaluation path of the repeats model: PATH_AUTO, PATH_PER_POINT, PATH_FACTORED (GEMM or
@@ -256,10 +257,12 @@ class LikelihoodContext:
         buf = (ctypes.c_double * 12)()
         self._check(self._lib.cvb_last_path_info(self._ctx, buf, 12), 'cvb_last_path_info')
         v = list(buf)
-        return {'path': {1: 'per-point', 2: 'factored', 3: 'factored'}.get(int(v[0]), 'none'),
-                'kernel': {1: 'cv_loglik_kernel', 2: 'cvf_gemm_kernel', 3: 'cvf_prefix_kernel'}.get(int(v[0]), 'none'),
+        return {'path': {1: 'per-point', 2: 'factored', 3: 'factored', 4: 'term-by-term'}.get(int(v[0]), 'none'),
+                'kernel': {1: 'cv_loglik_kernel', 2: 'cvf_gemm_kernel', 3: 'cvf_prefix_kernel',
+                           4: 'cv_faithful_kernel'}.get(int(v[0]), 'none'),
                 'groups': int(v[1]), 'tiles': int(v[2]), 'items': int(v[3]), 'profile_doubles': int(v[4]),
-                'plan_ms': v[5], 'profile_ms': v[6], 'gemm_ms': v[7], 'q_runs': int(v[8])}
+                'plan_ms': v[5], 'profile_ms': v[6], 'gemm_ms': v[7], 'q_runs': int(v[8]),
+                'refined_points': int(v[9]), 'analytic_plan': bool(v[10])}
 
     @property
     def sm_count(self):

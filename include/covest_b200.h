@@ -139,7 +139,8 @@ CVB_API int cvb_last_kernel_ms(cvb_ctx *ctx, double *out_ms, int *out_launches);
  * cut-off of such a q-run.  mode 0 = automatic (factored for batches of >= 2048 points with >= 12
  * points per distinct (c, e); prefix kernel at >= 4 points per q-run), 1 = per-point only,
  * 2 = factored whenever the model supports it, 3 = factored with the GEMM, 4 = factored with the
- * prefix kernel.  The environment variable COVEST_B200_PATH=direct|factored|gemm|prefix|auto sets
+ * prefix kernel, 5 = every point term by term in the reference's order of operations (the kernel
+ * that otherwise re-evaluates only points with subnormal bin probabilities; slow, a check).  The environment variable COVEST_B200_PATH=direct|factored|gemm|prefix|auto sets
  * the initial mode.  Per-bin probabilities (cvb_probs_batch) always use the per-point kernel. */
 CVB_API int cvb_set_path(cvb_ctx *ctx, int mode);
 
@@ -147,7 +148,11 @@ CVB_API int cvb_set_path(cvb_ctx *ctx, int mode);
  * GEMM, 3 factored with the prefix kernel); for the factored path out[1] = distinct (c, e) groups,
  * out[2] = tiles, out[3] = profile items (16 copy numbers each), out[4] = doubles of profile
  * workspace, out[5..7] = device ms of the planning kernels, the profile kernel and the GEMM /
- * prefix kernel (after cvb_set_timing(ctx, 1)), out[8] = q-runs (0 when the GEMM ordering ran). */
+ * prefix kernel (after cvb_set_timing(ctx, 1)), out[8] = q-runs (0 when the GEMM ordering ran);
+ * out[9] = points of the call that were re-evaluated term by term because a bin with a count had a
+ * probability in the subnormal range, where the reference's per-term roundings decide the value
+ * (reading it waits for the device); out[10] = 1 when the plan of the batch came from lattice axes
+ * (no sort, nothing read back). */
 #define CVB_PATH_INFO_LEN 12
 CVB_API int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out);
 

@@ -61,3 +61,14 @@ def loglik_batch(model, points, clip=True, want_probs=False):
     if rc:
         raise RuntimeError('emulation failed: %d' % rc)
     return (out, probs) if want_probs else out
+
+
+BAND_LL = -1.0e270  # CV_BAND_LL of csrc/cvmodel.h
+
+
+def marked(values):
+    """Points the epilogue marks for the term-by-term re-evaluation (a bin with a count has a
+    probability in the subnormal range; csrc/cvmodel.h CV_PSCALE).  That re-evaluation is a CUDA
+    kernel (csrc/faithful.cu) and is checked on the GPU; the host emulation stops at the mark."""
+    v = np.asarray(values, dtype=float)
+    return np.isfinite(v) & (v < BAND_LL)

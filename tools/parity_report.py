@@ -24,7 +24,7 @@ for name in sys.argv[1:] or ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5']:
     inside = ~(np.isposinf(want) | np.isnan(want))
     model = _model(big)
     ctx = model.device_context
-    for path in ([0] if big['cfg']['model'] == 'basic' else [0, 1, 3, 4]):
+    for path in ([0, 5] if big['cfg']['model'] == 'basic' else [0, 1, 3, 4, 5]):
         ctx.set_path(path)
         t0 = time.time()
         got = ctx.loglik(big['points'])
@@ -33,6 +33,7 @@ for name in sys.argv[1:] or ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5']:
         bad = np.nonzero(~(rel <= 1e-9))[0]
         fin = np.isfinite(rel)
         rec = {'cfg': name, 'path': path, 'kernel': ctx.last_path_info()['kernel'], 'seconds': dt,
+               'refined': ctx.last_path_info()['refined_points'],
                'inside': int(inside.sum()), 'bad': int(len(bad)), 'inf_mismatch': int((~fin).sum()),
                'max_finite_rel': float(rel[fin].max()) if fin.any() else None,
                'outside_finite_on_device': int(np.isfinite(got[~inside]).sum()),
