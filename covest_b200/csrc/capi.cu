@@ -75,8 +75,10 @@ struct cvb_ctx {
     int last_path = 0;         /* 1 per-point, 2 factored (GEMM), 3 factored (prefix kernel) */
     double min_run = 4.0;      /* auto: points per q-run below which the GEMM runs instead of the prefix kernel */
     /* re-evaluation of marked points (faithful.h) */
-    CvFaithTables faith = {nullptr, nullptr, 0, nullptr};
-    unsigned long long *d_fixed = nullptr; /* marked points of the most recent call */
+    CvFaithTables faith = {nullptr, nullptr, 0, 0, nullptr, 0};
+    unsigned long long *d_fixed = nullptr; /* two words: marked points of the most recent evaluation, work cursor */
+    unsigned int *d_marked = nullptr;      /* their indices */
+    size_t cap_marked = 0;
     std::string err;
 };
 
@@ -167,7 +169,7 @@ extern "C" void cvb_ctx_destroy(cvb_ctx *ctx)
         cudaFree(p);
     void *bufs[] = {ctx->d_params, ctx->d_ll,      ctx->d_probs, ctx->d_cand_ll, ctx->d_sel_ll,
                     ctx->d_rows,   ctx->d_cand_idx, ctx->d_sel_idx, ctx->d_axes,   ctx->d_counter,
-                    ctx->d_sink,   ctx->d_topk_scratch};
+                    ctx->d_sink,   ctx->d_topk_scratch, ctx->d_marked};
     for (void *p : bufs)
         if (p)
             cudaFree(p);
@@ -308,30 +310,35 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         if (const char *pm = getenv("COVEST_B200_PATH"))
             c->path_mode = !strcmp(pm, "direct") ? 1 : !strcmp(pm, "factored") ? 2 : !strcmp(pm, "gemm") ? 3
                            : !strcmp(pm, "prefix") ? 4 : !strcmp(pm, "faithful") ? 5 : 0;
+        if (const char *pv = getenv("COVEST_B200_PREFIX_KERNEL")) /* 1 = the first version of the prefix kernel */
+            c->fw.prefix_version = atoi(pv) == 1 ? 1 : 2;
         if (const char *wl = getenv("COVEST_B200_PROFILE_MIB"))
             if (atoll(wl) > 0)
                 c->w_limit = (size_t)atoll(wl) * (1 << 20) / sizeof(double);
-        {
-            std::vector<std::pair<int, double>> kv(n_bins);
-            for (int b = 0; b < n_bins; b++)
-                kv[b] = std::make_pair((int)bin_j[b], bin_h[b]);
-            std::sort(kv.begin(), kv.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) {
-                return a.first < b.first;
-            });
-            std::vector<int> fk(n_bins);
-            std::vector<double> fc(n_bins);
+        { /* tables of the term-by-term re-evaluation (faithful.h): by bin index j - 1 */
+            const int j_all = T.max_bin > 0 ? T.max_bin : 1;
+            std::vector<double> cnt(j_all, -1.0), rcp(j_all);
+            int j_counted = 0;
             for (int b = 0; b < n_bins; b++) {
-                fk[b] = kv[b].first;
-                fc[b] = kv[b].second;
+                const int j = (int)bin_j[b];
+                if (j >= 1 && j <= j_all) {
+                    cnt[j - 1] = bin_h[b];
+                    if (bin_h[b] != 0.0 && j > j_counted)
+                        j_counted = j;
+                }
             }
-            if ((e = upload(c, fk, &c->faith.key)) != cudaSuccess) break;
-            if ((e = upload(c, fc, &c->faith.cnt)) != cudaSuccess) break;
-            c->faith.n = n_bins;
+            for (int j = 1; j <= j_all; j++)
+                rcp[j - 1] = 1.0 / (double)j;
+            if ((e = upload(c, cnt, &c->faith.cnt_of_j)) != cudaSuccess) break;
+            if ((e = upload(c, rcp, &c->faith.rcp)) != cudaSuccess) break;
+            c->faith.j_all = j_all;
+            c->faith.j_counted = j_counted;
+            c->faith.acc_doubles = ((long long)j_all + 31) & ~31LL;
             void *scr = nullptr;
-            if ((e = cudaMalloc(&scr, (size_t)cv_faithful_warps(c->n_sm) * (n_bins > 0 ? n_bins : 1) * sizeof(double))) != cudaSuccess) break;
+            if ((e = cudaMalloc(&scr, (size_t)cv_faithful_warps(c->n_sm) * (size_t)c->faith.acc_doubles * sizeof(double))) != cudaSuccess) break;
             c->owned.push_back(scr);
             c->faith.scratch = (double *)scr;
-            if ((e = cudaMalloc((void **)&c->d_fixed, sizeof(unsigned long long))) != cudaSuccess) break;
+            if ((e = cudaMalloc((void **)&c->d_fixed, 2 * sizeof(unsigned long long))) != cudaSuccess) break;
             c->owned.push_back(c->d_fixed);
         }
         if ((e = cudaMalloc((void **)&c->d_counter, sizeof(unsigned long long))) != cudaSuccess) break;
@@ -421,9 +428,11 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *const
     }
     ctx->last_path = used ? 1 + used : 1;
     /* points whose value hinges on the reference's subnormal roundings: again, term by term */
-    CU(cv_launch_faithful(ctx->desc, lat, d_params, n, clip, d_ll, ctx->faith, ctx->n_sm, ctx->d_fixed, s),
+    CU(grow(&ctx->d_marked, &ctx->cap_marked, (size_t)n), "cudaMalloc(marked points)");
+    CU(cv_launch_faithful(ctx->desc, lat, d_params, n, clip, d_ll, ctx->faith, ctx->n_sm, ctx->d_marked,
+                          ctx->d_fixed, s),
        "cv_faithful_kernel launch");
-    ctx->last_launches++;
+    ctx->last_launches += 2; /* the scan for marked points, their re-evaluation */
     if (timed) {
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks + 1], s), "cudaEventRecord");
         ctx->timed_chunks++;
@@ -439,12 +448,6 @@ static int order_enter(cvb_ctx *ctx, cudaStream_t s)
 {
     if (ctx->order_valid && ctx->last_stream != s)
         CU(cudaStreamWaitEvent(s, ctx->order_ev, 0), "cudaStreamWaitEvent");
-    return CVB_OK;
-}
-
-static int reset_fixed(cvb_ctx *ctx, cudaStream_t s)
-{
-    CU(cudaMemsetAsync(ctx->d_fixed, 0, sizeof(unsigned long long), s), "cudaMemsetAsync");
     return CVB_OK;
 }
 
@@ -476,8 +479,6 @@ static int eval_batch(cvb_ctx *ctx, int64_t n_points, const double *params, int 
     if (n_points == 0 && k_best <= 0)
         return CVB_OK;
     if (int rc = order_enter(ctx, s))
-        return rc;
-    if (int rc = reset_fixed(ctx, s))
         return rc;
     const int np = ctx->desc.n_param;
     const long long nb = ctx->desc.n_bins;
@@ -714,8 +715,6 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     ctx->timed_chunks = 0;
     ctx->last_launches = 0;
     if (int rc = order_enter(ctx, s))
-        return rc;
-    if (int rc = reset_fixed(ctx, s))
         return rc;
     size_t total_vals = 0;
     double total_pts = 1.0;

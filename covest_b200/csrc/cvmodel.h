@@ -31,24 +31,27 @@
 /* Probabilities leave the accumulators scaled by 2^128 (slot_mult carries the factor): they stay
  * normal numbers down to p = 2^-1150, so a kernel can tell three classes of a bin with a count:
  *
- *   p >= 2^-1000   every intermediate of the reference's evaluation (c:33 rounds each term to a
- *                  double, models.py:236-239 each product) that matters is a normal number: the
- *                  fast arithmetic of the kernels agrees with it to ~1e-12
- *   p <  2^-1088   the reference's value is exactly 0 (a non-zero result needs a product that
+ *   p >= 2^-1030   the reference rounds every term to a double (c:33) and every product
+ *                  (models.py:236-239); where those are subnormal each rounding moves p by up to
+ *                  2^-1075, 3 T of them (T terms) by 3 T 2^-1075 / p relatively, and the
+ *                  log-likelihood -- whose magnitude is at least h |log p| > 693 h for this very bin
+ *                  -- by less than 3 T 2^-45 / 693 = 1e-12 relatively for T up to 8192 terms: the
+ *                  fast arithmetic of the kernels stands
+ *   p <  2^-1080   the reference's value is exactly 0 (a non-zero result needs a product that
  *                  rounds to at least one unit 2^-1074 of the subnormal grid, which takes a true
  *                  value of at least 2^-1077): log-likelihood -inf
  *   in between     the reference's per-term roundings to the subnormal grid decide the value
  *                  (one unit is ln 2 in log p): the bin contributes the sentinel CV_BAND_LOG, which
  *                  makes the point's value < CV_BAND_LL, and such points are re-evaluated term by
  *                  term, rounding where the reference rounds (faithful.cu).  They are far-off
- *                  points (log-likelihood ~ 700 x their count below any plausible one), about one
- *                  in 10^4 of a wide lattice. */
+ *                  points (a bin with a count is 700 nats off), about one in a hundred of a wide
+ *                  candidate box -- the ones whose last counted bins run out of the double range. */
 #define CV_PSCALE 0x1p128
 #define CV_PUNSCALE 0x1p-128
 #define CV_PSCALE_EXP 128
 #define CV_PSCALE_LOG 0x1.62e42fefa39efp+6 /* 128 ln 2 */
-#define CV_P_ZERO 0x1p-960  /* scaled: p < 2^-1088 */
-#define CV_P_BAND 0x1p-872  /* scaled: p < 2^-1000 */
+#define CV_P_ZERO 0x1p-952  /* scaled: p < 2^-1080 */
+#define CV_P_BAND 0x1p-902  /* scaled: p < 2^-1030 */
 #define CV_BAND_LOG (-1.0e280)
 #define CV_BAND_LL (-1.0e270)
 #define CV_DEAD_TERM (-1.0e30)

@@ -7,20 +7,23 @@
 #include "kernels.h"
 
 struct CvFaithTables {
-    const int *key;    /* [n] histogram keys, ascending */
-    const double *cnt; /* [n] their counts */
-    int n;
-    double *scratch;   /* cv_faithful_warps(n_sm) x n doubles */
+    const double *cnt_of_j; /* [j_all] count of bin j + 1; < 0: j + 1 is not a key of hist */
+    const double *rcp;      /* [j_all] 1 / (j + 1) */
+    int j_all;              /* max(hist) */
+    int j_counted;          /* the largest key with a non-zero count */
+    double *scratch;        /* cv_faithful_warps(n_sm) x acc_doubles */
+    long long acc_doubles;  /* per warp: j_all rounded up to a multiple of 32 */
 };
 
 /* warps the kernel runs at most: sizes the scratch */
 int cv_faithful_warps(int n_sm);
 
 /* Re-evaluates every point whose value in out_ll is marked (finite and below CV_BAND_LL, cvmodel.h)
- * and overwrites it; *n_fixed (device, may be NULL) counts them. */
+ * and overwrites it.  list: n entries of scratch; counters: two device words (marked points of the
+ * call, work cursor), zeroed here. */
 cudaError_t cv_launch_faithful(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
-                               int clip, double *out_ll, const CvFaithTables &ft, int n_sm,
-                               unsigned long long *n_fixed, cudaStream_t stream);
+                               int clip, double *out_ll, const CvFaithTables &ft, int n_sm, unsigned int *list,
+                               unsigned long long *counters, cudaStream_t stream);
 
 /* marks every point: the whole batch then goes through the term-by-term evaluation (path mode 5,
  * a check of that kernel against the oracle on ordinary points) */

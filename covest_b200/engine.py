@@ -192,11 +192,13 @@ class LikelihoodContext:
         return ll, rows
 
     def lattice_eval(self, axes, first=0, stride=1, count=None, want_ll=True, k_best=0,
-                     out_ll=None, stream=None, block=1):
+                     out_ll=None, stream=None, block=1, out_rows=None):
         """Evaluate the Cartesian lattice of `axes` (one 1-D array per model parameter, last axis
         fastest), generating the points on the device: runs of `block` consecutive lattice
         indices, run j starting at (first + j*stride)*block -- with block = 1 the indices
-        first + i*stride, i < count.  Returns (ll or None, rows or None)."""
+        first + i*stride, i < count.  Returns (ll or None, rows or None).  `out_ll` / `out_rows`
+        may be CUDA tensors: the call then only enqueues work (on `stream`, default torch's
+        current stream)."""
         if len(axes) != self.n_param:
             raise ValueError('need %d axes' % self.n_param)
         lens = np.ascontiguousarray([len(a) for a in axes], dtype=np.int32)
@@ -211,11 +213,14 @@ class LikelihoodContext:
         ll = out_ll
         if ll is None and want_ll:
             ll = _host_out(count)
-        rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64) if k_best > 0 else None
+        rows = out_rows
+        if rows is None and k_best > 0:
+            rows = np.empty((k_best, 1 + self.n_param), dtype=np.float64)
+        like = ll if _is_torch_cuda(ll) else rows
         self._check(self._lib.cvb_lattice_eval(self._ctx, lens.ctypes.data_as(_capi.c_int32_p),
                                                vals.ctypes.data_as(_capi.c_double_p), int(first),
                                                int(stride), int(block), int(count), _ptr(ll), int(k_best),
-                                               _ptr(rows), _stream_ptr(stream, ll)), 'cvb_lattice_eval')
+                                               _ptr(rows), _stream_ptr(stream, like)), 'cvb_lattice_eval')
         return ll, rows
 
     # -- measurement -----------------------------------------------------------------------

