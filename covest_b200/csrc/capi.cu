@@ -310,8 +310,8 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         if (const char *pm = getenv("COVEST_B200_PATH"))
             c->path_mode = !strcmp(pm, "direct") ? 1 : !strcmp(pm, "factored") ? 2 : !strcmp(pm, "gemm") ? 3
                            : !strcmp(pm, "prefix") ? 4 : !strcmp(pm, "faithful") ? 5 : 0;
-        if (const char *pv = getenv("COVEST_B200_PREFIX_KERNEL")) /* 1 = the first version of the prefix kernel */
-            c->fw.prefix_version = atoi(pv) == 1 ? 1 : 2;
+        if (const char *pv = getenv("COVEST_B200_PREFIX_KERNEL")) /* which prefix kernel (factored.cu, cvf_eval) */
+            c->fw.prefix_version = atoi(pv);
         if (const char *wl = getenv("COVEST_B200_PROFILE_MIB"))
             if (atoll(wl) > 0)
                 c->w_limit = (size_t)atoll(wl) * (1 << 20) / sizeof(double);

@@ -1040,12 +1040,54 @@ struct CvfPrefixSmem {
      *   double red[3][CVF_PW][CVF_PB]    per (warp, point) partial */
 };
 #define CVF_RING_BYTES (CVF_PD * CVF_SL * CVF_PT * 8)
+#define CVF_SMEM_HEAD ((sizeof(CvfPrefixSmem) + 127) & ~(size_t)127)
 #define CVF_TBUF_DOUBLES (CVF_PW * CVF_PE * CVF_PEW)
 
 static size_t cvf_prefix_smem_bytes(bool mass)
 {
     const size_t planes = mass ? 3 : 2;
-    return sizeof(CvfPrefixSmem) + CVF_RING_BYTES + planes * CVF_TBUF_DOUBLES * sizeof(double);
+    return CVF_SMEM_HEAD + CVF_RING_BYTES + planes * CVF_TBUF_DOUBLES * sizeof(double);
+}
+
+/* ---- mbarrier and bulk-copy (TMA) primitives of the prefix kernels ---- */
+__device__ __forceinline__ void cvf_mbar_init(unsigned int bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cvf_mbar_expect_tx(unsigned int bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cvf_mbar_arrive(unsigned int bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cvf_mbar_wait(unsigned int bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "CVF_MB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra CVF_MB_DONE;\n"
+        "bra CVF_MB_WAIT;\n"
+        "CVF_MB_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+/* global -> shared bulk copy (TMA), completion counted in bytes on the mbarrier */
+__device__ __forceinline__ void cvf_bulk_load(unsigned int dst, const void *src, unsigned int bytes, unsigned int bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+/* a row segment on its way from HBM to L2, nothing lands in shared memory */
+__device__ __forceinline__ void cvf_bulk_prefetch_l2(const void *src, unsigned int bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 /* safe_log (utils.py:32-35) off the fast path: below the band limit (cvmodel.h CV_PSCALE), zero,
@@ -1143,8 +1185,8 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
     extern __shared__ __align__(16) unsigned char cvf_smem_raw[];
     CvfPrefixSmem &S = *reinterpret_cast<CvfPrefixSmem *>(cvf_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *ring = reinterpret_cast<double *>(cvf_smem_raw + sizeof(CvfPrefixSmem)) + tid;
-    double *tbuf = reinterpret_cast<double *>(cvf_smem_raw + sizeof(CvfPrefixSmem) + CVF_RING_BYTES) +
+    double *ring = reinterpret_cast<double *>(cvf_smem_raw + CVF_SMEM_HEAD) + tid;
+    double *tbuf = reinterpret_cast<double *>(cvf_smem_raw + CVF_SMEM_HEAD + CVF_RING_BYTES) +
                    warp * (CVF_PE * CVF_PEW); /* plane stride CVF_TBUF_DOUBLES */
     double *red_all = scratch + (size_t)blockIdx.x * (3 * CVF_PW * CVF_PB);
     double *red = red_all + warp * CVF_PB; /* plane stride CVF_PW * CVF_PB */
@@ -1672,6 +1714,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
 #define V2_PEW 33
 #define V2_NST 3
 #define V2_CPS 2
+#define V2_PFG 8 /* groups ahead of the ring whose rows are prefetched into L2 */
 #define V2_PASS (V2_PT * V2_SL)
 #define V2_COPY_BYTES (V2_PASS * 8)
 #define V2_TBUF_DOUBLES (V2_PW * V2_PE * V2_PEW)
@@ -1693,40 +1736,6 @@ static size_t cvf_prefix2_smem_bytes(bool mass)
 {
     return cvf_prefix2_stage_offset() + (size_t)V2_NST * V2_CPS * V2_COPY_BYTES +
            (mass ? 3 : 2) * V2_TBUF_DOUBLES * sizeof(double);
-}
-
-__device__ __forceinline__ void cvf_mbar_init(unsigned int bar, unsigned int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void cvf_mbar_expect_tx(unsigned int bar, unsigned int bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cvf_mbar_arrive(unsigned int bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cvf_mbar_wait(unsigned int bar, unsigned int parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "CVF_MB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra CVF_MB_DONE;\n"
-        "bra CVF_MB_WAIT;\n"
-        "CVF_MB_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-/* global -> shared bulk copy (TMA), completion counted in bytes on the mbarrier */
-__device__ __forceinline__ void cvf_bulk_load(unsigned int dst, const void *src, unsigned int bytes, unsigned int bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
 }
 
 template <bool MASS, bool FULL>
@@ -1885,6 +1894,7 @@ cvf_prefix2_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
                                   __ldg(&slot_mh[slot0 + i * V2_PW * 64 + 8].y) != 0.0;
                     log_mask |= (__any_sync(CV_FULL_MASK, counted) ? 1 : 0) << i;
                 }
+                const double h0a = live[0] ? __ldg(&slot_mh[slot0].y) : 0.0, h0b = live[0] ? __ldg(&slot_mh[slot0 + 8].y) : 0.0;
                 /* the producer: group g of the pass holds copies g * V2_CPS + 1 .. of which those up
                  * to omax_b exist; it goes to stage (gbase + g) % V2_NST once every warp has
                  * released the group that used the stage before */
@@ -1901,10 +1911,20 @@ cvf_prefix2_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
                         cvf_bulk_load(stage_s + (st * V2_CPS + c) * V2_COPY_BYTES,
                                       src_pass + (long long)(o_first - 1 + c) * row_stride, pass_bytes,
                                       full_s + 8 * st);
+                    /* the rows of the copies V2_PFG groups further on start their way from HBM to L2
+                     * (the ring itself only covers L2 latency) */
+                    for (int c = 0; c < V2_CPS; c++) {
+                        const int o_far = o_first + V2_PFG * V2_CPS + c;
+                        if (o_far <= omax_b)
+                            cvf_bulk_prefetch_l2(src_pass + (long long)(o_far - 1) * row_stride, pass_bytes);
+                    }
                 };
-                if (tid == 0)
+                if (tid == 0) {
+                    for (int o = V2_NST * V2_CPS + 1; o <= min(omax_b, V2_PFG * V2_CPS); o++)
+                        cvf_bulk_prefetch_l2(src_pass + (long long)(o - 1) * row_stride, pass_bytes);
                     for (int g = 0; g < V2_NST && g < n_groups_pass; g++)
                         produce(g);
+                }
                 int g_local = 0, cidx = 0, o_taken = 0;
                 unsigned int stage = gbase % V2_NST, fparity = (gbase / V2_NST) & 1;
                 auto take = [&](double *x) { /* the next copy's profile for the thread's slots */
@@ -2071,30 +2091,37 @@ cvf_prefix2_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
                         mh = cv_add(cv_add(cv_add(p[0], p[1]), cv_add(p[2], p[3])),
                                     cv_add(cv_add(p[4], p[5]), cv_add(p[6], p[7])));
                     }
-                    /* ... and the logarithms of the lines that hold bins with counts, two side by side */
+                    /* ... and the logarithms of the lines that hold bins with counts, two side by side.
+                     * The bins with counts usually are the first ones of the histogram: the thread's
+                     * first line, whose counts stay in registers. */
                     double sum = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if ((log_mask >> i) & 1) {
-                            const double ha = __ldg(&slot_mh[slot0 + i * V2_PW * 64].y),
-                                         hb = __ldg(&slot_mh[slot0 + i * V2_PW * 64 + 8].y);
-                            const unsigned int ca = (unsigned int)(__double2hiint(p[2 * i]) - CVF_FAST_LO),
-                                               cb = (unsigned int)(__double2hiint(p[2 * i + 1]) - CVF_FAST_LO);
-                            double la, lb;
-                            if (ca < CVF_FAST_SPAN && cb < CVF_FAST_SPAN) {
-                                la = cvf_log_fast(p[2 * i], log_s);
-                                lb = cvf_log_fast(p[2 * i + 1], log_s);
-                            } else {
-                                la = cvf_safe_log(p[2 * i], log_s); /* utils.py:32-35 */
-                                lb = cvf_safe_log(p[2 * i + 1], log_s);
-                            }
-                            double ta = cv_mul(ha, la), tb = cv_mul(hb, lb);
-                            if (ha == 0.0) /* models.py:106 `if h` */
-                                ta = 0.0;
-                            if (hb == 0.0)
-                                tb = 0.0;
-                            sum = cv_add(sum, cv_add(ta, tb));
+                    auto two_logs = [&](double pa, double pb, double ha, double hb) {
+                        const unsigned int ca = (unsigned int)(__double2hiint(pa) - CVF_FAST_LO),
+                                           cb = (unsigned int)(__double2hiint(pb) - CVF_FAST_LO);
+                        double la, lb;
+                        if (ca < CVF_FAST_SPAN && cb < CVF_FAST_SPAN) {
+                            la = cvf_log_fast(pa, log_s);
+                            lb = cvf_log_fast(pb, log_s);
+                        } else {
+                            la = cvf_safe_log(pa, log_s); /* utils.py:32-35 */
+                            lb = cvf_safe_log(pb, log_s);
                         }
+                        double ta = cv_mul(ha, la), tb = cv_mul(hb, lb);
+                        if (ha == 0.0) /* models.py:106 `if h` */
+                            ta = 0.0;
+                        if (hb == 0.0)
+                            tb = 0.0;
+                        sum = cv_add(sum, cv_add(ta, tb));
+                    };
+                    if (log_mask & 1)
+                        two_logs(p[0], p[1], h0a, h0b);
+                    if (log_mask & 14) {
+#pragma unroll
+                        for (int i = 1; i < 4; i++)
+                            if ((log_mask >> i) & 1)
+                                two_logs(p[2 * i], p[2 * i + 1], __ldg(&slot_mh[slot0 + i * V2_PW * 64].y),
+                                         __ldg(&slot_mh[slot0 + i * V2_PW * 64 + 8].y));
+                    }
                     cvf_sts64(tb_a, sum);
                     cvf_sts64(tb_a + V2_TBUF_DOUBLES * 8, mh);
                     if (MASS)
@@ -2387,8 +2414,10 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
     if (wk.timed)
         CVF_CK(cudaEventRecord(wk.ev[0], stream));
 
-    /* which prefix kernel: 2 = bulk-copy pipeline, 8 slots per thread (default); 1 = the first version */
-    const int pver = wk.prefix_version == 1 ? 1 : 2;
+    /* which prefix kernel: 1 = cvf_prefix_kernel (8 warps, 4 slots per thread, thread-private cp.async
+     * rings: the default, it is the faster one -- DESIGN.md section 5.2); 2 = cvf_prefix2_kernel (4 warps,
+     * 8 slots per thread, rows by bulk copies through an mbarrier ring) */
+    const int pver = wk.prefix_version == 2 ? 2 : 1;
     pl.pnq = pver == 2 ? V2_NQ : CVF_PNQ;
     pl.ppb = pver == 2 ? V2_PB : CVF_PPB;
 

@@ -56,7 +56,7 @@ struct CvFactorWork {
     long long n_groups = 0, n_tiles = 0, n_items = 0, w_doubles = 0, n_runs = 0;
     int prefix = 0; /* 1: the prefix kernel ran, 0: the GEMM */
     int launches = 0;
-    int prefix_version = 2; /* 2: cvf_prefix2_kernel (bulk copies, 8 slots per thread); 1: cvf_prefix_kernel */
+    int prefix_version = 1; /* 1: cvf_prefix_kernel (cp.async rings), 2: cvf_prefix2_kernel (bulk copies, mbarrier ring) */
     int analytic = 0; /* 1: the plan came from the lattice axes (no sort, no host synchronisation) */
     CvfLatticeCache lattice;
     double gemm_fma = 0.0; /* FMAs the tiles of K2 issue (128 rows x padded copies x padded slots) */

@@ -124,14 +124,18 @@ def test_both_prefix_kernels_agree_with_the_other_paths(cfg2):
     assert np.array_equal(np.isfinite(ll), fin) and np.array_equal(np.isfinite(gemm), fin)
     assert np.max(np.abs(ll[fin] - direct[fin]) / np.abs(direct[fin])) <= 1e-11
     assert np.max(np.abs(gemm[fin] - direct[fin]) / np.abs(direct[fin])) <= 1e-11
-    os.environ['COVEST_B200_PREFIX_KERNEL'] = '1'   # the first version of the prefix kernel, in a new context
-    try:
-        old = RepeatsModel(21, 100, dict(cfg2.hist), 0, max_error=8)
-        ll_old, _ = old.device_context.lattice_eval(axes)
-        old.close()
-    finally:
-        del os.environ['COVEST_B200_PREFIX_KERNEL']
-    assert np.max(np.abs(ll[fin] - ll_old[fin]) / np.abs(direct[fin])) <= 1e-12
+    # the second prefix kernel (cvf_prefix2_kernel: rows by bulk copies through an mbarrier ring, four
+    # warps with 8 slots per thread) in a new context; the default is cvf_prefix_kernel
+    for version in ('2',):
+        os.environ['COVEST_B200_PREFIX_KERNEL'] = version
+        try:
+            other = RepeatsModel(21, 100, dict(cfg2.hist), 0, max_error=8)
+            ll_other, _ = other.device_context.lattice_eval(axes)
+            other.close()
+        finally:
+            del os.environ['COVEST_B200_PREFIX_KERNEL']
+        assert np.array_equal(np.isfinite(ll_other), fin)
+        assert np.max(np.abs(ll[fin] - ll_other[fin]) / np.abs(direct[fin])) <= 1e-12, version
 
 
 def test_grid_rounds_on_the_device_walk_the_same_centres(cfg2):
