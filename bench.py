@@ -355,7 +355,9 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     os.environ['COVEST_B200_DEVICE'] = str(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device('cuda', local_rank)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -448,7 +450,7 @@ def run_b200(args, rank, world, local_rank):
 
         # steps back to back for >= 2 s (no flush: the profile workspace alone is far larger than L2)
         def sustained():
-            n = max(steps, int(2200.0 / max(np.mean(step_ms), 1e-3)))
+            n = max(steps, int(2200.0 / max(total_ms / steps, 1e-3)))  # total_ms is the max over ranks: the same n everywhere
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
@@ -612,7 +614,7 @@ def run_b200(args, rank, world, local_rank):
         del out_p, rnd, rnd_ll
 
     cfg5 = None
-    if world == 8 and args.workload == 'cfg3' and not args.points and not args.no_cfg5:
+    if (world == 8 or args.cfg5) and args.workload == 'cfg3' and not args.points and not args.no_cfg5:
         # BASELINE.json configs[4] / the north-star target: 10^8 points x 2000 bins over 8 ranks, per-rank
         # top-64, all-gather, multi-start refinement from the global best rows, second all-gather
         from covest_b200.covest import CoverageEstimator
@@ -695,6 +697,8 @@ def main():
     ap.add_argument('--points', type=int, default=0, help='cap the points per rank (development)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-cfg5', action='store_true', help='at --gpus 8: skip the cfg5 sub-record')
+    ap.add_argument('--cfg5', action='store_true',
+                    help='add the cfg5 sub-record at any number of GPUs (12.5e6 points x 2000 bins per rank)')
     ap.add_argument('--path', default='auto', choices=['auto', 'prefix', 'gemm', 'direct'],
                     help='evaluation path of the device arm (development; auto = what a user gets)')
     args = ap.parse_args()

@@ -312,6 +312,8 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
                            : !strcmp(pm, "prefix") ? 4 : !strcmp(pm, "faithful") ? 5 : 0;
         if (const char *pv = getenv("COVEST_B200_PREFIX_KERNEL")) /* which prefix kernel (factored.cu, cvf_eval) */
             c->fw.prefix_version = atoi(pv);
+        if (const char *to = getenv("COVEST_B200_TILE_ORDER")) /* 0 = by descending cost, 1 = group by group */
+            c->fw.tile_interleave = atoi(to) != 0;
         if (const char *wl = getenv("COVEST_B200_PROFILE_MIB"))
             if (atoll(wl) > 0)
                 c->w_limit = (size_t)atoll(wl) * (1 << 20) / sizeof(double);

@@ -383,15 +383,27 @@ cvf_lattice_fill(CvfPlan pl, CvfLatticeDev T, int G, int M, int R, int nq, int n
     }
 }
 
-/* tiles of the groups g0 .. g1 - 1 by descending cost: every group has the same tiles */
+/* The order in which the CTAs draw the tiles of the groups g0 .. g1 - 1 (every group has the same
+ * tiles).  interleave = 0: by descending cost over the whole range, i.e. first every group's costliest
+ * tile -- the ones that stream the long copy series of the smallest q -- then the next ...;
+ * interleave = 1: group by group, inside a group by descending cost: at any time the CTAs in flight
+ * hold all kinds of tiles, so the HBM traffic of the long series (2.6 of cfg3's 3.0 GB) spreads over
+ * the whole kernel instead of saturating the memory system during its first third. */
 __global__ void __launch_bounds__(256)
-cvf_lattice_order(CvfLatticeDev T, int g0, int g1, int nT, int *__restrict__ out)
+cvf_lattice_order(CvfLatticeDev T, int g0, int g1, int nT, int interleave, int *__restrict__ out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int ng = g1 - g0;
     if (i >= (long long)ng * nT)
         return;
-    const int k = (int)(i / ng), g = g0 + (int)(i - (long long)k * ng);
+    int k, g;
+    if (interleave) {
+        g = g0 + (int)(i / nT);
+        k = (int)(i - (long long)(g - g0) * nT);
+    } else {
+        k = (int)(i / ng);
+        g = g0 + (int)(i - (long long)k * ng);
+    }
     out[i] = g * nT + T.tt_order[k];
 }
 
@@ -1023,8 +1035,9 @@ __device__ __forceinline__ void cvf_sts64(unsigned int a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
+#define CVF_LOG_REP 8
 struct CvfPrefixSmem {
-    double log_tab[2 * CV_LOG_N];
+    double log_tab[2 * CV_LOG_N * CVF_LOG_REP]; /* CVF_LOG_REP interleaved copies of cv_log_table */
     /* the points of the batch by ascending cut-off (the schedule), 32 bytes each: weights of
      * copy 1, copy 2 and of the running sum; batch position | run << 16; copies = O_thr - 1 */
     CvfEvent ev[CVF_PB + 2];
@@ -1107,6 +1120,10 @@ __device__ __noinline__ double cvf_log_rare(double x)
  * immediate field of the FP64 instructions; errors below 2^-58 and none: k * ln2_hi stays exact);
  * the polynomial in Estrin form, the last sum reordered: absolute error below 2.5e-16 (1 + |log x|)
  * (cv_log_tab: 2e-16). */
+/* REP: copies of the table side by side (entry e of copy c at 16 (e REP + c) bytes; tab_s already points
+ * at the lane's copy): with 8 copies the 8 lanes of a quarter warp read 8 different 16-byte bank groups
+ * whatever their arguments -- the lookups are free of bank conflicts */
+template <int REP = 1>
 __device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
 {
     const int hi = __double2hiint(x);
@@ -1114,7 +1131,8 @@ __device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
         return cvf_log_rare(x);
     const int t = hi - (int)(CV_LOG_OFF >> 32);
     const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
-    const double2 c = cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4))); /* (invc, logc) of interval (t >> 13) & 127 */
+    const double2 c = REP == 8 ? cvf_lds128(tab_s + ((t >> 6) & ((CV_LOG_N - 1) << 7)))
+                                : cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4))); /* (invc, logc) of interval (t >> 13) & 127 */
     const double r = cv_fma(z, c.x, -1.0);
     const double kd = (double)((t >> 20) - CV_PSCALE_EXP); /* log(x 2^-128) */
     const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y); /* ln 2 to 20 bits */
@@ -1132,12 +1150,14 @@ __device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
 }
 
 /* the fast path of cvf_safe_log alone: x positive, normal, finite */
+template <int REP = 1>
 __device__ __forceinline__ double cvf_log_fast(double x, unsigned int tab_s)
 {
     const int hi = __double2hiint(x);
     const int t = hi - (int)(CV_LOG_OFF >> 32);
     const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
-    const double2 c = cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4)));
+    const double2 c = REP == 8 ? cvf_lds128(tab_s + ((t >> 6) & ((CV_LOG_N - 1) << 7)))
+                                : cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4)));
     const double r = cv_fma(z, c.x, -1.0);
     const double kd = (double)((t >> 20) - CV_PSCALE_EXP); /* log(x 2^-128) */
     const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y);
@@ -1191,11 +1211,12 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
     double *red_all = scratch + (size_t)blockIdx.x * (3 * CVF_PW * CVF_PB);
     double *red = red_all + warp * CVF_PB; /* plane stride CVF_PW * CVF_PB */
     const unsigned int ring_s = cvf_pin((unsigned int)__cvta_generic_to_shared(ring));
-    const unsigned int log_s = cvf_pin((unsigned int)__cvta_generic_to_shared(S.log_tab));
+    /* the lane's copy of the logarithm table */
+    const unsigned int log_s = cvf_pin((unsigned int)__cvta_generic_to_shared(S.log_tab) + (unsigned int)((lane & (CVF_LOG_REP - 1)) * 16));
     const unsigned int ev_s = cvf_pin((unsigned int)__cvta_generic_to_shared(S.ev));
     const unsigned int tbuf_s = cvf_pin((unsigned int)__cvta_generic_to_shared(tbuf + lane)); /* the lane's column */
-    for (int i = tid; i < 2 * CV_LOG_N; i += CVF_PT)
-        S.log_tab[i] = log_tab[i];
+    for (int i = tid; i < 2 * CV_LOG_N * CVF_LOG_REP; i += CVF_PT) /* entry e of copy c: doubles 2 (e REP + c) .. + 1 */
+        S.log_tab[i] = log_tab[2 * (i / (2 * CVF_LOG_REP)) + (i & 1)];
     const int nslots = nsteps * CVF_NS;
     const long long row_stride = (long long)nslots; /* doubles between the rows of consecutive copies */
 
@@ -1544,11 +1565,11 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                                                cb = (unsigned int)(__double2hiint(pb[0]) - CVF_FAST_LO);
                             double la, lb;
                             if (ca < CVF_FAST_SPAN && cb < CVF_FAST_SPAN) { /* both on the fast path */
-                                la = cvf_log_fast(pa[0], log_s);
-                                lb = cvf_log_fast(pb[0], log_s);
+                                la = cvf_log_fast<CVF_LOG_REP>(pa[0], log_s);
+                                lb = cvf_log_fast<CVF_LOG_REP>(pb[0], log_s);
                             } else {
-                                la = cvf_safe_log(pa[0], log_s);
-                                lb = cvf_safe_log(pb[0], log_s);
+                                la = cvf_safe_log<CVF_LOG_REP>(pa[0], log_s);
+                                lb = cvf_safe_log<CVF_LOG_REP>(pb[0], log_s);
                             }
                             sa = cv_mul(hcnt[0], la);
                             sb = cv_mul(hcnt[0], lb);
@@ -1562,11 +1583,11 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                                                        cb = (unsigned int)(__double2hiint(pb[i]) - CVF_FAST_LO);
                                     double la, lb;
                                     if (ca < CVF_FAST_SPAN && cb < CVF_FAST_SPAN) {
-                                        la = cvf_log_fast(pa[i], log_s);
-                                        lb = cvf_log_fast(pb[i], log_s);
+                                        la = cvf_log_fast<CVF_LOG_REP>(pa[i], log_s);
+                                        lb = cvf_log_fast<CVF_LOG_REP>(pb[i], log_s);
                                     } else {
-                                        la = cvf_safe_log(pa[i], log_s);
-                                        lb = cvf_safe_log(pb[i], log_s);
+                                        la = cvf_safe_log<CVF_LOG_REP>(pa[i], log_s);
+                                        lb = cvf_safe_log<CVF_LOG_REP>(pb[i], log_s);
                                     }
                                     double ta = cv_mul(hcnt[i], la), tb = cv_mul(hcnt[i], lb);
                                     if (hcnt[i] == 0.0)
@@ -1633,7 +1654,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             mh = cv_add(mh, p[i]);
                     }
                     if (ONE ? log_mask != 0 : log_mask == 1) { /* the usual case: the warp's first half-line holds the bins with counts */
-                        double term = cv_mul(hcnt[0], cvf_safe_log(p[0], log_s)); /* utils.py:32-35 */
+                        double term = cv_mul(hcnt[0], cvf_safe_log<CVF_LOG_REP>(p[0], log_s)); /* utils.py:32-35 */
                         if (hcnt[0] == 0.0) /* models.py:106 `if h` */
                             term = 0.0;
                         sum = term;
@@ -1641,7 +1662,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
 #pragma unroll
                         for (int i = 0; i < CVF_SL; i++)
                             if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
-                                double term = cv_mul(hcnt[i], cvf_safe_log(p[i], log_s));
+                                double term = cv_mul(hcnt[i], cvf_safe_log<CVF_LOG_REP>(p[i], log_s));
                                 if (hcnt[i] == 0.0)
                                     term = 0.0;
                                 sum = cv_add(sum, term);
@@ -2671,7 +2692,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
             /* tiles of the range by descending cost: the long ones start first */
             if (analytic) {
                 cvf_lattice_order<<<(unsigned int)((tiles + tb - 1) / tb), tb, 0, stream>>>(
-                    TD, g0, g1, (int)(n_tiles / n_groups), pl.t_order_alt + tile0);
+                    TD, g0, g1, (int)(n_tiles / n_groups), wk.tile_interleave, pl.t_order_alt + tile0);
                 CVF_CK(cudaGetLastError());
                 pl.t_sorted = pl.t_order_alt + tile0;
             } else {

@@ -17,9 +17,15 @@
  *     buffers (the copies are part of the call);
  *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream; name the default
  *     stream with cudaStreamLegacy, (void*)1).  Calls with
- *     host buffers return after the results are in the host buffer; calls where all buffers are
- *     device pointers only enqueue work on the stream;
- *   - a context is bound to one device and is not re-entrant; distinct contexts are independent;
+ *     host buffers return after the results are in the host buffer (one stream synchronisation per
+ *     call); calls where all buffers are device pointers only enqueue work on the stream -- with one
+ *     exception: cvb_loglik_batch / cvb_loglik_topk on an explicit point array that takes the
+ *     factored path (cvb_set_path) synchronise the stream once, because the general plan reads the
+ *     group and tile counts back to size its workspace.  cvb_lattice_eval never does: the plan of a
+ *     lattice follows from its axes;
+ *   - a context is bound to one device and is not re-entrant; its calls share scratch memory, so a
+ *     call issued on a different stream than the previous call of the same context first waits
+ *     (on the device) for that call's work; distinct contexts are independent;
  *   - there is no CPU fallback: without a CUDA device every call fails with CVB_ECUDA.
  */
 #ifndef COVEST_B200_H
