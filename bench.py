@@ -316,7 +316,7 @@ def committed_traffic(kernel, workload_name, n_points):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
     `ncu --set full` capture of this same command (profiles/, per launch) -- only when this run
     launches the kernel on the batch the capture was taken on; else None."""
-    path = os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')
+    path = os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')
     try:
         with open(path) as f:
             for row in json.load(f):
@@ -356,6 +356,7 @@ def run_b200(args, rank, world, local_rank):
     os.environ['COVEST_B200_DEVICE'] = str(local_rank)
     if world > 1:
         import datetime
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
                                 timeout=datetime.timedelta(seconds=180))
     dev = torch.device('cuda', local_rank)

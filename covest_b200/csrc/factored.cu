@@ -386,9 +386,10 @@ cvf_lattice_fill(CvfPlan pl, CvfLatticeDev T, int G, int M, int R, int nq, int n
 /* The order in which the CTAs draw the tiles of the groups g0 .. g1 - 1 (every group has the same
  * tiles).  interleave = 0: by descending cost over the whole range, i.e. first every group's costliest
  * tile -- the ones that stream the long copy series of the smallest q -- then the next ...;
- * interleave = 1: group by group, inside a group by descending cost: at any time the CTAs in flight
- * hold all kinds of tiles, so the HBM traffic of the long series (2.6 of cfg3's 3.0 GB) spreads over
- * the whole kernel instead of saturating the memory system during its first third. */
+ * interleave = 1: group by group, inside a group by descending cost, so that the CTAs in flight hold
+ * all kinds of tiles and the HBM traffic of the long series spreads over the whole kernel.  Measured:
+ * cfg3 1.50 ms against 1.44 ms (the costly tiles finishing last leave SMs idle at the end), cfg5
+ * 27.4 against 27.8 ms -- the default stays 0 (COVEST_B200_TILE_ORDER). */
 __global__ void __launch_bounds__(256)
 cvf_lattice_order(CvfLatticeDev T, int g0, int g1, int nT, int interleave, int *__restrict__ out)
 {
@@ -1035,7 +1036,7 @@ __device__ __forceinline__ void cvf_sts64(unsigned int a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-#define CVF_LOG_REP 8
+#define CVF_LOG_REP 1 /* 8 interleaved copies make the lookups free of bank conflicts; measured: no gain (1.444 ms either way) */
 struct CvfPrefixSmem {
     double log_tab[2 * CV_LOG_N * CVF_LOG_REP]; /* CVF_LOG_REP interleaved copies of cv_log_table */
     /* the points of the batch by ascending cut-off (the schedule), 32 bytes each: weights of

@@ -57,7 +57,7 @@ struct CvFactorWork {
     int prefix = 0; /* 1: the prefix kernel ran, 0: the GEMM */
     int launches = 0;
     int prefix_version = 1; /* 1: cvf_prefix_kernel (cp.async rings), 2: cvf_prefix2_kernel (bulk copies, mbarrier ring) */
-    int tile_interleave = 1; /* lattice plans: tiles group by group (1) or by descending cost over all groups (0) */
+    int tile_interleave = 0; /* lattice plans: tiles by descending cost over all groups (0, default) or group by group (1) */
     int analytic = 0; /* 1: the plan came from the lattice axes (no sort, no host synchronisation) */
     CvfLatticeCache lattice;
     double gemm_fma = 0.0; /* FMAs the tiles of K2 issue (128 rows x padded copies x padded slots) */
