@@ -397,6 +397,26 @@ class CoverageEstimator:
         return x, fx
 
 
+def candidate_lattice(model, guess, bounds, shape=None):
+    """Axes of a candidate lattice over the box initial_grid draws from (covest/grid.py:95-110: every
+    coordinate in [v / 3, 3 v] cut to the bounds): coverage and error rate log-spaced around the guess,
+    the copy-number parameters over their whole ranges.  Model coordinates."""
+    n = model.param_count
+    shape = shape or ((24, 16, 8, 8, 8) if n == 5 else (64, 48))
+    axes = []
+    for i in range(n):
+        lo, hi = bounds[i]
+        v = float(guess[i])
+        if i < 2:
+            a, b = v / constants.INITIAL_GRID_STEP, v * constants.INITIAL_GRID_STEP
+            a = max(a, lo if lo is not None else a, 1e-12)
+            b = min(b, hi) if hi is not None else b
+            axes.append(np.geomspace(a, max(b, a), shape[i]))
+        else:
+            axes.append(np.linspace(lo if lo is not None else 0.0, hi if hi is not None else 1.0, shape[i]))
+    return axes
+
+
 def _scipy_has_workers():
     import scipy
     major, minor = (int(v) for v in scipy.__version__.split('.')[:2])
@@ -468,9 +488,16 @@ def main(args):
 
         estimator = CoverageEstimator(model, err_scale=err_scale, fix=fix,
                                       optimizer=getattr(args, 'optimizer', None))
-        res, success = estimator.compute_coverage(
-            guess, starting_points=args.starting_points, use_grid_search=args.grid,
-            n_threads=args.thread_count)
+        if getattr(args, 'lattice_starts', 0) and not fix:
+            # starts = the best rows of a candidate lattice (sharded over the ranks under torchrun)
+            # instead of random draws; refined with all starts per launch
+            estimator.optimizer = 'lockstep'
+            res, success, _ = estimator.compute_coverage_from_lattice(
+                candidate_lattice(model, guess, model.bounds), k_best=args.lattice_starts)
+        else:
+            res, success = estimator.compute_coverage(
+                guess, starting_points=args.starting_points, use_grid_search=args.grid,
+                n_threads=args.thread_count)
         if getattr(args, 'polish', False):
             scaled = list(res)
             scaled[1] *= err_scale
@@ -533,6 +560,9 @@ def build_parser():
     p.add_argument('--optimizer', choices=['scipy', 'lockstep'], default=None,
                    help='Multi-start refinement: scipy L-BFGS-B per start (the reference\'s optimiser, '
                         'default) or the lock-step Newton iteration with all starts per launch')
+    p.add_argument('--lattice-starts', type=int, default=0, metavar='K',
+                   help='Refine from the K best points of a candidate lattice over the initial-grid box '
+                        '(evaluated on the device, sharded over the GPUs under torchrun) instead of -sp random starts')
     p.add_argument('--seed', type=int, default=None,
                    help='Seed Python\'s random (multi-start points, histogram sampling)')
     return p

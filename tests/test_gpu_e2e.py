@@ -92,3 +92,25 @@ def test_cli_report_has_the_reference_keys(tmp_path):
     kmers = sum(j * h for j, h in hist.items())
     want_size = kmers / (g['polished']['x'][0] * (100 - 21 + 1) / 100)
     assert out['genome_size'] == pytest.approx(want_size, rel=EST_RTOL)
+
+
+def test_cli_lattice_starts(tmp_path):
+    """`--lattice-starts K`: the K best points of a candidate lattice as starts, lock-step refinement."""
+    from covest_b200 import covest as cli
+    g = _golden()['cfg2_repeats']
+    path = tmp_path / 'cfg2.hist'
+    path.write_text(''.join('%d %d\n' % (j, h) for j, h in g['hist']))
+    buf = io.StringIO()
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with redirect_stdout(buf):
+            cli.run([str(path), '-m', 'repeat', '-k', '21', '-r', '100', '-sf', '1', '--lattice-starts', '16'])
+    finally:
+        os.chdir(cwd)
+    out = yaml.safe_load(buf.getvalue())
+    assert out['success']
+    # at least as good as the optimum the polished reference run ends at
+    assert out['loglikelihood'] >= -g['polished']['objective'] * (1 + 1e-12)
+    if out['loglikelihood'] <= -g['polished']['objective'] * (1 - 1e-10):
+        assert out['coverage'] == pytest.approx(g['polished']['x'][0], rel=EST_RTOL)

@@ -9,6 +9,9 @@ KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor_subpipe_dmma.sum',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
