@@ -340,7 +340,7 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
             if ((e = cudaMalloc(&scr, (size_t)cv_faithful_warps(c->n_sm) * (size_t)c->faith.acc_doubles * sizeof(double))) != cudaSuccess) break;
             c->owned.push_back(scr);
             c->faith.scratch = (double *)scr;
-            if ((e = cudaMalloc((void **)&c->d_fixed, 2 * sizeof(unsigned long long))) != cudaSuccess) break;
+            if ((e = cudaMalloc((void **)&c->d_fixed, 4 * sizeof(unsigned long long))) != cudaSuccess) break;
             c->owned.push_back(c->d_fixed);
         }
         if ((e = cudaMalloc((void **)&c->d_counter, sizeof(unsigned long long))) != cudaSuccess) break;
@@ -430,11 +430,11 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *const
     }
     ctx->last_path = used ? 1 + used : 1;
     /* points whose value hinges on the reference's subnormal roundings: again, term by term */
-    CU(grow(&ctx->d_marked, &ctx->cap_marked, (size_t)n), "cudaMalloc(marked points)");
+    CU(grow(&ctx->d_marked, &ctx->cap_marked, 2 * (size_t)n), "cudaMalloc(marked points)");
     CU(cv_launch_faithful(ctx->desc, lat, d_params, n, clip, d_ll, ctx->faith, ctx->n_sm, ctx->d_marked,
                           ctx->d_fixed, s),
        "cv_faithful_kernel launch");
-    ctx->last_launches += 2; /* the scan for marked points, their re-evaluation */
+    ctx->last_launches += 3; /* the scan for marked points, their re-evaluation (warp / CTA per point) */
     if (timed) {
         CU(cudaEventRecord(ctx->ev[2 * ctx->timed_chunks + 1], s), "cudaEventRecord");
         ctx->timed_chunks++;

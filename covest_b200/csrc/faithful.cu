@@ -27,8 +27,10 @@
  * products supplies -- and every lane runs over all (copy number, error class) terms, so the sums
  * over s and o are plain sequential sums in registers.  Only bins up to the last one with a count
  * are needed when the histogram has no tail (models.py:103-104: the mass then does not enter).
- * A few microseconds per point with two copy numbers; it is correct for any point (path mode 5 runs
- * every point through it, tests/test_gpu_big_golden.py).
+ * A few microseconds per point with two copy numbers; points with many copy numbers (their cost grows
+ * with copies x bins) are worked off by a whole CTA each, the copy numbers dealt to its warps.  The
+ * kernels are correct for any point (path mode 5 runs every point through them,
+ * tests/test_gpu_big_golden.py).
  *
  * Reference lines are relative to /root/reference.
  */
@@ -86,10 +88,10 @@ struct CvxPoint {
     int n_copies;
 };
 
-/* The log-likelihood of one point, evaluated by the whole warp.
- * acc: ft.acc_doubles doubles of scratch (p_j at acc[j - 1]); every lane touches its own bins only. */
-__device__ double cvx_point(int lane, const CvModelDesc &m, const CvxPoint &P, const CvFaithTables &ft,
-                            double *acc)
+/* The bin probabilities of one point, summed over the copy numbers o_first, o_first + o_step, ...:
+ * p_j at acc[j - 1] (ft.acc_doubles doubles of scratch; every lane touches its own bins only). */
+__device__ void cvx_accumulate(int lane, const CvModelDesc &m, const CvxPoint &P, const CvFaithTables &ft,
+                               double *acc, int o_first, int o_step)
 {
     const int S = m.n_err;
     const int J = m.tail != 0.0 ? ft.j_all : ft.j_counted; /* bins that enter the result */
@@ -98,7 +100,7 @@ __device__ double cvx_point(int lane, const CvModelDesc &m, const CvxPoint &P, c
     for (int j = lane; j < J; j += 32)
         acc[j] = 0.0;
     __syncwarp();
-    for (int o = 1; o <= P.n_copies; o++) {
+    for (int o = o_first; o <= P.n_copies; o += o_step) {
         const double b_o = m.model_kind ? cv_copy_weight(o, P.q1, P.two, P.many, P.base) : 1.0;
         /* models.py:221-232: n_os = comb[s] * (1.0 - exp(o * -l_s)), a_os = n_os / (sum_s n_os or 1),
          * the sum left to right as Python's.  Lane l holds the classes l and l + 32. */
@@ -213,7 +215,14 @@ __device__ double cvx_point(int lane, const CvModelDesc &m, const CvxPoint &P, c
         }
         __syncwarp();
     }
-    /* models.py:100-107 */
+}
+
+/* models.py:100-107 from the bin probabilities, which are the sums of n_acc arrays `stride` doubles
+ * apart (the shares of the warps that split the copy numbers), added in a fixed order */
+__device__ double cvx_finish(int lane, const CvModelDesc &m, const CvFaithTables &ft, const double *acc, int n_acc,
+                             long long stride)
+{
+    const int J = m.tail != 0.0 ? ft.j_all : ft.j_counted;
     CvPartial part;
     part.sum = 0.0;
     part.mass_h = part.mass_l = 0.0;
@@ -221,7 +230,9 @@ __device__ double cvx_point(int lane, const CvModelDesc &m, const CvxPoint &P, c
         const double h = __ldg(ft.cnt_of_j + j); /* < 0: j + 1 is not a key of hist */
         if (h < 0.0)
             continue;
-        const double p = acc[j];
+        double p = acc[j];
+        for (int a = 1; a < n_acc; a++)
+            p = cv_add(p, acc[a * stride + j]);
         cv_partial_add_mass(part, p);
         if (h != 0.0)
             part.sum = cv_add(part.sum, cv_mul(h, p <= 0.0 ? -INFINITY : log(p))); /* utils.py:32-35 */
@@ -238,6 +249,27 @@ __device__ double cvx_point(int lane, const CvModelDesc &m, const CvxPoint &P, c
     if (!(mass < 1.0))
         mass = 1.0;
     return cv_finish_loglik(part.sum, mass, m.tail);
+}
+
+__device__ __forceinline__ CvxPoint cvx_load_point(const CvModelDesc &m, const CvLattice &lat,
+                                                   const double *__restrict__ params, long long pi, int clip)
+{
+    double row[CV_MAX_PARAMS];
+    cvf_raw_row(m, lat, params, pi, row);
+    CvxPoint P;
+    P.c = cvf_clipped(m, row, clip, 0);
+    P.e = cvf_clipped(m, row, clip, 1);
+    P.q1 = P.two = P.many = P.base = 0.0;
+    P.n_copies = 1; /* basic model: the single copy o = 1 with weight 1 */
+    if (m.model_kind) {
+        P.q1 = cvf_clipped(m, row, clip, 2);
+        const double q2 = cvf_clipped(m, row, clip, 3), q = cvf_clipped(m, row, clip, 4);
+        P.two = cv_mul(cv_sub(1.0, P.q1), q2);
+        P.many = cv_mul(cv_mul(cv_sub(1.0, P.q1), cv_sub(1.0, q2)), q);
+        P.base = cv_sub(1.0, q);
+        P.n_copies = cvf_cutoff(m, P.q1, P.two, P.many, P.base) - 1; /* models.py:235 */
+    }
+    return P;
 }
 
 /* the marked points of a batch: their indices, in any order */
@@ -260,43 +292,73 @@ cv_marked_list_kernel(const double *__restrict__ out_ll, long long n, unsigned i
         list[at + __popc(ballot & ((1u << lane) - 1))] = (unsigned int)i;
 }
 
+/* One warp per marked point.  Points with more than CVX_HEAVY copy numbers would keep a single warp
+ * busy for milliseconds (cfg4: 50 copies x 5000 bins): they go to a second list, which
+ * cv_faithful_heavy_kernel works off with a whole CTA per point. */
+#define CVX_HEAVY 8
+#define CVX_HEAVY_THREADS 512
 __global__ void __launch_bounds__(CVX_THREADS)
 cv_faithful_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                    const double *__restrict__ params, int clip, double *__restrict__ out_ll, CvFaithTables ft,
-                   const unsigned int *__restrict__ list, const unsigned long long *__restrict__ count,
-                   unsigned long long *__restrict__ cursor)
+                   const unsigned int *__restrict__ list, unsigned long long *__restrict__ counters,
+                   unsigned int *__restrict__ heavy_list)
 {
     const int lane = threadIdx.x & 31;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *acc = ft.scratch + gw * ft.acc_doubles;
-    const unsigned long long total = *count;
+    const unsigned long long total = counters[0];
     for (;;) {
         unsigned long long it = 0;
         if (lane == 0)
-            it = atomicAdd(cursor, 1ULL);
+            it = atomicAdd(counters + 1, 1ULL);
         it = __shfl_sync(CV_FULL_MASK, it, 0);
         if (it >= total)
             break;
         const long long pi = list[it];
-        double row[CV_MAX_PARAMS];
-        cvf_raw_row(m, lat, params, pi, row);
-        CvxPoint P;
-        P.c = cvf_clipped(m, row, clip, 0);
-        P.e = cvf_clipped(m, row, clip, 1);
-        P.q1 = P.two = P.many = P.base = 0.0;
-        P.n_copies = 1; /* basic model: the single copy o = 1 with weight 1 */
-        if (m.model_kind) {
-            P.q1 = cvf_clipped(m, row, clip, 2);
-            const double q2 = cvf_clipped(m, row, clip, 3), q = cvf_clipped(m, row, clip, 4);
-            P.two = cv_mul(cv_sub(1.0, P.q1), q2);
-            P.many = cv_mul(cv_mul(cv_sub(1.0, P.q1), cv_sub(1.0, q2)), q);
-            P.base = cv_sub(1.0, q);
-            P.n_copies = cvf_cutoff(m, P.q1, P.two, P.many, P.base) - 1; /* models.py:235 */
+        const CvxPoint P = cvx_load_point(m, lat, params, pi, clip);
+        if (P.n_copies > CVX_HEAVY) {
+            if (lane == 0)
+                heavy_list[atomicAdd(counters + 2, 1ULL)] = (unsigned int)pi;
+            continue;
         }
-        const double r = cvx_point(lane, m, P, ft, acc);
+        cvx_accumulate(lane, m, P, ft, acc, 1, 1);
+        const double r = cvx_finish(lane, m, ft, acc, 1, 0);
         if (lane == 0)
             out_ll[pi] = r;
         __syncwarp();
+    }
+}
+
+/* One CTA per point with many copy numbers: warp w takes the copies w + 1, w + 1 + W, ..., the shares
+ * meet in cvx_finish in a fixed order (the value does not depend on which CTA got the point). */
+__global__ void __launch_bounds__(CVX_HEAVY_THREADS, 1)
+cv_faithful_heavy_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
+                         const double *__restrict__ params, int clip, double *__restrict__ out_ll, CvFaithTables ft,
+                         const unsigned int *__restrict__ heavy_list, unsigned long long *__restrict__ counters)
+{
+    __shared__ unsigned long long s_it;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int W = CVX_HEAVY_THREADS / 32;
+    double *acc0 = ft.scratch + (long long)blockIdx.x * W * ft.acc_doubles;
+    const unsigned long long total = counters[2];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_it = atomicAdd(counters + 3, 1ULL);
+        __syncthreads();
+        const unsigned long long it = s_it;
+        if (it >= total)
+            break;
+        const long long pi = heavy_list[it];
+        const CvxPoint P = cvx_load_point(m, lat, params, pi, clip);
+        cvx_accumulate(lane, m, P, ft, acc0 + warp * ft.acc_doubles, warp + 1, W);
+        __threadfence_block();
+        __syncthreads();
+        if (warp == 0) {
+            const double r = cvx_finish(lane, m, ft, acc0, P.n_copies < W ? P.n_copies : W, ft.acc_doubles);
+            if (lane == 0)
+                out_ll[pi] = r;
+        }
     }
 }
 
@@ -323,7 +385,8 @@ cudaError_t cv_launch_faithful(const CvModelDesc &m, const CvLattice &lat, const
 {
     if (n <= 0)
         return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream);
+    /* counters: marked points, cursor, points with many copies, cursor */
+    cudaError_t e = cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess)
         return e;
     cv_marked_list_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, stream>>>(out_ll, n, list, counters);
@@ -333,6 +396,11 @@ cudaError_t cv_launch_faithful(const CvModelDesc &m, const CvLattice &lat, const
     if (ctas > 2 * n_sm)
         ctas = 2 * n_sm;
     cv_faithful_kernel<<<(unsigned int)ctas, CVX_THREADS, 0, stream>>>(m, lat, params, clip, out_ll, ft, list, counters,
-                                                                   counters + 1);
+                                                                   list + n);
+    if ((e = cudaGetLastError()) != cudaSuccess)
+        return e;
+    /* the same scratch: n_sm CTAs x 16 warps = the 2 n_sm x 8 warps of the kernel before */
+    cv_faithful_heavy_kernel<<<(unsigned int)(n < n_sm ? n : n_sm), CVX_HEAVY_THREADS, 0, stream>>>(
+        m, lat, params, clip, out_ll, ft, list + n, counters);
     return cudaGetLastError();
 }

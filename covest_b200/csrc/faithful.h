@@ -19,8 +19,9 @@ struct CvFaithTables {
 int cv_faithful_warps(int n_sm);
 
 /* Re-evaluates every point whose value in out_ll is marked (finite and below CV_BAND_LL, cvmodel.h)
- * and overwrites it.  list: n entries of scratch; counters: two device words (marked points of the
- * call, work cursor), zeroed here. */
+ * and overwrites it.  list: 2 n entries of scratch (marked points, those of them with many copy
+ * numbers); counters: four device words (marked points of the call, cursor, points with many copies,
+ * cursor), zeroed here. */
 cudaError_t cv_launch_faithful(const CvModelDesc &m, const CvLattice &lat, const double *params, long long n,
                                int clip, double *out_ll, const CvFaithTables &ft, int n_sm, unsigned int *list,
                                unsigned long long *counters, cudaStream_t stream);

@@ -4,6 +4,8 @@ TAG=${1:-r02}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest rc=$?"; tail -4 gpurun_out/${TAG}_pytest.log
+PARITY_EXTRA=--lattice timeout 900 python tools/parity_report.py > gpurun_out/${TAG}_parity.json 2> gpurun_out/${TAG}_parity.err
+echo "parity rc=$?"; grep -c '"bad": 0' gpurun_out/${TAG}_parity.json
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench rc=$?"; tail -c 300 gpurun_out/${TAG}_bench.json
 timeout 900 python bench.py --impl reference > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
