@@ -466,10 +466,11 @@ def run_b200(args, rank, world, local_rank):
 
         # end to end: host buffers, the copies inside the timed region
         def step_host_lattice():
-            ll, rows = ctx.lattice_eval(axes, first=rank, stride=world, count=count, block=block, k_best=K_BEST)
-            if world > 1:
-                rows = parallel.merge_topk(parallel.allgather_rows(torch.from_numpy(rows).to(dev)), K_BEST).cpu().numpy()
-            return ll, rows
+            if world > 1:  # the best rows stay on the device for the all-gather; the values go to host memory
+                ll, rows = ctx.lattice_eval(axes, first=rank, stride=world, count=count, block=block, k_best=K_BEST,
+                                            out_rows=dev_rows, stream=stream)
+                return ll, parallel.merge_topk(parallel.allgather_rows(rows), K_BEST).cpu().numpy()
+            return ctx.lattice_eval(axes, first=rank, stride=world, count=count, block=block, k_best=K_BEST)
         e2e_s = timed_host(step_host_lattice, steps, 3)
         rec = {
             'cfg': cfg, 'model': model, 'ctx': ctx, 'hist': hist, 'axes': axes, 'count': count, 'block': block,
