@@ -354,9 +354,13 @@ def run_b200(args, rank, world, local_rank):
         raise SystemExit('bench.py needs a CUDA device (the library has no CPU path)')
     torch.cuda.set_device(local_rank)
     os.environ['COVEST_B200_DEVICE'] = str(local_rank)
+    json_out = sys.stdout
     if world > 1:
         import datetime
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # NCCL's version banner must not share stdout with the JSON line
+        # NCCL prints its version banner on file descriptor 1: everything but the JSON line goes to stderr
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
                                 timeout=datetime.timedelta(seconds=180))
     dev = torch.device('cuda', local_rank)
@@ -683,7 +687,7 @@ def run_b200(args, rank, world, local_rank):
                 line['covest_e2e'] = covest_end_to_end(cores)
             except Exception as exc:  # never lose the throughput line over the extra figure
                 line['covest_e2e'] = {'error': repr(exc)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     barrier()
     if world > 1:
         dist.destroy_process_group()
