@@ -28,6 +28,9 @@ BIG_CONFIGS = {
     'cfg3': dict(model='repeats', k=21, r=100, theta=(30.0, 0.03, 0.7, 0.5, 0.5), bins=1000, kmers=1e8, seed=1003),
     'cfg4': dict(model='repeats', k=31, r=150, theta=(200.0, 0.01, 0.7, 0.5, 0.28), bins=5000, kmers=1e7, seed=1004),
     'cfg5': dict(model='repeats', k=21, r=100, theta=(30.0, 0.03, 0.7, 0.5, 0.5), bins=2000, kmers=1e8, seed=1005),
+    # cfg2 trimmed at 30 with the rest of the counts as the tail (models.py:103-104: the mass term)
+    'cfg2t': dict(model='repeats', k=21, r=100, theta=(30.0, 0.03, 0.7, 0.5, 0.5), bins=300, kmers=1e7, seed=1002,
+                  trim=30),
 }
 
 
@@ -68,6 +71,8 @@ def big_points(name, n=N_BIG):
             pts[5 + i] = [(200 * nn + d) / (1 - e) ** k * r / (r - k + 1), e]
         return np.ascontiguousarray(pts)
     q_lo = 0.05 if name == 'cfg4' else 0.02
+    if name == 'cfg2t':  # stay where the histogram carries most of the mass: the tail term is the point here
+        cols = [c0 * 3 ** rng.uniform(-0.5, 0.5, n), np.exp(rng.uniform(np.log(3e-3), np.log(.2), n))]
     q = np.where(rng.uniform(size=n) < 0.4, rng.uniform(q_lo, 0.3, n), rng.uniform(0.3, 1, n))
     cols += [rng.uniform(.3, 1, n), rng.uniform(0, 1, n), q]
     pts = np.column_stack(cols)
@@ -106,12 +111,13 @@ def big_path(name):
 
 
 def load_big(name):
-    """-> dict(cfg, hist {j: h}, points (10^4 x n_param), ll (oracle), digest-checked)."""
+    """-> dict(cfg, hist {j: h}, tail, points (10^4 x n_param), ll (oracle), digest-checked)."""
     with np.load(big_path(name)) as z:
         hist = {int(j): int(h) for j, h in zip(z['hist_j'], z['hist_h'])}
         ll = z['ll'].astype(np.float64)
         digest = str(z['points_sha256'])
+        tail = int(z['tail']) if 'tail' in z else 0
     pts = big_points(name, len(ll))
     if points_digest(pts) != digest:
         raise RuntimeError('big_points(%r) no longer reproduces the points the fixture was made on' % name)
-    return dict(cfg=BIG_CONFIGS[name], hist=hist, points=pts, ll=ll)
+    return dict(cfg=BIG_CONFIGS[name], hist=hist, tail=tail, points=pts, ll=ll)

@@ -35,11 +35,16 @@ def main(names):
     for name in names:
         cfg = bigpoints.BIG_CONFIGS[name]
         j, h = histogram(cfg)
+        tail = 0
+        if cfg.get('trim'):  # histogram.py:111-134 trim_hist: bins below the cut stay, the rest is the tail
+            keep = j < cfg['trim']
+            tail = int(h[~keep].sum())
+            j, h = j[keep], h[keep]
         pts = bigpoints.big_points(name)
-        m = orc.Model(cfg['model'], cfg['k'], cfg['r'], dict(zip(j.tolist(), h.tolist())), 0, max_error=8)
+        m = orc.Model(cfg['model'], cfg['k'], cfg['r'], dict(zip(j.tolist(), h.tolist())), tail, max_error=8)
         t0 = time.time()
         ll = m.loglik_batch(pts, mode=orc.LADDER, threads=threads)
-        np.savez_compressed(bigpoints.big_path(name), hist_j=j, hist_h=h, ll=ll,
+        np.savez_compressed(bigpoints.big_path(name), hist_j=j, hist_h=h, ll=ll, tail=np.array(tail),
                             points_sha256=np.array(bigpoints.points_digest(pts)))
         fin = np.isfinite(ll)
         print('%s: %d points x %d bins in %.0f s; finite %d, -inf %d, +inf/nan %d' % (

@@ -7,8 +7,10 @@ three device paths, at 1e-9 relative with no carve-out inside the reference's nu
 import numpy as np
 import pytest
 
+from oracle import covest_oracle as orc
 from tests import bigpoints
-from tests.helpers import rel_err_ll
+from tests.helpers import (case_ctor_kwargs, case_hist, context_for, golden_case_names, load_case,
+                           rel_err_ll)
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +21,7 @@ def _model(big):
     from covest_b200.models import BasicModel, RepeatsModel
     cfg = big['cfg']
     cls = RepeatsModel if cfg['model'] == 'repeats' else BasicModel
-    return cls(cfg['k'], cfg['r'], big['hist'], 0, max_error=8)
+    return cls(cfg['k'], cfg['r'], big['hist'], big['tail'], max_error=8)
 
 
 def check(name, path):
@@ -43,27 +45,27 @@ def check(name, path):
     return info
 
 
-@pytest.mark.parametrize('name', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5'])
+@pytest.mark.parametrize('name', ['cfg1', 'cfg2', 'cfg2t', 'cfg3', 'cfg4', 'cfg5'])
 def test_big_golden_default_path(name):
     check(name, 0)
 
 
-@pytest.mark.parametrize('name', ['cfg2', 'cfg3', 'cfg4', 'cfg5'])
+@pytest.mark.parametrize('name', ['cfg2', 'cfg2t', 'cfg3', 'cfg4', 'cfg5'])
 def test_big_golden_per_point_kernel(name):
     assert check(name, 1)['kernel'] == 'cv_loglik_kernel'
 
 
-@pytest.mark.parametrize('name', ['cfg2', 'cfg3', 'cfg4', 'cfg5'])
+@pytest.mark.parametrize('name', ['cfg2', 'cfg2t', 'cfg3', 'cfg4', 'cfg5'])
 def test_big_golden_factored_gemm(name):
     assert check(name, 3)['kernel'] == 'cvf_gemm_kernel'
 
 
-@pytest.mark.parametrize('name', ['cfg2', 'cfg3', 'cfg4', 'cfg5'])
+@pytest.mark.parametrize('name', ['cfg2', 'cfg2t', 'cfg3', 'cfg4', 'cfg5'])
 def test_big_golden_factored_prefix(name):
     assert check(name, 4)['kernel'] == 'cvf_prefix_kernel'
 
 
-@pytest.mark.parametrize('name', ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5'])
+@pytest.mark.parametrize('name', ['cfg1', 'cfg2', 'cfg2t', 'cfg3', 'cfg4', 'cfg5'])
 def test_big_golden_term_by_term_kernel(name):
     """The kernel that re-evaluates points with subnormal bin probabilities in the reference's order
     of operations (csrc/faithful.cu), run on EVERY point: it must agree with the oracle everywhere."""
@@ -104,3 +106,17 @@ def test_cfg3_lattice_points_with_subnormal_bins_match_the_oracle():
     m = orc.Model('repeats', cfg['k'], cfg['r'], big['hist'], 0, max_error=8)
     want = m.loglik_batch(pts[pick], threads=8)
     assert rel_err_ll(vals[0][pick], want).max() <= LL_RTOL
+
+
+@pytest.mark.parametrize('name', golden_case_names())
+def test_term_by_term_kernel_on_the_reference_goldens(name):
+    """Every golden case produced by the unmodified reference -- sparse key sets, histograms with a
+    tail, all k + 1 error classes (S = 22), a coverage bound -- through the term-by-term kernel."""
+    case = load_case(name)
+    m = orc.Model(case['model'], case['k'], case['r'], case_hist(case), case['tail'], **case_ctor_kwargs(case))
+    with context_for(m) as ctx:
+        ctx.set_path(ctx.PATH_TERM_BY_TERM)
+        got = ctx.loglik(case['points'])
+        assert ctx.last_path_info()['kernel'] == 'cv_faithful_kernel'
+    rel = rel_err_ll(got, np.array(case['ll'], dtype=float))
+    assert rel.max() <= LL_RTOL, (name, int(rel.argmax()), case['points'][int(rel.argmax())])

@@ -18,7 +18,7 @@ from tests.helpers import rel_err_ll  # noqa: E402
 from tests.test_gpu_big_golden import _model  # noqa: E402
 
 out = []
-for name in sys.argv[1:] or ['cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5']:
+for name in sys.argv[1:] or ['cfg1', 'cfg2', 'cfg2t', 'cfg3', 'cfg4', 'cfg5']:
     big = bigpoints.load_big(name)
     want = big['ll']
     inside = ~(np.isposinf(want) | np.isnan(want))
