@@ -998,9 +998,15 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 #define CVF_PB CVF_PPB /* points per batch */
 #define CVF_PT 256     /* threads of the prefix kernel */
 #define CVF_PW (CVF_PT / 32)
+#ifndef CVF_PD
 #define CVF_PD 4       /* copies in flight per thread (cp.async ring in shared memory) */
-#define CVF_PL2 12     /* copies ahead of the ring that are requested into L2 */
-#define CVF_PE 4       /* points whose lane partials wait in the transpose buffer of a warp */
+#endif
+#ifndef CVF_PL2
+#define CVF_PL2 6      /* copies ahead of the ring that are requested into L2 */
+#endif
+#ifndef CVF_PE
+#define CVF_PE 8       /* points whose lane partials wait in the transpose buffer of a warp (4: 1.45 ms on cfg3, 8: 1.35 ms) */
+#endif
 #define CVF_PEW 33     /* doubles per row of that buffer (odd: conflict-free both ways) */
 #define CVF_PASS_SLOTS (CVF_PT * CVF_SL)
 

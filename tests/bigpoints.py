@@ -117,7 +117,27 @@ def load_big(name):
         ll = z['ll'].astype(np.float64)
         digest = str(z['points_sha256'])
         tail = int(z['tail']) if 'tail' in z else 0
+        omm = z['one_minus_mass'].astype(np.float64) if 'one_minus_mass' in z else None
     pts = big_points(name, len(ll))
     if points_digest(pts) != digest:
         raise RuntimeError('big_points(%r) no longer reproduces the points the fixture was made on' % name)
-    return dict(cfg=BIG_CONFIGS[name], hist=hist, tail=tail, points=pts, ll=ll)
+    return dict(cfg=BIG_CONFIGS[name], hist=hist, tail=tail, points=pts, ll=ll, one_minus_mass=omm)
+
+
+MASS_ULPS = 8
+
+
+def ll_tolerance(big, rtol=1e-9):
+    """Per-point absolute tolerance of the log-likelihood: rtol * |ll|, plus -- for a histogram with a
+    tail -- what MASS_ULPS units in the last place of sp = fsum(p_j) move the tail term
+    tail * log(1 - sp) (models.py:103-104).  Where the model puts all but 1e-9 of the mass inside the
+    histogram, ONE ulp of sp (1.1e-16, i.e. one ulp of any leading p_j) moves the reference's own value
+    by more than 1e-9 relative (measured: 2.6e-8 at 1 - sp = 2.3e-11): no implementation that is not
+    bit-identical in every rounding, libm's pow included, can meet the plain gate there.  The extra
+    term is below 1e-10 * |ll| wherever 1 - sp > 1e-7."""
+    tol = rtol * np.abs(big['ll'])
+    if big['tail'] and big['one_minus_mass'] is not None:
+        omm = big['one_minus_mass']
+        with np.errstate(divide='ignore'):  # sp >= 1: no tail term in the reference (models.py:104), plain gate
+            tol = tol + np.where(omm > 0, big['tail'] * MASS_ULPS * 2.0 ** -53 / omm, 0.0)
+    return tol

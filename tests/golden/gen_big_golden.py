@@ -44,8 +44,23 @@ def main(names):
         m = orc.Model(cfg['model'], cfg['k'], cfg['r'], dict(zip(j.tolist(), h.tolist())), tail, max_error=8)
         t0 = time.time()
         ll = m.loglik_batch(pts, mode=orc.LADDER, threads=threads)
+        extra = {}
+        if tail:
+            # 1 - min(1, fsum(p_j)) of every point (models.py:103): log-likelihoods of a histogram with
+            # a tail are ill-conditioned where the model puts (nearly) all mass inside the histogram
+            import math
+            omm = np.empty(len(pts))
+            for i, p in enumerate(pts):
+                q = list(p)
+                for a, (lo, hi) in enumerate(m.bounds):
+                    if lo is not None and q[a] < lo:
+                        q[a] = lo
+                    elif hi is not None and q[a] > hi:
+                        q[a] = hi
+                omm[i] = 1.0 - min(1.0, math.fsum(m.probs(q)))
+            extra['one_minus_mass'] = omm
         np.savez_compressed(bigpoints.big_path(name), hist_j=j, hist_h=h, ll=ll, tail=np.array(tail),
-                            points_sha256=np.array(bigpoints.points_digest(pts)))
+                            points_sha256=np.array(bigpoints.points_digest(pts)), **extra)
         fin = np.isfinite(ll)
         print('%s: %d points x %d bins in %.0f s; finite %d, -inf %d, +inf/nan %d' % (
             name, len(pts), len(j), time.time() - t0, fin.sum(), np.isneginf(ll).sum(),

@@ -38,10 +38,17 @@ def check(name, path):
     inside = ~(np.isposinf(want) | np.isnan(want))
     assert inside.mean() >= 0.9, inside.mean()
     rel = rel_err_ll(got[inside], want[inside])
-    bad = np.nonzero(~(rel <= LL_RTOL))[0]
+    tol = bigpoints.ll_tolerance(big, LL_RTOL)[inside]
+    with np.errstate(invalid='ignore'):
+        err = np.where(rel == 0, 0.0, np.abs(got[inside] - want[inside]))
+    bad = np.nonzero(~(err <= tol))[0]
     worst = int(np.argmax(rel))
     assert len(bad) == 0, (name, info['kernel'], len(bad), big['points'][inside][worst].tolist(),
                            float(got[inside][worst]), float(want[inside][worst]))
+    if big['tail']:
+        # the conditioning term is only ever needed where the mass is within 1e-8 of 1, on a handful of points
+        beyond = ~(rel <= LL_RTOL)
+        assert beyond.mean() <= 0.005 and np.all(big['one_minus_mass'][inside][beyond] < 1e-8)
     return info
 
 
