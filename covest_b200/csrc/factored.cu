@@ -4,11 +4,17 @@
  *   cvf_point_keys      K0: per point clip, cut-off O_thr, sort key ((c, e) hash | q | O_thr)
  *   cvf_heads / cvf_group_starts / cvf_group_counts / cvf_group_scan / cvf_tile_table
  *                       groups (equal (c, e)), q-runs (equal q inside a group) and tiles from the
- *                       sorted keys
+ *                       sorted keys -- the plan of an explicit point array
+ *   cvf_lattice_fill / cvf_lattice_order
+ *                       the same tables for a lattice handed over as its axes: from a template of
+ *                       one group computed on the host (cvf_lattice_template), no sort, nothing
+ *                       read back
  *   cvf_profile_kernel  K1: one warp per (group, 16 copy numbers): profiles over all bins
  *   cvf_prefix_kernel   K2p: one CTA per tile of up to four q-runs: running sums over the copy
  *                       numbers, per point the three-term combination + epilogue (the default for
  *                       batches whose points share q, as lattices do)
+ *   cvf_prefix2_kernel  the same on bulk copies (TMA) through an mbarrier ring, 8 slots per
+ *                       thread; selectable, slower
  *   cvf_weights_kernel, cvf_gemm_kernel   K1b, K2: one CTA per tile of 128 points: copy weights and
  *                       FP64 tensor-core GEMM + epilogue (batches that share (c, e) but not q)
  *
