@@ -64,9 +64,8 @@ struct cvb_ctx {
     cudaStream_t timed_stream = nullptr;
     /* the factored path of the repeats model (factored.h) */
     CvFactorWork fw;
-    const double2 *d_slot_mh = nullptr;
-    const int *d_step_mask = nullptr;
-    bool counts_first = false; /* cvf_counts_first(slot_h) */
+    CvfSlots slots;            /* the row layout of the profiles (factored.h) */
+    int table_lines = 0;       /* 64-slot lines of the histogram tables */
     const double *d_log_tab = nullptr;
     int path_mode = 0;         /* 0 auto, 1 per-point kernel only, 2 factored whenever supported */
     size_t w_limit = (size_t)2 << 30; /* doubles: 16 GiB of profiles per group range */
@@ -297,12 +296,19 @@ extern "C" int cvb_ctx_create(int model_kind, int k, int r, int max_error, int n
         if ((e = upload(c, T.run_len, &t.run_len)) != cudaSuccess) break;
         if ((e = upload(c, T.blk_run_begin, &t.blk_run_begin)) != cudaSuccess) break;
         {
-            std::vector<double2> mh(T.slot_mult.size());
-            for (size_t i = 0; i < mh.size(); i++)
-                mh[i] = make_double2(T.slot_mult[i], T.slot_h[i]);
-            if ((e = upload(c, mh, &c->d_slot_mh)) != cudaSuccess) break;
-            if ((e = upload(c, cvf_step_masks(T.slot_h), &c->d_step_mask)) != cudaSuccess) break;
-            c->counts_first = cvf_counts_first(T.slot_h);
+            /* rows of the profiles: the lines with counts, the others summed (COVEST_B200_ROWS=full: every line) */
+            const char *rows = getenv("COVEST_B200_ROWS");
+            std::vector<int> line_map;
+            std::vector<double2> mh;
+            std::vector<double> row_h;
+            cvf_build_slots(T.slot_mult, T.slot_h, !(rows && !strcmp(rows, "full")), line_map, mh, row_h,
+                            &c->slots.sum_line);
+            c->table_lines = (int)line_map.size();
+            c->slots.nsteps = (int)(row_h.size() / 64);
+            if ((e = upload(c, line_map, &c->slots.line_map)) != cudaSuccess) break;
+            if ((e = upload(c, mh, &c->slots.slot_mh)) != cudaSuccess) break;
+            if ((e = upload(c, cvf_step_masks(row_h), &c->slots.step_mask)) != cudaSuccess) break;
+            c->slots.counts_first = cvf_counts_first(row_h);
             std::vector<double> lt(2 * CV_LOG_N);
             cv_log_table(lt.data());
             if ((e = upload(c, lt, &c->d_log_tab)) != cudaSuccess) break;
@@ -415,10 +421,10 @@ static int launch_loglik(cvb_ctx *ctx, const CvLattice &lat, const double *const
     }
     if (try_factored) {
         ctx->fw.timed = ctx->timing;
-        CU(cvf_eval(ctx->desc, lat, lat_axes_host, d_params, n, clip, d_ll, ctx->d_slot_mh, ctx->d_step_mask,
+        CU(cvf_eval(ctx->desc, lat, lat_axes_host, d_params, n, clip, d_ll, ctx->slots,
                     ctx->d_log_tab, ctx->fw, ctx->n_sm,
                     ctx->smem_max, ctx->w_limit, forced ? 0.0 : ctx->min_group, ctx->min_run,
-                    ctx->path_mode == 3 ? 1 : ctx->path_mode == 4 ? 2 : 0, ctx->counts_first, s, &used),
+                    ctx->path_mode == 3 ? 1 : ctx->path_mode == 4 ? 2 : 0, s, &used),
            "factored evaluation");
         ctx->last_launches += ctx->fw.launches;
     }
@@ -837,6 +843,7 @@ extern "C" int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out)
     }
     if (ctx->last_path >= 2) {
         v[10] = (double)ctx->fw.analytic;
+        v[11] = (double)ctx->slots.nsteps;
         const CvFactorWork &w = ctx->fw;
         v[1] = (double)w.n_groups;
         v[2] = (double)w.n_tiles;

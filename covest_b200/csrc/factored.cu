@@ -437,7 +437,10 @@ __device__ __forceinline__ int cvf_find_warp(const int *__restrict__ start, int 
 /* Layout of the profiles of a group in HBM: one ROW per copy number, [copy][line][pair L][2]: a
  * row holds all (padded) slots of the histogram in lines of 64 slots (one N-step of K2), and inside
  * a line pair L = 8 * (row of the N-step) + column % 8 holds the slots with columns c and c + 8 of
- * that row.  K1 writes 512 contiguous bytes per (copy, line) with one warp-wide store; the prefix
+ * that row.  The lines of a row are those of the histogram tables that hold a bin with a count, in
+ * their order, and -- when there are others -- one more line with the column sums of the others
+ * (CvfSlots, factored.h): the bins without counts enter the result through the mass only, and the
+ * mass is linear in the profiles.  K1 writes 512 contiguous bytes per (copy, line) with one warp-wide store; the prefix
  * kernel fetches whole rows (a pass of 1024 slots = 8 KB contiguous) with bulk copies; K2 scatters
  * 16 rows x one line into its fragment order while loading. */
 #define CVF_STAGE_DOUBLES (CV_GB * CV_NA_MAX * CV_W)
@@ -449,6 +452,7 @@ __device__ __forceinline__ int cvf_find_warp(const int *__restrict__ start, int 
 template <int NA>
 __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int nsteps,
                                                   const double *__restrict__ slot_mult /* pairs */,
+                                                  const int *__restrict__ line_map, int sum_line,
                                                   double *__restrict__ Wg, double *stage, const double *acc)
 {
     const int r = lane >> 2, q = lane & 3;
@@ -461,8 +465,9 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
                 make_double2(acc[4 * mt + c], acc[4 * mt + 2 + c]);
         }
     __syncwarp();
-    /* row o - 1 of the group's profiles, 64-slot line blk * 2 NA + ns, pair `lane` */
-    double *tile0 = Wg + (long long)(o - 1) * nsteps * CVF_NS + (long long)blk * (2 * NA) * CVF_NS + lane * 2;
+    /* row o - 1 of the group's profiles, pair `lane` of its lines */
+    double *row0 = Wg + (long long)(o - 1) * nsteps * CVF_NS + lane * 2;
+    double2 rest = make_double2(0.0, 0.0); /* the lane's columns of the lines without counts */
 #pragma unroll
     for (int ns = 0; ns < 2 * NA; ns++) {
         const int row = 4 * ns + (lane >> 3);
@@ -473,15 +478,31 @@ __device__ __forceinline__ void cvf_store_profile(int lane, int blk, int o, int 
         const double2 mm = __ldg(reinterpret_cast<const double2 *>(slot_mult) + (blk * (2 * NA) + ns) * 32 + lane);
         v.x = cv_mul(v.x, mm.x); /* the accumulators are finite (that is what the scale is for): times 0 is 0 */
         v.y = cv_mul(v.y, mm.y);
-        *reinterpret_cast<double2 *>(tile0 + ns * CVF_NS) = v;
+        const int line = __ldg(line_map + blk * (2 * NA) + ns); /* the same in every lane */
+        if (line >= 0) {
+            *reinterpret_cast<double2 *>(row0 + line * CVF_NS) = v;
+        } else {
+            rest.x = cv_add(rest.x, v.x);
+            rest.y = cv_add(rest.y, v.y);
+        }
+    }
+    if (sum_line >= 0) {
+        /* one sum per lane: the first half of the line; block after block adds to the lane's own
+         * double, a fixed order.  The second half stays zero (K2 reads whole lines). */
+        double *dst = Wg + ((long long)(o - 1) * nsteps + sum_line) * CVF_NS + lane;
+        double sum = cv_add(rest.x, rest.y);
+        if (blk > 0)
+            sum = cv_add(*dst, sum);
+        dst[0] = sum;
+        dst[32] = 0.0;
     }
     __syncwarp();
 }
 
 template <int NA>
 __device__ __forceinline__ void cvf_profile_item(int lane, const CvModelDesc &m, CvWarpMem &M,
-                                                 int o0, int omax4, int nsteps, double *__restrict__ Wg,
-                                                 double *stage)
+                                                 int o0, int omax4, int nsteps, const int *__restrict__ line_map,
+                                                 int sum_line, double *__restrict__ Wg, double *stage)
 {
     const int sp = cvf_copy_slots(m.n_err);
     const int cpt = cvf_copies_per_tile(m.n_err);
@@ -500,7 +521,7 @@ __device__ __forceinline__ void cvf_profile_item(int lane, const CvModelDesc &m,
                 for (int i = 0; i < 4 * NA; i++)
                     acc[i] = 0.0;
                 cv_w_fused<NA>(lane, G, cc * kpc, (cc + 1) * kpc, *M.fx, acc);
-                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, m.tab.slot_mult_pair, Wg, stage, acc);
+                cvf_store_profile<NA>(lane, blk, oa + cc, nsteps, m.tab.slot_mult_pair, line_map, sum_line, Wg, stage, acc);
             }
             __syncwarp();
         }
@@ -511,7 +532,7 @@ __global__ void __launch_bounds__(32 * CV_WARPS_MAX, 1)
 cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                    const double *__restrict__ params, int clip, CvfPlan pl, int n_groups,
                    int first_item, int n_items, double *__restrict__ W, long long w_base, int nsteps,
-                   unsigned long long *counter, int groups_staged)
+                   const int *__restrict__ line_map, int sum_line, unsigned long long *counter, int groups_staged)
 {
     extern __shared__ __align__(16) unsigned char cv_smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -552,10 +573,10 @@ cvf_profile_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant_
         double *Wg = W + (pl.w_off[g] - w_base);
         const int o0 = kchunk * CVF_KC + 1;
         switch (m.na) {
-        case 1: cvf_profile_item<1>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
-        case 2: cvf_profile_item<2>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
-        case 4: cvf_profile_item<4>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
-        default: cvf_profile_item<8>(lane, m, M, o0, omax4, nsteps, Wg, stage); break;
+        case 1: cvf_profile_item<1>(lane, m, M, o0, omax4, nsteps, line_map, sum_line, Wg, stage); break;
+        case 2: cvf_profile_item<2>(lane, m, M, o0, omax4, nsteps, line_map, sum_line, Wg, stage); break;
+        case 4: cvf_profile_item<4>(lane, m, M, o0, omax4, nsteps, line_map, sum_line, Wg, stage); break;
+        default: cvf_profile_item<8>(lane, m, M, o0, omax4, nsteps, line_map, sum_line, Wg, stage); break;
         }
     }
 }
@@ -986,7 +1007,7 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
  * and all cut-offs O_thr of such a *q-run* are served by ONE running sum over the copies: the
  * contraction over o is done once per q-run instead of once per point.  A CTA takes a tile (one
  * batch: up to CVF_NQ whole q-runs of a group with up to CVF_PB points; or a window of a longer
- * run).  Every thread owns CVF_SL slots per pass and keeps the CVF_NQ running sums of its slots in
+ * run).  Every thread owns SL slots per pass (template parameter, 3 or 4) and keeps the CVF_NQ running sums of its slots in
  * registers.  The points of the batch are put in the order of their cut-offs once (the *schedule*);
  * the threads then walk the copies upwards -- the profile of copy o travels through a private
  * cp.async ring, CVF_PD copies ahead -- and finish every point as soon as its copies are in: the
@@ -995,15 +1016,17 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
  * at a time.  Values do not depend on what else is in the batch: a point's sums run over its own
  * copies and over the bins in a fixed order.
  *
- * Slots to threads: a pass covers 32 * CVF_PW * CVF_SL slots = CVF_PW * CVF_SL half-lines (a line
- * = the 64 doubles of one copy and one N-step in the layout of K1); warp w takes the half-lines
- * u = i * CVF_PW + w, i < CVF_SL, lane l the double l of each.  Bins with counts usually are the
+ * Slots to threads: a CTA has NW warps (template parameter: 8 for rows of more than 768 slots, else
+ * as many as it takes to cover the row in one pass -- histograms with few bins that have counts,
+ * cvf_build_slots); a pass covers 32 * NW * SL slots = NW * SL half-lines (a line = the 64
+ * doubles of one copy and one N-step in the layout of K1); warp w takes the half-lines
+ * u = i * NW + w, i < SL, lane l the double l of each.  Bins with counts usually are the
  * first ones of the histogram, so this deals them evenly to the warps. */
 #define CVF_NQ CVF_PNQ /* q-runs whose running sums a thread holds */
-#define CVF_SL 4       /* slots per thread and pass */
+#ifndef CVF_WARPS_SM
+#define CVF_WARPS_SM 16 /* warps per SM the register budget of the prefix kernel is cut for */
+#endif
 #define CVF_PB CVF_PPB /* points per batch */
-#define CVF_PT 256     /* threads of the prefix kernel */
-#define CVF_PW (CVF_PT / 32)
 #ifndef CVF_PD
 #define CVF_PD 4       /* copies in flight per thread (cp.async ring in shared memory) */
 #endif
@@ -1014,7 +1037,6 @@ cvf_gemm_kernel(const __grid_constant__ CvModelDesc m, CvfPlan pl, int first_til
 #define CVF_PE 8       /* points whose lane partials wait in the transpose buffer of a warp (4: 1.45 ms on cfg3, 8: 1.35 ms) */
 #endif
 #define CVF_PEW 33     /* doubles per row of that buffer (odd: conflict-free both ways) */
-#define CVF_PASS_SLOTS (CVF_PT * CVF_SL)
 
 struct __align__(16) CvfEvent {
     double q1, two, many;
@@ -1048,31 +1070,35 @@ __device__ __forceinline__ void cvf_sts64(unsigned int a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-#define CVF_LOG_REP 1 /* 8 interleaved copies make the lookups free of bank conflicts; measured: no gain (1.444 ms either way) */
+#ifndef CVF_LOG_REP
+#define CVF_LOG_REP 1
+#endif
+/* CVF_LOG_REP: 8 interleaved copies make the lookups free of bank conflicts; measured: no gain (1.444 ms either way) */
 struct CvfPrefixSmem {
     double log_tab[2 * CV_LOG_N * CVF_LOG_REP]; /* CVF_LOG_REP interleaved copies of cv_log_table */
     /* the points of the batch by ascending cut-off (the schedule), 32 bytes each: weights of
      * copy 1, copy 2 and of the running sum; batch position | run << 16; copies = O_thr - 1 */
     CvfEvent ev[CVF_PB + 2];
-    int need[CVF_PB];  /* by batch position: copies of the point */
     double base[CVF_NQ];
     int seg[CVF_NQ + 1]; /* batch positions where its q-runs start */
     int tile, bend;
     /* then, in this order:
-     *   double ring[CVF_PD][CVF_SL][CVF_PT]   every thread's own slots of the copies in flight
-     *   double tbuf[planes][CVF_PW][CVF_PE][CVF_PEW]   lane partials of the last points, per warp
+     *   double ring[CVF_PD][SL][threads]   every thread's own slots of the copies in flight
+     *   double tbuf[planes][warps][CVF_PE][CVF_PEW]   lane partials of the last points, per warp
+     *                                           (while the schedule is built: int need[CVF_PB], the
+     *                                           copies of the points by batch position)
      * planes = 2 (sum, mass) or, with a tail, 3 (sum, mass high, mass low: compensated)
      * and in global memory, per CTA (L2-resident scratch):
-     *   double red[3][CVF_PW][CVF_PB]    per (warp, point) partial */
+     *   double red[3][warps][CVF_PB]    per (warp, point) partial */
 };
-#define CVF_RING_BYTES (CVF_PD * CVF_SL * CVF_PT * 8)
 #define CVF_SMEM_HEAD ((sizeof(CvfPrefixSmem) + 127) & ~(size_t)127)
-#define CVF_TBUF_DOUBLES (CVF_PW * CVF_PE * CVF_PEW)
 
-static size_t cvf_prefix_smem_bytes(bool mass)
+/* nw = warps of the CTA (the kernel's NW), sl = slots per thread and pass (its SL) */
+static size_t cvf_prefix_smem_bytes(bool mass, int nw, int sl)
 {
     const size_t planes = mass ? 3 : 2;
-    return CVF_SMEM_HEAD + CVF_RING_BYTES + planes * CVF_TBUF_DOUBLES * sizeof(double);
+    return CVF_SMEM_HEAD + (size_t)CVF_PD * sl * 32 * nw * 8 +
+           planes * (size_t)nw * CVF_PE * CVF_PEW * sizeof(double);
 }
 
 /* ---- mbarrier and bulk-copy (TMA) primitives of the prefix kernels ---- */
@@ -1128,40 +1154,23 @@ __device__ __noinline__ double cvf_log_rare(double x)
 #define CVF_FAST_SPAN (0x7ff00000u - (unsigned int)CVF_FAST_LO)
 
 /* cv_log_tab's algorithm for positive normal x with the index arithmetic on the high word and the
- * table at the shared-window address `tab_s`; everything else takes cvf_log_rare.  The
- * coefficients of r^5 .. r^7 and the high part of ln 2 are cut to 20 mantissa bits (they fit the
- * immediate field of the FP64 instructions; errors below 2^-58 and none: k * ln2_hi stays exact);
- * the polynomial in Estrin form, the last sum reordered: absolute error below 2.5e-16 (1 + |log x|)
- * (cv_log_tab: 2e-16). */
+ * table at the shared-window address `tab_s`; everything else takes cvf_log_rare.
+ *
+ * |r| <= 2^-8 on every table interval, so log1p(r) - r = r^2 (-1/2 + r/3 - r^2/4 + r^3/5) leaves
+ * r^6/6 <= 5.9e-16: with CVF_LOG_DEG 5 (the default) the logarithm is 9 FP64 instructions in four
+ * dependent steps -- k ln 2 + logc in one FMA (|k| <= 1100: 0.3 ulp of the result from the rounded
+ * ln 2), hi + r, and the polynomial joined by a last FMA.  Measured against logl over 4e7 arguments:
+ * relative error <= 9.3e-16 for x < 0.6875 (every probability of a bin that is not ~1), absolute
+ * error <= 5.8e-16 on [0.6875, 1.375).  CVF_LOG_DEG 7 is the earlier form (r^7 kept, ln 2 split in
+ * two, 14 instructions in six steps, 2.5e-16 (1 + |log x|)): the count-weighted sum has a 1e-9 gate
+ * and sees neither.  The coefficient of r^3 and those of r^5 .. r^7 are cut to 20 mantissa bits
+ * (they fit the immediate field of the FP64 instructions; errors below 2^-58). */
 /* REP: copies of the table side by side (entry e of copy c at 16 (e REP + c) bytes; tab_s already points
  * at the lane's copy): with 8 copies the 8 lanes of a quarter warp read 8 different 16-byte bank groups
  * whatever their arguments -- the lookups are free of bank conflicts */
-template <int REP = 1>
-__device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
-{
-    const int hi = __double2hiint(x);
-    if ((unsigned int)(hi - CVF_FAST_LO) >= CVF_FAST_SPAN)
-        return cvf_log_rare(x);
-    const int t = hi - (int)(CV_LOG_OFF >> 32);
-    const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
-    const double2 c = REP == 8 ? cvf_lds128(tab_s + ((t >> 6) & ((CV_LOG_N - 1) << 7)))
-                                : cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4))); /* (invc, logc) of interval (t >> 13) & 127 */
-    const double r = cv_fma(z, c.x, -1.0);
-    const double kd = (double)((t >> 20) - CV_PSCALE_EXP); /* log(x 2^-128) */
-    const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y); /* ln 2 to 20 bits */
-    /* log1p(r) - r = r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7), in three short dependent
-     * steps (Estrin) instead of five */
-    const double r2 = cv_mul(r, r);
-    const double a = cv_fma(r, 1.0 / 3.0, -0.5);
-    const double b = cv_fma(r, 0x1.9999ap-3 /* 1/5 */, -0.25);
-    const double c2 = cv_fma(r, 0x1.24925p-3 /* 1/7 */, -0x1.55555p-3 /* 1/6 */);
-    const double r4 = cv_mul(r2, r2);
-    const double ab = cv_fma(r2, b, a);
-    const double p = cv_fma(r4, c2, ab);
-    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.fdf473de6af28p-22)); /* ln 2 - 0x1.62e42p-1 */
-    return cv_add(cv_add(hi_part, r), lo); /* hi_part + r does not wait for the polynomial */
-}
-
+#ifndef CVF_LOG_DEG
+#define CVF_LOG_DEG 5
+#endif
 /* the fast path of cvf_safe_log alone: x positive, normal, finite */
 template <int REP = 1>
 __device__ __forceinline__ double cvf_log_fast(double x, unsigned int tab_s)
@@ -1170,19 +1179,35 @@ __device__ __forceinline__ double cvf_log_fast(double x, unsigned int tab_s)
     const int t = hi - (int)(CV_LOG_OFF >> 32);
     const double z = __hiloint2double(hi - (t & (int)0xfff00000), __double2loint(x));
     const double2 c = REP == 8 ? cvf_lds128(tab_s + ((t >> 6) & ((CV_LOG_N - 1) << 7)))
-                                : cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4)));
+                                : cvf_lds128(tab_s + ((t >> 9) & ((CV_LOG_N - 1) << 4))); /* (invc, logc) of interval (t >> 13) & 127 */
     const double r = cv_fma(z, c.x, -1.0);
     const double kd = (double)((t >> 20) - CV_PSCALE_EXP); /* log(x 2^-128) */
-    const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y);
     const double r2 = cv_mul(r, r);
     const double a = cv_fma(r, 1.0 / 3.0, -0.5);
-    const double b = cv_fma(r, 0x1.9999ap-3, -0.25);
-    const double c2 = cv_fma(r, 0x1.24925p-3, -0x1.55555p-3);
+    const double b = cv_fma(r, 0x1.9999ap-3 /* 1/5 */, -0.25);
+#if CVF_LOG_DEG == 5
+    const double hi_part = cv_fma(kd, 0x1.62e42fefa39efp-1, c.y);
+    const double p = cv_fma(r2, b, a);
+    return cv_fma(r2, p, cv_add(hi_part, r)); /* hi_part + r does not wait for the polynomial */
+#else
+    const double hi_part = cv_fma(kd, 0x1.62e42p-1, c.y); /* ln 2 to 20 bits: k * ln2_hi stays exact */
+    /* log1p(r) - r = r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7), in three short dependent
+     * steps (Estrin) instead of five */
+    const double c2 = cv_fma(r, 0x1.24925p-3 /* 1/7 */, -0x1.55555p-3 /* 1/6 */);
     const double r4 = cv_mul(r2, r2);
     const double ab = cv_fma(r2, b, a);
     const double p = cv_fma(r4, c2, ab);
-    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.fdf473de6af28p-22));
+    const double lo = cv_fma(r2, p, cv_mul(kd, 0x1.fdf473de6af28p-22)); /* ln 2 - 0x1.62e42p-1 */
     return cv_add(cv_add(hi_part, r), lo);
+#endif
+}
+
+template <int REP = 1>
+__device__ __forceinline__ double cvf_safe_log(double x, unsigned int tab_s)
+{
+    if ((unsigned int)(__double2hiint(x) - CVF_FAST_LO) >= CVF_FAST_SPAN)
+        return cvf_log_rare(x);
+    return cvf_log_fast<REP>(x, tab_s);
 }
 
 /* number of entries of the ascending a[0..n) that are < x (strict) resp. <= x */
@@ -1203,35 +1228,42 @@ __device__ __forceinline__ int cvf_count_below(const int *a, int n, int x, bool 
 /* MASS: the histogram has a tail (models.py:103-104): the mass sum_j p_j enters the result through
  * 1 - mass and is summed compensated (the reference uses fsum); without a tail it only has to
  * tell whether it is below 1 (models.py:104), a plain sum.
- * FULL: the slots are a multiple of CVF_PASS_SLOTS, no thread ever idles in a pass.
- * ONE: the bins with counts all lie in the first of a thread's CVF_SL slots (histograms whose
+ * FULL: the slots are a multiple of a pass (32 NW SL), no thread ever idles in a pass.
+ * ONE: the bins with counts all lie in the first of a thread's SL slots (histograms whose
  * counted bins are the first quarter of every pass): the code for the other slots' logarithms is
  * not even compiled in. */
-template <bool MASS, bool FULL, bool ONE>
-__global__ void __launch_bounds__(CVF_PT, 2)
+template <bool MASS, bool FULL, bool ONE, int NW, int SL>
+__global__ void __launch_bounds__(32 * NW, CVF_WARPS_SM / NW)
 cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__ CvLattice lat,
                   const double *__restrict__ params, int clip, CvfPlan pl, int first_tile, int n_tiles,
                   const double *__restrict__ W, long long w_base, const double2 *__restrict__ slot_mh,
-                  const double *__restrict__ log_tab, int nsteps, double *__restrict__ out_ll,
+                  const double *__restrict__ log_tab, int nsteps, int nslots, double *__restrict__ out_ll,
                   unsigned long long *counter, double *__restrict__ scratch)
 {
+    constexpr int PT_ = 32 * NW, PW_ = NW;          /* threads, warps */
+    constexpr int PASS_ = PT_ * SL;             /* slots per pass */
+    constexpr int RING_ = CVF_PD * SL * PT_ * 8; /* bytes */
+    constexpr int TBUF_ = PW_ * CVF_PE * CVF_PEW;   /* doubles per plane */
     extern __shared__ __align__(16) unsigned char cvf_smem_raw[];
     CvfPrefixSmem &S = *reinterpret_cast<CvfPrefixSmem *>(cvf_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *ring = reinterpret_cast<double *>(cvf_smem_raw + CVF_SMEM_HEAD) + tid;
-    double *tbuf = reinterpret_cast<double *>(cvf_smem_raw + CVF_SMEM_HEAD + CVF_RING_BYTES) +
-                   warp * (CVF_PE * CVF_PEW); /* plane stride CVF_TBUF_DOUBLES */
-    double *red_all = scratch + (size_t)blockIdx.x * (3 * CVF_PW * CVF_PB);
-    double *red = red_all + warp * CVF_PB; /* plane stride CVF_PW * CVF_PB */
+    double *tbuf = reinterpret_cast<double *>(cvf_smem_raw + CVF_SMEM_HEAD + RING_) +
+                   warp * (CVF_PE * CVF_PEW); /* plane stride TBUF_ */
+    /* by batch position: copies of the point; only while the schedule is built, in the place of the transpose buffers */
+    int *need_s = reinterpret_cast<int *>(cvf_smem_raw + CVF_SMEM_HEAD + RING_);
+    static_assert(2 * TBUF_ * 8 >= CVF_PB * 4, "the transpose buffers hold the cut-offs of a batch");
+    double *red_all = scratch + (size_t)blockIdx.x * (3 * PW_ * CVF_PB);
+    double *red = red_all + warp * CVF_PB; /* plane stride PW_ * CVF_PB */
     const unsigned int ring_s = cvf_pin((unsigned int)__cvta_generic_to_shared(ring));
     /* the lane's copy of the logarithm table */
     const unsigned int log_s = cvf_pin((unsigned int)__cvta_generic_to_shared(S.log_tab) + (unsigned int)((lane & (CVF_LOG_REP - 1)) * 16));
     const unsigned int ev_s = cvf_pin((unsigned int)__cvta_generic_to_shared(S.ev));
     const unsigned int tbuf_s = cvf_pin((unsigned int)__cvta_generic_to_shared(tbuf + lane)); /* the lane's column */
-    for (int i = tid; i < 2 * CV_LOG_N * CVF_LOG_REP; i += CVF_PT) /* entry e of copy c: doubles 2 (e REP + c) .. + 1 */
+    for (int i = tid; i < 2 * CV_LOG_N * CVF_LOG_REP; i += PT_) /* entry e of copy c: doubles 2 (e REP + c) .. + 1 */
         S.log_tab[i] = log_tab[2 * (i / (2 * CVF_LOG_REP)) + (i & 1)];
-    const int nslots = nsteps * CVF_NS;
-    const long long row_stride = (long long)nslots; /* doubles between the rows of consecutive copies */
+    /* nslots: the slots of a row that can be other than zero (a multiple of 32; the line of the sums ends after its first half) */
+    const long long row_stride = (long long)nsteps * CVF_NS; /* doubles between the rows of consecutive copies */
 
     for (;;) {
         __syncthreads();
@@ -1253,7 +1285,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
             if (tid <= CVF_NQ)
                 S.seg[tid] = nload;
             __syncthreads();
-            for (int t = tid; t < nload; t += CVF_PT) {
+            for (int t = tid; t < nload; t += PT_) {
                 const int rel = pl.rid[b0 + t] - rid0;
                 if (rel >= CVF_NQ)
                     atomicMin(&S.bend, t);
@@ -1262,28 +1294,14 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
             }
             __syncthreads();
             const int npts = S.bend;
-            /* per point: the weights (kept in registers until its place in the schedule is known) */
-            constexpr int PPT = CVF_PB / CVF_PT;
-            double pq1[PPT], ptwo[PPT], pmany[PPT];
-#pragma unroll
-            for (int j = 0; j < PPT; j++) {
-                const int t = tid + j * CVF_PT;
-                pq1[j] = ptwo[j] = pmany[j] = 0.0;
-                if (t < npts) {
-                    const unsigned int pi = pl.idx_sorted[b0 + t];
+            /* per point: its copies */
+            for (int t = tid; t < npts; t += PT_) {
+                const unsigned int pi = pl.idx_sorted[b0 + t];
+                need_s[t] = pl.othr[pi] - 1;
+                if (t == 0 || pl.head2[b0 + t]) {
                     double row[CV_MAX_PARAMS];
                     cvf_raw_row(m, lat, params, pi, row);
-                    const double q1 = cvf_clipped(m, row, clip, 2), q2 = cvf_clipped(m, row, clip, 3),
-                                 qq = cvf_clipped(m, row, clip, 4);
-                    const int need = pl.othr[pi] - 1;
-                    /* copies beyond the cut-off do not enter (models.py:235): exact zero weights (the
-                     * profiles are probabilities, finite) */
-                    pq1[j] = need >= 1 ? q1 : 0.0;
-                    ptwo[j] = need >= 2 ? cv_mul(cv_sub(1.0, q1), q2) : 0.0;
-                    pmany[j] = need >= 3 ? cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), qq) : 0.0;
-                    S.need[t] = need;
-                    if (t == 0 || pl.head2[b0 + t])
-                        S.base[pl.rid[b0 + t] - rid0] = cv_sub(1.0, qq);
+                    S.base[pl.rid[b0 + t] - rid0] = cv_sub(1.0, cvf_clipped(m, row, clip, 4));
                 }
             }
             __syncthreads();
@@ -1297,34 +1315,36 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                 if (seg_end[s] < seg0[s])
                     seg_end[s] = seg0[s];
                 base[s] = seg_end[s] > seg0[s] ? S.base[s] : 0.0;
-                last_need[s] = seg_end[s] > seg0[s] ? S.need[seg_end[s] - 1] : -1;
+                last_need[s] = seg_end[s] > seg0[s] ? need_s[seg_end[s] - 1] : -1;
                 omax_b = max(omax_b, last_need[s]);
             }
             /* the schedule: rank of a point = points before it by (copies, run, position) */
+            for (int t = tid; t < npts; t += PT_) {
+                const int need = need_s[t];
+                int rank = 0, mine = 0;
 #pragma unroll
-            for (int j = 0; j < PPT; j++) {
-                const int t = tid + j * CVF_PT;
-                if (t < npts) {
-                    const int need = S.need[t];
-                    int rank = 0, mine = 0;
+                for (int s = 0; s < CVF_NQ; s++)
+                    if (t >= seg0[s] && t < seg_end[s]) {
+                        mine = s;
+                        rank += t - seg0[s];
+                    }
 #pragma unroll
-                    for (int s = 0; s < CVF_NQ; s++)
-                        if (t >= seg0[s] && t < seg_end[s]) {
-                            mine = s;
-                            rank += t - seg0[s];
-                        }
-#pragma unroll
-                    for (int s = 0; s < CVF_NQ; s++)
-                        if (s != mine && seg_end[s] > seg0[s])
-                            rank += cvf_count_below(S.need + seg0[s], seg_end[s] - seg0[s], need, s < mine);
-                    CvfEvent e;
-                    e.q1 = pq1[j];
-                    e.two = ptwo[j];
-                    e.many = pmany[j];
-                    e.info = t | (mine << 16);
-                    e.need = need;
-                    S.ev[rank] = e;
-                }
+                for (int s = 0; s < CVF_NQ; s++)
+                    if (s != mine && seg_end[s] > seg0[s])
+                        rank += cvf_count_below(need_s + seg0[s], seg_end[s] - seg0[s], need, s < mine);
+                double row[CV_MAX_PARAMS];
+                cvf_raw_row(m, lat, params, pl.idx_sorted[b0 + t], row);
+                const double q1 = cvf_clipped(m, row, clip, 2), q2 = cvf_clipped(m, row, clip, 3),
+                             qq = cvf_clipped(m, row, clip, 4);
+                CvfEvent e;
+                /* copies beyond the cut-off do not enter (models.py:235): exact zero weights (the
+                 * profiles are probabilities, finite) */
+                e.q1 = need >= 1 ? q1 : 0.0;
+                e.two = need >= 2 ? cv_mul(cv_sub(1.0, q1), q2) : 0.0;
+                e.many = need >= 3 ? cv_mul(cv_mul(cv_sub(1.0, q1), cv_sub(1.0, q2)), qq) : 0.0;
+                e.info = t | (mine << 16);
+                e.need = need;
+                S.ev[rank] = e;
             }
             if (tid < 2) { /* read ahead by the loop below, never used */
                 CvfEvent e;
@@ -1335,17 +1355,17 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
             __syncthreads();
 
             /* ---- passes over the slots ---- */
-            for (int pass0 = 0; pass0 < nslots; pass0 += CVF_PASS_SLOTS) {
-                /* the thread's slots: double `lane` of the half-lines u = pass0 / 32 + i * CVF_PW + warp */
+            for (int pass0 = 0; pass0 < nslots; pass0 += PASS_) {
+                /* the thread's slots: double `lane` of the half-lines u = pass0 / 32 + i * PW_ + warp */
                 const int u0 = (pass0 >> 5) + warp;
                 const double *src0 = Wg + u0 * 32 + lane; /* row 0 (copy 1) */
-                constexpr long long SRC_STEP = (long long)CVF_PW * 32; /* doubles between i and i + 1 */
-                double hcnt[CVF_SL];
+                constexpr long long SRC_STEP = (long long)PW_ * 32; /* doubles between i and i + 1 */
+                double hcnt[SL];
                 int log_mask = 0;
-                bool live[CVF_SL];
+                bool live[SL];
 #pragma unroll
-                for (int i = 0; i < CVF_SL; i++) {
-                    const int u = u0 + i * CVF_PW;
+                for (int i = 0; i < SL; i++) {
+                    const int u = u0 + i * PW_;
                     live[i] = FULL || u * 32 < nslots;
                     const int e = (u & 1) * 32 + lane, L = e >> 1; /* pair L, member e & 1 of N-step u / 2 */
                     const int slot = (u >> 1) * CVF_NS + 16 * (L >> 3) + (L & 7) + 8 * (e & 1);
@@ -1364,14 +1384,14 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                 auto request = [&]() { /* one commit group per call, also when there is nothing left to load */
                     if (o_req <= omax_b) {
 #pragma unroll
-                        for (int i = 0; i < CVF_SL; i++)
+                        for (int i = 0; i < SL; i++)
                             if (live[i])
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst_req + i * CVF_PT * 8),
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst_req + i * PT_ * 8),
                                              "l"(src_req + i * SRC_STEP)
                                              : "memory");
                         if (o_req + CVF_PL2 <= omax_b && far_lane) {
 #pragma unroll
-                            for (int i = 0; i < CVF_SL; i++)
+                            for (int i = 0; i < SL; i++)
                                 if (live[i])
                                     asm volatile("prefetch.global.L2 [%0];" ::"l"(src_far + i * SRC_STEP));
                         }
@@ -1379,16 +1399,16 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     cvf_cp_commit();
                     src_req += row_stride;
                     src_far += row_stride;
-                    dst_req = (o_req % CVF_PD == 0) ? ring_s : dst_req + CVF_SL * CVF_PT * 8;
+                    dst_req = (o_req % CVF_PD == 0) ? ring_s : dst_req + SL * PT_ * 8;
                     o_req++;
                 };
                 int slot_take = 0;
                 auto take = [&](double *x) { /* the oldest copy in flight has landed */
                     asm volatile("cp.async.wait_group %0;\n" ::"n"(CVF_PD - 1) : "memory");
 #pragma unroll
-                    for (int i = 0; i < CVF_SL; i++) {
+                    for (int i = 0; i < SL; i++) {
                         double v;
-                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ring_s + (unsigned int)((slot_take * CVF_SL + i) * CVF_PT * 8)));
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ring_s + (unsigned int)((slot_take * SL + i) * PT_ * 8)));
                         x[i] = live[i] ? v : 0.0;
                     }
                     slot_take = slot_take == CVF_PD - 1 ? 0 : slot_take + 1;
@@ -1396,9 +1416,9 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
 #pragma unroll
                 for (int o = 1; o <= CVF_PD; o++)
                     request();
-                double P1[CVF_SL], P2[CVF_SL];
+                double P1[SL], P2[SL];
 #pragma unroll
-                for (int i = 0; i < CVF_SL; i++)
+                for (int i = 0; i < SL; i++)
                     P1[i] = P2[i] = 0.0;
                 if (omax_b >= 1) {
                     take(P1);
@@ -1408,11 +1428,11 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     take(P2);
                     request();
                 }
-                double R[CVF_NQ][CVF_SL], w[CVF_NQ];
+                double R[CVF_NQ][SL], w[CVF_NQ];
 #pragma unroll
                 for (int s = 0; s < CVF_NQ; s++) {
 #pragma unroll
-                    for (int i = 0; i < CVF_SL; i++)
+                    for (int i = 0; i < SL; i++)
                         R[s][i] = 0.0;
                     w[s] = 1.0;
                 }
@@ -1426,17 +1446,17 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     /* lane group g = lane / CVF_PE takes the columns g * CVF_PE .. + CVF_PE - 1 of row e */
                     const int e = lane & (CVF_PE - 1), c0 = (lane / CVF_PE) * CVF_PE;
                     const double *rowp = tbuf + e * CVF_PEW + c0;
-                    double acc0 = rowp[0], acc1 = rowp[CVF_TBUF_DOUBLES], acc2 = 0.0;
+                    double acc0 = rowp[0], acc1 = rowp[TBUF_], acc2 = 0.0;
                     if (MASS)
-                        acc2 = rowp[2 * CVF_TBUF_DOUBLES];
+                        acc2 = rowp[2 * TBUF_];
 #pragma unroll
                     for (int c = 1; c < CVF_PE; c++) {
                         acc0 = cv_add(acc0, rowp[c]);
                         if (MASS) { /* high parts exactly (two-sum), low parts plainly */
-                            cvf_two_sum_acc(acc1, acc2, rowp[CVF_TBUF_DOUBLES + c]);
-                            acc2 = cv_add(acc2, rowp[2 * CVF_TBUF_DOUBLES + c]);
+                            cvf_two_sum_acc(acc1, acc2, rowp[TBUF_ + c]);
+                            acc2 = cv_add(acc2, rowp[2 * TBUF_ + c]);
                         } else {
-                            acc1 = cv_add(acc1, rowp[CVF_TBUF_DOUBLES + c]);
+                            acc1 = cv_add(acc1, rowp[TBUF_ + c]);
                         }
                     }
 #pragma unroll
@@ -1453,7 +1473,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     }
                     const int pt = __shfl_sync(CV_FULL_MASK, mypt, e);
                     if (lane < pending) {
-                        double *r0 = red + pt, *r1 = r0 + CVF_PW * CVF_PB, *r2 = r1 + CVF_PW * CVF_PB;
+                        double *r0 = red + pt, *r1 = r0 + PW_ * CVF_PB, *r2 = r1 + PW_ * CVF_PB;
                         if (first_pass) {
                             *r0 = acc0;
                             *r1 = acc1;
@@ -1487,14 +1507,14 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                 unsigned int tb_a = tbuf_s; /* row `pending` of the transpose buffer */
                 auto step = [&]() { /* one more copy into the running sums (o_done >= 3 afterwards) */
                     o_done++;
-                    double x[CVF_SL];
+                    double x[SL];
                     take(x);
                     request();
 #pragma unroll
                     for (int s = 0; s < CVF_NQ; s++)
                         if (o_done <= last_need[s]) { /* runs whose points are all out need no more copies */
 #pragma unroll
-                            for (int i = 0; i < CVF_SL; i++)
+                            for (int i = 0; i < SL; i++)
                                 R[s][i] = cv_fma(w[s], x[i], R[s][i]);
                             w[s] = cv_mul(w[s], base[s]);
                         }
@@ -1512,14 +1532,14 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         /* two points at once: this one is combined now, the next one after the copies
                          * it still needs; then their logarithms run side by side (two dependent
                          * chains instead of one) and the bookkeeping is shared */
-                        double pa[CVF_SL], pb[CVF_SL];
+                        double pa[SL], pb[SL];
 #pragma unroll
-                        for (int i = 0; i < CVF_SL; i++)
+                        for (int i = 0; i < SL; i++)
                             pa[i] = cv_fma(two, P2[i], cv_mul(q1, P1[i]));
                         switch ((info >> 16) & 3) {
 #define CVF_CASE(s_)                                                                                   \
     case s_:                                                                                           \
-        _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) pa[i] = cv_fma(many, R[s_][i], pa[i]);      \
+        _Pragma("unroll") for (int i = 0; i < SL; i++) pa[i] = cv_fma(many, R[s_][i], pa[i]);      \
         break;
                             CVF_CASE(0)
                             CVF_CASE(1)
@@ -1534,12 +1554,12 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         while (o_done < need_next)
                             step();
 #pragma unroll
-                        for (int i = 0; i < CVF_SL; i++)
+                        for (int i = 0; i < SL; i++)
                             pb[i] = cv_fma(qt_next.y, P2[i], cv_mul(qt_next.x, P1[i]));
                         switch ((info_next >> 16) & 3) {
 #define CVF_CASE(s_)                                                                                   \
     case s_:                                                                                           \
-        _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) pb[i] = cv_fma(many_next, R[s_][i], pb[i]); \
+        _Pragma("unroll") for (int i = 0; i < SL; i++) pb[i] = cv_fma(many_next, R[s_][i], pb[i]); \
         break;
                             CVF_CASE(0)
                             CVF_CASE(1)
@@ -1563,7 +1583,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         k++;
                         double ma = 0.0, mb = 0.0, mla = 0.0, mlb = 0.0; /* models.py:103: the mass */
 #pragma unroll
-                        for (int i = 0; i < CVF_SL; i++) {
+                        for (int i = 0; i < SL; i++) {
                             if (MASS) {
                                 cvf_two_sum_acc(ma, mla, pa[i]);
                                 cvf_two_sum_acc(mb, mlb, pb[i]);
@@ -1590,7 +1610,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                                 sa = sb = 0.0;
                         } else if (!ONE && log_mask) {
 #pragma unroll
-                            for (int i = 0; i < CVF_SL; i++)
+                            for (int i = 0; i < SL; i++)
                                 if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
                                     const unsigned int ca = (unsigned int)(__double2hiint(pa[i]) - CVF_FAST_LO),
                                                        cb = (unsigned int)(__double2hiint(pb[i]) - CVF_FAST_LO);
@@ -1614,12 +1634,12 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             tb_a = tbuf_s;
                         }
                         cvf_sts64(tb_a, sa);
-                        cvf_sts64(tb_a + CVF_TBUF_DOUBLES * 8, ma);
+                        cvf_sts64(tb_a + TBUF_ * 8, ma);
                         cvf_sts64(tb_a + CVF_PEW * 8, sb);
-                        cvf_sts64(tb_a + CVF_PEW * 8 + CVF_TBUF_DOUBLES * 8, mb);
+                        cvf_sts64(tb_a + CVF_PEW * 8 + TBUF_ * 8, mb);
                         if (MASS) {
-                            cvf_sts64(tb_a + 2 * CVF_TBUF_DOUBLES * 8, mla);
-                            cvf_sts64(tb_a + CVF_PEW * 8 + 2 * CVF_TBUF_DOUBLES * 8, mlb);
+                            cvf_sts64(tb_a + 2 * TBUF_ * 8, mla);
+                            cvf_sts64(tb_a + CVF_PEW * 8 + 2 * TBUF_ * 8, mlb);
                         }
                         tb_a += 2 * CVF_PEW * 8;
                         if (lane == pending)
@@ -1635,14 +1655,14 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     }
                     /* the three-term combination for the thread's slots, models.py:235-241 */
                     const int pt = info & 0xffff;
-                    double p[CVF_SL];
+                    double p[SL];
 #pragma unroll
-                    for (int i = 0; i < CVF_SL; i++)
+                    for (int i = 0; i < SL; i++)
                         p[i] = cv_fma(two, P2[i], cv_mul(q1, P1[i]));
                     switch ((info >> 16) & 3) {
 #define CVF_CASE(s_)                                                                                   \
     case s_:                                                                                           \
-        _Pragma("unroll") for (int i = 0; i < CVF_SL; i++) p[i] = cv_fma(many, R[s_][i], p[i]);        \
+        _Pragma("unroll") for (int i = 0; i < SL; i++) p[i] = cv_fma(many, R[s_][i], p[i]);        \
         break;
                         CVF_CASE(0)
                         CVF_CASE(1)
@@ -1660,7 +1680,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                     /* models.py:100-107 for the thread's slots */
                     double sum = 0.0, mh = 0.0, ml = 0.0;
 #pragma unroll
-                    for (int i = 0; i < CVF_SL; i++) {
+                    for (int i = 0; i < SL; i++) {
                         if (MASS)
                             cvf_two_sum_acc(mh, ml, p[i]);
                         else
@@ -1673,7 +1693,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                         sum = term;
                     } else if (!ONE && log_mask) {
 #pragma unroll
-                        for (int i = 0; i < CVF_SL; i++)
+                        for (int i = 0; i < SL; i++)
                             if ((log_mask >> i) & 1) { /* some lane of the warp has a count in its slot i */
                                 double term = cv_mul(hcnt[i], cvf_safe_log<CVF_LOG_REP>(p[i], log_s));
                                 if (hcnt[i] == 0.0)
@@ -1682,9 +1702,9 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             }
                     }
                     cvf_sts64(tb_a, sum);
-                    cvf_sts64(tb_a + CVF_TBUF_DOUBLES * 8, mh);
+                    cvf_sts64(tb_a + TBUF_ * 8, mh);
                     if (MASS)
-                        cvf_sts64(tb_a + 2 * CVF_TBUF_DOUBLES * 8, ml);
+                        cvf_sts64(tb_a + 2 * TBUF_ * 8, ml);
                     tb_a += CVF_PEW * 8;
                     if (lane == pending)
                         mypt = pt;
@@ -1698,18 +1718,18 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                 cvf_cp_wait0();
             }
             __syncthreads();
-            for (int t = tid; t < npts; t += CVF_PT) {
+            for (int t = tid; t < npts; t += PT_) {
                 CvPartial part;
                 part.sum = red_all[t];
-                part.mass_h = red_all[CVF_PW * CVF_PB + t];
-                part.mass_l = MASS ? red_all[2 * CVF_PW * CVF_PB + t] : 0.0;
-                for (int wv = 1; wv < CVF_PW; wv++) {
+                part.mass_h = red_all[PW_ * CVF_PB + t];
+                part.mass_l = MASS ? red_all[2 * PW_ * CVF_PB + t] : 0.0;
+                for (int wv = 1; wv < PW_; wv++) {
                     part.sum = cv_add(part.sum, red_all[wv * CVF_PB + t]);
                     if (MASS) {
-                        cvf_two_sum_acc(part.mass_h, part.mass_l, red_all[(CVF_PW + wv) * CVF_PB + t]);
-                        part.mass_l = cv_add(part.mass_l, red_all[(2 * CVF_PW + wv) * CVF_PB + t]);
+                        cvf_two_sum_acc(part.mass_h, part.mass_l, red_all[(PW_ + wv) * CVF_PB + t]);
+                        part.mass_l = cv_add(part.mass_l, red_all[(2 * PW_ + wv) * CVF_PB + t]);
                     } else {
-                        part.mass_h = cv_add(part.mass_h, red_all[(CVF_PW + wv) * CVF_PB + t]);
+                        part.mass_h = cv_add(part.mass_h, red_all[(PW_ + wv) * CVF_PB + t]);
                     }
                 }
                 out_ll[pl.idx_sorted[b0 + t]] = cv_point_finish(m, part);
@@ -2347,17 +2367,20 @@ static bool cvf_lattice_aligned(const CvModelDesc &m, const CvLattice &lat, long
 
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *const *lat_axes_host,
                      const double *params, long long n,
-                     int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
+                     int clip, double *out_ll, const CvfSlots &sl,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
-                     double min_group, double min_run, int kernel_mode, bool counts_first, cudaStream_t stream,
+                     double min_group, double min_run, int kernel_mode, cudaStream_t stream,
                      int *used)
 {
     *used = 0;
     wk.launches = 0;
     if (n <= 0 || n > 0x7fffffffLL || !cvf_supported(m))
         return cudaSuccess;
-    const int slots_padded = m.n_blocks * CV_GB * m.na * CV_W;
-    const int nsteps = slots_padded / CVF_NS;
+    /* the slots of a profile row as the batch kernels see them (cvf_build_slots) */
+    const int nsteps = sl.nsteps;
+    const int slots_padded = nsteps * CVF_NS;
+    const double2 *slot_mh = sl.slot_mh;
+    const int *step_mask = sl.step_mask;
 
     /* ---- carve the plan ---- */
     size_t sort_tmp = 0, sort_tmp_t = 0, scan_tmp_i = 0, scan_tmp_l = 0;
@@ -2400,9 +2423,9 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
         CVF_CK(cudaMallocHost((void **)&wk.h_header, 64));
     if (!wk.d_counters)
         CVF_CK(cudaMalloc((void **)&wk.d_counters, 2 * sizeof(unsigned long long)));
-    const int kp_grid_max = 4 * n_sm; /* CTAs of the prefix kernel at most; each owns a scratch of partials */
+    /* the CTAs of the prefix kernel own a scratch of partials each: at most 32 warps per SM */
     if (!wk.d_scratch)
-        CVF_CK(cudaMalloc((void **)&wk.d_scratch, (size_t)kp_grid_max * 3 * CVF_PW * CVF_PB * sizeof(double)));
+        CVF_CK(cudaMalloc((void **)&wk.d_scratch, (size_t)n_sm * 32 * 3 * CVF_PB * sizeof(double)));
     if (wk.timed && !wk.ev[0])
         for (cudaEvent_t &e : wk.ev)
             CVF_CK(cudaEventCreate(&e));
@@ -2660,15 +2683,56 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
         return cudaErrorInvalidConfiguration;
     const size_t k1_smem = tab + (size_t)k1_warps * wb1;
     const bool want_mass = m.tail != 0.0;
-    const size_t kp_smem = cvf_prefix_smem_bytes(want_mass);
-    const bool full_passes = (nsteps * CVF_NS) % CVF_PASS_SLOTS == 0;
+    /* warps of the prefix kernel's CTAs: one pass over the row when 768 slots or fewer do it */
+    const int kp_slots = slots_padded - (sl.sum_line >= 0 ? 32 : 0); /* the line of the sums is half a line */
+    /* Geometry of the prefix kernel: warps per CTA and slots per thread so that one pass covers the
+     * row when 32 half-lines or fewer do it -- the fewest warps, then the fewest slots (measured on
+     * the 9 half-lines of cfg3: 3 warps x 3 slots 0.82 ms, 3 x 4 0.91 ms) */
+    const int kp_half = kp_slots / 32;
+    int kp_nw = 8, kp_sl = 4;
+    if (kp_half <= 24) {
+        static const int nws[] = {1, 2, 3, 4, 6, 8};
+        int n3 = 8, n4 = 8;
+        for (int i = 5; i >= 0; i--) {
+            if (nws[i] * 3 >= kp_half && nws[i] != 4 && nws[i] != 8)
+                n3 = nws[i];
+            if (nws[i] * 4 >= kp_half)
+                n4 = nws[i];
+        }
+        if (n3 <= n4) {
+            kp_nw = n3;
+            kp_sl = 3;
+        } else {
+            kp_nw = n4;
+        }
+    }
+    const size_t kp_smem = cvf_prefix_smem_bytes(want_mass, kp_nw, kp_sl);
+    const bool full_passes = kp_slots % (8 * 32 * 4) == 0;
+    const bool counts_first = sl.counts_first;
+    typedef decltype(&cvf_prefix_kernel<true, true, true, 8, 4>) CvfPrefixFn;
+    CvfPrefixFn kp = nullptr;
+#define CVF_PICK(nw_, sl_) \
+    (want_mass ? cvf_prefix_kernel<true, false, false, nw_, sl_> : cvf_prefix_kernel<false, false, false, nw_, sl_>)
+    switch (kp_nw * 10 + kp_sl) {
+    case 13: kp = CVF_PICK(1, 3); break;
+    case 14: kp = CVF_PICK(1, 4); break;
+    case 23: kp = CVF_PICK(2, 3); break;
+    case 24: kp = CVF_PICK(2, 4); break;
+    case 33: kp = CVF_PICK(3, 3); break;
+    case 34: kp = CVF_PICK(3, 4); break;
+    case 44: kp = CVF_PICK(4, 4); break;
+    case 63: kp = CVF_PICK(6, 3); break;
+    case 64: kp = CVF_PICK(6, 4); break;
+    default:
+        kp = want_mass ? (full_passes ? (counts_first ? cvf_prefix_kernel<true, true, true, 8, 4> : cvf_prefix_kernel<true, true, false, 8, 4>)
+                                      : (counts_first ? cvf_prefix_kernel<true, false, true, 8, 4> : cvf_prefix_kernel<true, false, false, 8, 4>))
+                       : (full_passes ? (counts_first ? cvf_prefix_kernel<false, true, true, 8, 4> : cvf_prefix_kernel<false, true, false, 8, 4>)
+                                      : (counts_first ? cvf_prefix_kernel<false, false, true, 8, 4> : cvf_prefix_kernel<false, false, false, 8, 4>));
+    }
+#undef CVF_PICK
     CVF_CK(cudaFuncSetAttribute(cvf_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
     CVF_CK(cudaFuncSetAttribute(cvf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(CvfSmem)));
-    auto kp = want_mass ? (full_passes ? (counts_first ? cvf_prefix_kernel<true, true, true> : cvf_prefix_kernel<true, true, false>)
-                                       : (counts_first ? cvf_prefix_kernel<true, false, true> : cvf_prefix_kernel<true, false, false>))
-                        : (full_passes ? (counts_first ? cvf_prefix_kernel<false, true, true> : cvf_prefix_kernel<false, true, false>)
-                                       : (counts_first ? cvf_prefix_kernel<false, false, true> : cvf_prefix_kernel<false, false, false>));
     CVF_CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kp_smem));
     const size_t kp2_smem = cvf_prefix2_smem_bytes(want_mass);
     const bool full2 = (nsteps * CVF_NS) % V2_PASS == 0;
@@ -2690,8 +2754,8 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
             if (grid > n_sm)
                 grid = n_sm;
             cvf_profile_kernel<<<grid, 32 * k1_warps, k1_smem, stream>>>(
-                m, lat, params, clip, pl, (int)n_groups, item0, items, wk.W, w0, nsteps, wk.d_counters,
-                groups_staged);
+                m, lat, params, clip, pl, (int)n_groups, item0, items, wk.W, w0, nsteps, sl.line_map, sl.sum_line,
+                wk.d_counters, groups_staged);
             CVF_CK(cudaGetLastError());
             wk.launches++;
         }
@@ -2719,7 +2783,7 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
                 CVF_CK(cudaEventRecord(wk.ev[2], stream));
             int grid = tiles < 2 * n_sm ? tiles : 2 * n_sm;
             if (prefix) {
-                int per_sm = std::max(1, std::min(4, (int)((size_t)smem_max / (kp_smem + 1024))));
+                int per_sm = std::max(1, std::min(CVF_WARPS_SM / kp_nw, (int)((size_t)smem_max / (kp_smem + 1024))));
                 if (const char *lim = getenv("COVEST_B200_PREFIX_CTAS")) /* development: CTAs per SM */
                     per_sm = std::max(1, std::min(per_sm, atoi(lim)));
                 if (pver == 2) {
@@ -2729,8 +2793,9 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
                                                             log_tab, nsteps, out_ll, wk.d_counters + 1, wk.d_scratch);
                 } else {
                     grid = tiles < per_sm * n_sm ? tiles : per_sm * n_sm;
-                    kp<<<grid, CVF_PT, kp_smem, stream>>>(m, lat, params, clip, pl, tile0, tiles, wk.W, w0, slot_mh,
-                                                           log_tab, nsteps, out_ll, wk.d_counters + 1, wk.d_scratch);
+                    kp<<<grid, 32 * kp_nw, kp_smem, stream>>>(m, lat, params, clip, pl, tile0, tiles, wk.W, w0, slot_mh,
+                                                               log_tab, nsteps, kp_slots, out_ll, wk.d_counters + 1,
+                                                               wk.d_scratch);
                 }
             } else {
                 cvf_gemm_kernel<<<grid, CVF_THREADS, sizeof(CvfSmem), stream>>>(

@@ -63,22 +63,80 @@ struct CvFactorWork {
     double gemm_fma = 0.0; /* FMAs the tiles of K2 issue (128 rows x padded copies x padded slots) */
 };
 
+/* The slots of a profile row as the batch kernels (K1's stores, K2, K2p) see them.
+ *
+ * The histogram tables (cvtables.h) lay the bins out in lines of 64 slots.  A bin without a count
+ * enters the log-likelihood only through the mass sum_j p_j (models.py:103-107), and p_j is linear
+ * in the profiles: sum over such bins of p_j = sum_o b(o) * (sum over such bins of P_o[j]).  So a
+ * profile row keeps the lines that hold at least one bin with a count as they are, and ONE more line
+ * whose first half holds the sums of all other lines (32 partial sums per copy, one per lane of the
+ * warp that stores the row; its second half is zero; every profile value is still evaluated by K1
+ * and still part of the mass).  Histograms simulated or counted to a fixed max_hist
+ * are mostly zero beyond a few multiples of the coverage: cfg3 keeps 4 + 1 of its 16 lines. */
+struct CvfSlots {
+    int nsteps = 0;                /* lines of a row */
+    int sum_line = -1;             /* the line of the sums, -1: every line has counts */
+    const int *line_map = nullptr; /* device: line of the histogram tables -> line of the row, -1: summed */
+    const double2 *slot_mh = nullptr; /* device: (slot_mult or 1 on the sum line, count) per slot of the row */
+    const int *step_mask = nullptr;   /* device: cvf_step_masks of those counts */
+    bool counts_first = false;        /* cvf_counts_first of those counts */
+};
+
+/* host: the row layout for the tables (slot_mult, slot_h), both of the same length, a multiple of
+ * 64.  compact = false keeps every line (the layout before this existed; COVEST_B200_ROWS=full). */
+static inline void cvf_build_slots(const std::vector<double> &slot_mult, const std::vector<double> &slot_h,
+                                   bool compact, std::vector<int> &line_map, std::vector<double2> &mh,
+                                   std::vector<double> &row_h, int *sum_line)
+{
+    const size_t lines = slot_h.size() / 64;
+    line_map.assign(lines, -1);
+    mh.clear();
+    row_h.clear();
+    int kept = 0;
+    for (size_t l = 0; l < lines; l++) {
+        bool counts = !compact;
+        for (int i = 0; i < 64 && !counts; i++)
+            counts = slot_h[l * 64 + i] != 0.0;
+        if (!counts)
+            continue;
+        line_map[l] = kept++;
+        for (int i = 0; i < 64; i++) {
+            double2 v;
+            v.x = slot_mult[l * 64 + i];
+            v.y = slot_h[l * 64 + i];
+            mh.push_back(v);
+            row_h.push_back(v.y);
+        }
+    }
+    *sum_line = -1;
+    if ((size_t)kept < lines) {
+        *sum_line = kept;
+        for (int i = 0; i < 64; i++) {
+            double2 v;
+            v.x = 1.0; /* a slot of the histogram as far as K2 is concerned */
+            v.y = 0.0;
+            mh.push_back(v);
+            row_h.push_back(0.0);
+        }
+    }
+}
+
 /* Can this context use the factored path at all (repeats model, few enough error classes)? */
 bool cvf_supported(const CvModelDesc &m);
 
 /* Evaluates n points.  *used = 0 when the batch does not group well enough (nothing written to
  * out_ll; the caller runs the per-point kernel), 1 when K2 (the GEMM) ran, 2 when the prefix kernel
- * ran.  counts_first: cvf_counts_first(slot_h).  kernel_mode: 0 = prefix kernel when the batch has at least min_run points per q-run (points
- * of a group that also share q), else the GEMM; 1 = GEMM; 2 = prefix kernel.  Device tables: `slot_mh` = (slot_mult, slot_h)
- * pairs; `step_mask` = per 32 slots, bit 2 nt + c set when one of the slots 8 nt + 2 q + c, q < 4,
- * has a count (cvf_step_masks); `log_tab` = cv_log_table.  w_limit = largest profile workspace in
+ * ran.  sl: the row layout (CvfSlots).  kernel_mode: 0 = prefix kernel when the batch has at least min_run points per q-run (points
+ * of a group that also share q), else the GEMM; 1 = GEMM; 2 = prefix kernel.  `step_mask` of the row layout = per 32 slots,
+ * bit 2 nt + c set when one of the slots 8 nt + 2 q + c, q < 4, has a count (cvf_step_masks);
+ * `log_tab` = cv_log_table.  w_limit = largest profile workspace in
  * doubles; larger batches run in several group ranges. */
 /* lat_axes_host: the lattice axes in host memory (n_param pointers) when lat.enabled, else NULL */
 cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *const *lat_axes_host,
                      const double *params, long long n,
-                     int clip, double *out_ll, const double2 *slot_mh, const int *step_mask,
+                     int clip, double *out_ll, const CvfSlots &sl,
                      const double *log_tab, CvFactorWork &wk, int n_sm, int smem_max, size_t w_limit,
-                     double min_group, double min_run, int kernel_mode, bool counts_first, cudaStream_t stream,
+                     double min_group, double min_run, int kernel_mode, cudaStream_t stream,
                      int *used);
 
 /* host: the step masks of a slot_h table (length a multiple of 32) */
