@@ -527,6 +527,9 @@ def run_b200(args, rank, world, local_rank):
         work, n_bins = rec['work'], rec['n_bins']
         factored = info['path'] == 'factored'
         if factored:
+            # the kernels after K1 carry the slots of a profile row, not every bin (csrc/factored.h, CvfSlots)
+            work = workload.lattice_flop(rec['model'], rec['axes'], rec['count'] // rec['block'], n_bins,
+                                         rec['counted_bins'], row_bins=info['row_slots'])
             dom_ms = float(np.mean([p['gemm_ms'] for p in rec['phases']]))
             dominant = info['kernel']
             flop_launch = work['prefix_flop'] if dominant == 'cvf_prefix_kernel' else work['gemm_flop']
@@ -562,7 +565,7 @@ def run_b200(args, rank, world, local_rank):
                    'plan_ms': float(np.mean([p['plan_ms'] for p in rec['phases']])),
                    'profile_ms': float(np.mean([p['profile_ms'] for p in rec['phases']])),
                    'kernel_ms': dom_ms, 'evaluation_ms': km, 'profile_flop': work['profile_flop'],
-                   'kernel_flop': flop_launch, 'counted_bins': rec['counted_bins'],
+                   'kernel_flop': flop_launch, 'counted_bins': rec['counted_bins'], 'row_slots': info['row_slots'],
                    'mean_copies_per_point': work['mean_copies'],
                    'evaluation_tflops': (work['profile_flop'] + flop_launch) / (km * 1e-3) / 1e12}
                   if factored else {'path': info['path'], 'evaluation_ms': km,
@@ -618,6 +621,30 @@ def run_b200(args, rank, world, local_rank):
                                 'note': 'cvb_probs_batch, device buffers (includes zero-filling the output); compute-bound: '
                                         'the per-point kernel forms every term, the 8 B per point x bin are written once'}
         del out_p, rnd, rnd_ll
+        if world == 1 and main['phases'][-1].get('row_slots', 0) < 64 * ((main['n_bins'] + 63) // 64):
+            # the same step with every bin carried through K2p (COVEST_B200_ROWS=full, read when a context
+            # is created): what the row layout of csrc/factored.h is worth on this histogram
+            os.environ['COVEST_B200_ROWS'] = 'full'
+            try:
+                full = RepeatsModel(main['cfg']['k'], main['cfg']['r'], main['hist'], 0, max_error=8)
+                fctx = full.device_context
+            finally:
+                del os.environ['COVEST_B200_ROWS']
+            f_ll = torch.empty(main['count'], dtype=torch.float64, device=dev)
+            f_rows = torch.empty((K_BEST, 6), dtype=torch.float64, device=dev)
+
+            def step_full():
+                fctx.lattice_eval(main['axes'], count=main['count'], block=main['block'], k_best=K_BEST,
+                                  out_ll=f_ll, out_rows=f_rows, stream=stream)
+                return f_rows
+            f_ms, _ = timed_device(step_full, max(3, args.steps // 2), 2)
+            f_steps = max(3, args.steps // 2)
+            extra['full_rows'] = {'value': main['count'] * main['n_bins'] * f_steps / (f_ms * 1e-3), 'unit': UNIT,
+                                  'ms_per_step': f_ms / f_steps, 'row_slots': fctx.last_path_info()['row_slots'],
+                                  'note': 'COVEST_B200_ROWS=full: every line of the histogram in the profile rows, '
+                                          'bins without counts carried one by one instead of as 32 sums'}
+            full.close()
+            del f_ll, f_rows
 
     cfg5 = None
     if (world == 8 or args.cfg5) and args.workload == 'cfg3' and not args.points and not args.no_cfg5:

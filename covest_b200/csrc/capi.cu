@@ -843,7 +843,7 @@ extern "C" int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out)
     }
     if (ctx->last_path >= 2) {
         v[10] = (double)ctx->fw.analytic;
-        v[11] = (double)ctx->slots.nsteps;
+        v[11] = (double)(ctx->slots.nsteps * 64 - (ctx->slots.sum_line >= 0 ? 32 : 0));
         const CvFactorWork &w = ctx->fw;
         v[1] = (double)w.n_groups;
         v[2] = (double)w.n_tiles;

@@ -267,7 +267,7 @@ class LikelihoodContext:
                            4: 'cv_faithful_kernel'}.get(int(v[0]), 'none'),
                 'groups': int(v[1]), 'tiles': int(v[2]), 'items': int(v[3]), 'profile_doubles': int(v[4]),
                 'plan_ms': v[5], 'profile_ms': v[6], 'gemm_ms': v[7], 'q_runs': int(v[8]),
-                'refined_points': int(v[9]), 'analytic_plan': bool(v[10]), 'row_lines': int(v[11])}
+                'refined_points': int(v[9]), 'analytic_plan': bool(v[10]), 'row_slots': int(v[11])}
 
     @property
     def sm_count(self):

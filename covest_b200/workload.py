@@ -116,7 +116,7 @@ def _clip(model, pts):
 # 64 flop per bin for the epilogue (a log, the count-weighted sum, the mass).
 FLOP_PER_TERM_BIN = 2.0
 FLOP_PER_BIN = 64.0
-PREFIX_FLOP_PER_BIN = 6.0  # q1*P1 (1) + two*P2 (2) + many*R (2) + the add into the mass (1)
+PREFIX_FLOP_PER_BIN = 6.0  # per slot of a profile row: q1*P1 (1) + two*P2 (2) + many*R (2) + the add into the mass (1)
 
 
 def algorithmic_flop(n_bins, terms):
@@ -124,8 +124,9 @@ def algorithmic_flop(n_bins, terms):
     return float(np.sum(n_bins * (FLOP_PER_TERM_BIN * terms + FLOP_PER_BIN)))
 
 
-def factored_flop(model, points, n_bins, counted_bins):
-    """FP64 work of the factored path on a batch:
+def factored_flop(model, points, n_bins, counted_bins, row_bins=None):
+    """FP64 work of the factored path on a batch (row_bins: the slots of a
+    profile row the kernels after K1 carry, cvb_last_path_info's row_slots; default every bin):
       profile_flop  one FMA per (error class, copy number, bin) for every copy number up to the
                     largest cut-off of each distinct (coverage, error_rate)
       gemm_flop     one FMA per (copy number below the point's cut-off, bin) for every point, plus
@@ -138,8 +139,9 @@ def factored_flop(model, points, n_bins, counted_bins):
     _, inverse = np.unique(keys, return_inverse=True)
     gmax = np.zeros(inverse.max() + 1)
     np.maximum.at(gmax, inverse, copies)
+    rb = n_bins if row_bins is None else row_bins
     profile = FLOP_PER_TERM_BIN * model.max_error * n_bins * float(gmax.sum())
-    gemm = float(np.sum(FLOP_PER_TERM_BIN * n_bins * copies + FLOP_PER_BIN * counted_bins))
+    gemm = float(np.sum(FLOP_PER_TERM_BIN * rb * copies + FLOP_PER_BIN * counted_bins))
     # prefix kernel: per (point, bin) the three-term combination (a multiply and two FMAs) and the
     # add into the mass; per (point, bin with a count) the same 64 flop as above; per (q-run, copy
     # number beyond 2 up to the run's largest cut-off, bin) one FMA into the running sum
@@ -147,8 +149,8 @@ def factored_flop(model, points, n_bins, counted_bins):
     _, rinv = np.unique(rkeys, return_inverse=True)
     rmax = np.zeros(rinv.max() + 1)
     np.maximum.at(rmax, rinv, copies)
-    prefix = float(len(pts)) * (PREFIX_FLOP_PER_BIN * n_bins + FLOP_PER_BIN * counted_bins) + \
-        FLOP_PER_TERM_BIN * n_bins * float(np.maximum(rmax - 2, 0).sum())
+    prefix = float(len(pts)) * (PREFIX_FLOP_PER_BIN * rb + FLOP_PER_BIN * counted_bins) + \
+        FLOP_PER_TERM_BIN * rb * float(np.maximum(rmax - 2, 0).sum())
     return {'profile_flop': profile, 'gemm_flop': gemm, 'prefix_flop': prefix, 'groups': int(len(gmax)),
             'q_runs': int(len(rmax)), 'mean_copies': float(copies.mean())}
 
@@ -162,10 +164,11 @@ def lattice_term_stats(model, axes):
     return float(t.sum()) * reps, float(t.mean())
 
 
-def lattice_flop(model, axes, n_groups, n_bins, counted_bins):
+def lattice_flop(model, axes, n_groups, n_bins, counted_bins, row_bins=None):
     """factored_flop of `n_groups` whole (coverage, error_rate) groups of the lattice of `axes`
     without materialising the points: cut-offs and q-runs depend on the (q1, q2, q) axes only, every
     group holds the same combinations."""
+    rb = n_bins if row_bins is None else row_bins
     q_pts = lattice_points([np.array([1.0]), np.array([0.1])] + [np.asarray(a, dtype=np.float64) for a in axes[2:]])
     q_pts = _clip(model, q_pts)
     copies = np.maximum(copy_cutoff(q_pts, max(model.hist), model.threshold) - 1, 0).astype(np.float64)
@@ -174,9 +177,9 @@ def lattice_flop(model, axes, n_groups, n_bins, counted_bins):
     np.maximum.at(rmax, rinv, copies)
     m = len(q_pts)
     profile = FLOP_PER_TERM_BIN * model.max_error * n_bins * float(copies.max()) * n_groups
-    gemm = float(np.sum(FLOP_PER_TERM_BIN * n_bins * copies + FLOP_PER_BIN * counted_bins)) * n_groups
-    prefix = n_groups * (m * (PREFIX_FLOP_PER_BIN * n_bins + FLOP_PER_BIN * counted_bins) +
-                         FLOP_PER_TERM_BIN * n_bins * float(np.maximum(rmax - 2, 0).sum()))
+    gemm = float(np.sum(FLOP_PER_TERM_BIN * rb * copies + FLOP_PER_BIN * counted_bins)) * n_groups
+    prefix = n_groups * (m * (PREFIX_FLOP_PER_BIN * rb + FLOP_PER_BIN * counted_bins) +
+                         FLOP_PER_TERM_BIN * rb * float(np.maximum(rmax - 2, 0).sum()))
     return {'profile_flop': profile, 'gemm_flop': gemm, 'prefix_flop': float(prefix), 'groups': int(n_groups),
             'q_runs': int(n_groups * len(rmax)), 'mean_copies': float(copies.mean()),
             'mean_terms': float(model.max_error * copies.mean()), 'sum_terms_per_group': float(model.max_error * copies.sum())}

@@ -158,8 +158,9 @@ CVB_API int cvb_set_path(cvb_ctx *ctx, int mode);
  * out[9] = points of the call that were re-evaluated term by term because a bin with a count had a
  * probability in the subnormal range, where the reference's per-term roundings decide the value
  * (reading it waits for the device); out[10] = 1 when the plan of the batch came from lattice axes
- * (no sort, nothing read back); out[11] = 64-bin lines of a profile row in the factored path (the
- * lines of the histogram that hold a count, plus one with the sums of the others). */
+ * (no sort, nothing read back); out[11] = slots of a profile row in the factored path: 64 per line
+ * of the histogram tables that holds a bin with a count, plus 32 sums over all other lines when
+ * there are any (a bin without a count enters the result through the mass only). */
 #define CVB_PATH_INFO_LEN 12
 CVB_API int cvb_last_path_info(cvb_ctx *ctx, double *out, int n_out);
 
