@@ -1376,6 +1376,19 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                  * (o - 1) % 16 lines of 64 doubles.  Copies travel through the thread's own places
                  * of a ring in shared memory (cp.async, CVF_PD copies in flight, nothing to
                  * synchronise between threads); further ahead they are requested into L2. */
+                const bool wide = !ONE && log_mask == (1 << SL) - 1; /* measured: also taking masks with one slot less gains nothing */
+                /* are the values of two points in all of the thread's slots with counts on the fast path of the logarithm? */
+                auto pair_fast = [&](const double *pa, const double *pb) {
+                    unsigned int worst = 0;
+#pragma unroll
+                    for (int i = 0; i < SL; i++) {
+                        const unsigned int ca = (unsigned int)(__double2hiint(pa[i]) - CVF_FAST_LO),
+                                           cb = (unsigned int)(__double2hiint(pb[i]) - CVF_FAST_LO);
+                        if (hcnt[i] != 0.0)
+                            worst = max(worst, max(ca, cb));
+                    }
+                    return worst < CVF_FAST_SPAN;
+                };
                 int o_req = 1;                 /* the next copy to request */
                 unsigned int dst_req = ring_s; /* its place in the ring */
                 const double *src_req = src0;  /* its first slot */
@@ -1608,6 +1621,21 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             sb = cv_mul(hcnt[0], lb);
                             if (hcnt[0] == 0.0) /* models.py:106 `if h` */
                                 sa = sb = 0.0;
+                        } else if (wide && pair_fast(pa, pb)) {
+                            /* counts in all of the warp's half-lines (rows that keep only the
+                             * lines with counts) and this thread's values all on the fast path: the 2 SL
+                             * logarithms side by side, nothing between them to branch on; what they make
+                             * of a slot without a count is not used */
+#pragma unroll
+                            for (int i = 0; i < SL; i++) {
+                                const double la = cvf_log_fast<CVF_LOG_REP>(pa[i], log_s),
+                                             lb = cvf_log_fast<CVF_LOG_REP>(pb[i], log_s);
+                                double ta = cv_mul(hcnt[i], la), tb = cv_mul(hcnt[i], lb);
+                                if (hcnt[i] == 0.0)
+                                    ta = tb = 0.0;
+                                sa = cv_add(sa, ta);
+                                sb = cv_add(sb, tb);
+                            }
                         } else if (!ONE && log_mask) {
 #pragma unroll
                             for (int i = 0; i < SL; i++)
