@@ -321,7 +321,8 @@ def committed_traffic(kernel, workload_name, n_points):
         with open(path) as f:
             for row in json.load(f):
                 if row['kernel'] == kernel and row['workload'] == workload_name and row['points'] == n_points:
-                    return {'bytes': row['dram_bytes'], 'source': row['source']}
+                    return {'bytes': row['dram_bytes'], 'source': row['source'],
+                            'pipe_fp64_active_pct': row.get('pipe_fp64_active_pct')}
     except (OSError, ValueError, KeyError):
         pass
     return None
@@ -544,6 +545,11 @@ def run_b200(args, rank, world, local_rank):
         roof = {'bound': 'fp64', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
                 'frac': achieved / peak_tflops if peak_tflops else None,
                 'traffic': traffic.get('bytes'), 'traffic_source': traffic.get('source'),
+                'ncu_pipe_fp64_active_pct': traffic.get('pipe_fp64_active_pct'),
+                'flop_accounting': 'SURVEY.md section 8(d) / DESIGN.md section 6: 64 flop per (point, bin with a count) '
+                                   'for the logarithm and the weighted sum, 6 per (point, slot of a profile row), 2 per '
+                                   '(q-run, copy, slot); the logarithm as executed is 9 FP64 instructions -- the pipe '
+                                   'utilisation ncu measures is ncu_pipe_fp64_active_pct',
                 'kernel': dominant, 'kernel_ms': dom_ms, 'flop_per_launch': flop_launch,
                 'mean_terms_per_point': work['mean_terms'],
                 'peak_source': 'register-resident DFMA chain measured in this run (cvb_fp64_peak); '

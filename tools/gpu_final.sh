@@ -18,6 +18,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cvf_prefix_kernel -s 2 -c 1 -o gpurun_out/${TAG}_prof_prefix -f python tools/prof_lattice.py cfg3 3 > gpurun_out/${TAG}_ncu_prefix.log 2>&1
 echo "ncu prefix rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cvf_profile_kernel -s 2 -c 1 -o gpurun_out/${TAG}_prof_k1 -f python tools/prof_lattice.py cfg3 3 > gpurun_out/${TAG}_ncu_k1.log 2>&1
+echo "ncu k1 rc=$?"
 M=gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor_subpipe_dmma.sum,sm__inst_executed_pipe_fp64.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum
 COVEST_B200_PATH=gemm timeout 600 ncu --metrics $M --clock-control none -k regex:'cvf_gemm|cvf_profile|cvf_weights' -s 3 -c 3 --csv --log-file gpurun_out/${TAG}_dmma_metrics.csv python tools/prof_lattice.py cfg3 2 > gpurun_out/${TAG}_ncu_dmma.log 2>&1
 echo "ncu dmma rc=$?"
