@@ -707,6 +707,7 @@ extern "C" int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const 
 }
 
 /* ---- lattice ------------------------------------------------------------------------------ */
+#define CVB_LATTICE_PART ((int64_t)1 << 21) /* points per part of a long slice with host output */
 extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double *axis_values,
                                 int64_t first, int64_t stride, int64_t block, int64_t count,
                                 double *out_ll, int k_best, double *out_rows, void *stream)
@@ -765,13 +766,47 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
         CU(grow(&ctx->d_ll, &ctx->cap_ll, (size_t)(count > 0 ? count : 1)), "cudaMalloc(loglik staging)");
         dl = ctx->d_ll;
     }
-    if (count > 0) {
+    bool need_sync = false, side_copy = false;
+    /* A long slice whose values go to host memory is evaluated in parts of whole runs (and whole
+     * (coverage, error_rate) groups), so that the values of a part travel while the next part is
+     * evaluated: at 8 bytes per point the copy is otherwise a third of the call (cfg5: 100 MB per rank). */
+    int64_t part = 0;
+    if (out_ll && !l_dev && count >= 2 * CVB_LATTICE_PART) {
+        int64_t unit = block;
+        if (block == 1 && stride == 1 && np == 5)
+            unit = (int64_t)axis_len[2] * axis_len[3] * axis_len[4];
+        if (unit >= 1 && unit <= CVB_LATTICE_PART && (block > 1 || first % unit == 0))
+            part = (CVB_LATTICE_PART + unit - 1) / unit * unit;
+    }
+    if (part > 0) {
+        if (!ctx->copy_stream)
+            CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!ctx->copy_ev)
+            CU(cudaEventCreateWithFlags(&ctx->copy_ev, cudaEventDisableTiming), "cudaEventCreate");
+        if (!ctx->copy_done)
+            CU(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming), "cudaEventCreate");
+        for (int64_t off = 0; off < count; off += part) {
+            const int64_t n_part = count - off < part ? count - off : part;
+            CvLattice lp = lat;
+            lp.first = first + (off / block) * stride;
+            int rc = launch_loglik(ctx, lp, axes_host, nullptr, n_part, 1, dl + off, nullptr, s);
+            if (rc != CVB_OK)
+                return rc;
+            CU(cudaEventRecord(ctx->copy_ev, s), "cudaEventRecord");
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev, 0), "cudaStreamWaitEvent");
+            CU(cudaMemcpyAsync(out_ll + off, dl + off, (size_t)n_part * sizeof(double), cudaMemcpyDeviceToHost,
+                               ctx->copy_stream),
+               "cudaMemcpyAsync(loglik)");
+        }
+        CU(cudaEventRecord(ctx->copy_done, ctx->copy_stream), "cudaEventRecord");
+        side_copy = true;
+        need_sync = true;
+    } else if (count > 0) {
         int rc = launch_loglik(ctx, lat, axes_host, nullptr, count, 1, dl, nullptr, s);
         if (rc != CVB_OK)
             return rc;
     }
-    bool need_sync = false, side_copy = false;
-    if (out_ll && !l_dev && count > 0) {
+    if (out_ll && !l_dev && count > 0 && part == 0) {
         cudaStream_t cs = s;
         if (k_best > 0 && count >= (1 << 16)) { /* the values leave next to the top-K, on a stream of their own */
             if (!ctx->copy_stream)

@@ -89,3 +89,28 @@ def test_calls_on_alternating_streams_are_ordered(rep):
     torch.cuda.synchronize()
     for out in outs:
         assert np.array_equal(out.cpu().numpy(), want, equal_nan=True)
+
+
+def test_long_slices_with_host_output_come_in_parts(rep):
+    """cvb_lattice_eval evaluates a slice of >= 2^22 points in parts of 2^21 (rounded to whole runs and
+    whole (coverage, error rate) groups) when the values go to host memory, so that a part's values
+    travel while the next is evaluated: the values and the best rows are those of one evaluation."""
+    import torch
+    ctx = rep.device_context
+    axes = [np.geomspace(10, 90, 48), np.geomspace(.01, .09, 20), np.linspace(.3, 1, 10), np.linspace(0, 1, 10),
+            np.linspace(.05, 1, 90)]
+    total = 48 * 20 * 9000
+    assert total // 2 >= 1 << 22
+    dev = torch.empty(total, dtype=torch.float64, device='cuda')
+    _, rows_dev = ctx.lattice_eval(axes, out_ll=dev, k_best=16)
+    one = dev.cpu().numpy()
+    host, rows = ctx.lattice_eval(axes, k_best=16)
+    assert np.array_equal(host, one, equal_nan=True)
+    assert np.array_equal(rows, rows_dev)
+    # a rank's share: whole groups dealt round-robin (the bench's slicing), and a ragged tail
+    block = 9000
+    mine, _ = ctx.lattice_eval(axes, first=1, stride=2, block=block)
+    idx = (1 + 2 * (np.arange(len(mine)) // block)) * block + np.arange(len(mine)) % block
+    assert len(mine) == total // 2 and np.array_equal(mine, one[idx], equal_nan=True)
+    tail, _ = ctx.lattice_eval(axes, first=3 * block, count=total - 3 * block - 1234)
+    assert np.array_equal(tail, one[3 * block:total - 1234], equal_nan=True)
