@@ -707,7 +707,9 @@ extern "C" int cvb_topk(cvb_ctx *ctx, int64_t n_points, const double *ll, const 
 }
 
 /* ---- lattice ------------------------------------------------------------------------------ */
-#define CVB_LATTICE_PART ((int64_t)1 << 21) /* points per part of a long slice with host output */
+/* slices with host output from this size on are evaluated in parts (measured on cfg3, 10^6 points: two parts cost
+ * 0.11 ms of a 1.7 ms call on one GPU -- shorter K1 / K2p launches leave SMs idle at their ends) */
+#define CVB_LATTICE_PART_MIN ((int64_t)1 << 22)
 extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double *axis_values,
                                 int64_t first, int64_t stride, int64_t block, int64_t count,
                                 double *out_ll, int k_best, double *out_rows, void *stream)
@@ -769,14 +771,19 @@ extern "C" int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const dou
     bool need_sync = false, side_copy = false;
     /* A long slice whose values go to host memory is evaluated in parts of whole runs (and whole
      * (coverage, error_rate) groups), so that the values of a part travel while the next part is
-     * evaluated: at 8 bytes per point the copy is otherwise a third of the call (cfg5: 100 MB per rank). */
+     * evaluated: at 8 bytes per point the copy is otherwise up to a third of the call (cfg5: 100 MB per
+     * rank; and the ranks of a box finish together and share the way to host memory). */
     int64_t part = 0;
-    if (out_ll && !l_dev && count >= 2 * CVB_LATTICE_PART) {
+    if (out_ll && !l_dev && count >= CVB_LATTICE_PART_MIN) {
         int64_t unit = block;
         if (block == 1 && stride == 1 && np == 5)
             unit = (int64_t)axis_len[2] * axis_len[3] * axis_len[4];
-        if (unit >= 1 && unit <= CVB_LATTICE_PART && (block > 1 || first % unit == 0))
-            part = (CVB_LATTICE_PART + unit - 1) / unit * unit;
+        /* parts of about 2^21 points, at most eight */
+        int64_t n_parts = count >> 21;
+        n_parts = n_parts < 2 ? 2 : n_parts > 8 ? 8 : n_parts;
+        const int64_t want = (count + n_parts - 1) / n_parts;
+        if (unit >= 1 && unit <= want && (block > 1 || first % unit == 0))
+            part = (want + unit - 1) / unit * unit;
     }
     if (part > 0) {
         if (!ctx->copy_stream)

@@ -92,8 +92,8 @@ def test_calls_on_alternating_streams_are_ordered(rep):
 
 
 def test_long_slices_with_host_output_come_in_parts(rep):
-    """cvb_lattice_eval evaluates a slice of >= 2^22 points in parts of 2^21 (rounded to whole runs and
-    whole (coverage, error rate) groups) when the values go to host memory, so that a part's values
+    """cvb_lattice_eval evaluates a slice of >= 2^22 points in two to eight parts (of whole runs and whole
+    (coverage, error rate) groups) when the values go to host memory, so that a part's values
     travel while the next is evaluated: the values and the best rows are those of one evaluation."""
     import torch
     ctx = rep.device_context
