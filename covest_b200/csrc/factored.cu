@@ -2739,8 +2739,10 @@ cudaError_t cvf_eval(const CvModelDesc &m, const CvLattice &lat, const double *c
     const bool counts_first = sl.counts_first;
     typedef decltype(&cvf_prefix_kernel<true, true, true, 8, 4>) CvfPrefixFn;
     CvfPrefixFn kp = nullptr;
-#define CVF_PICK(nw_, sl_) \
-    (want_mass ? cvf_prefix_kernel<true, false, false, nw_, sl_> : cvf_prefix_kernel<false, false, false, nw_, sl_>)
+    const bool full_one = kp_slots == kp_nw * 32 * kp_sl; /* the one pass of a small geometry has no idle thread */
+#define CVF_PICK(nw_, sl_)                                                                                          \
+    (full_one ? (want_mass ? cvf_prefix_kernel<true, true, false, nw_, sl_> : cvf_prefix_kernel<false, true, false, nw_, sl_>) \
+              : (want_mass ? cvf_prefix_kernel<true, false, false, nw_, sl_> : cvf_prefix_kernel<false, false, false, nw_, sl_>))
     switch (kp_nw * 10 + kp_sl) {
     case 13: kp = CVF_PICK(1, 3); break;
     case 14: kp = CVF_PICK(1, 4); break;

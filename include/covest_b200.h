@@ -119,7 +119,10 @@ CVB_API int cvb_merge_rows(const double *rows, int n_rows, int n_cols, int k_bes
  * (coverage, error_rate) groups to a rank, which is how the ranks of a multi-GPU run shard a
  * repeats-model lattice (each group's bin profiles are then computed on one rank only).
  * Evaluates `count` points; out_ll (host or device, may be NULL) receives them; if k_best > 0,
- * out_rows (host or device) receives the k_best best rows as in cvb_topk. */
+ * out_rows (host or device) receives the k_best best rows as in cvb_topk.  With a host out_ll a
+ * slice of 2^22 points or more is evaluated in parts of about 2^21 points (whole runs, whole
+ * (coverage, error_rate) groups): the values of a part travel while the next part is evaluated;
+ * values and rows are those of one evaluation. */
 CVB_API int cvb_lattice_eval(cvb_ctx *ctx, const int32_t *axis_len, const double *axis_values,
                      int64_t first, int64_t stride, int64_t block, int64_t count, double *out_ll,
                      int k_best, double *out_rows, void *stream);
