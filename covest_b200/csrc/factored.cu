@@ -9,10 +9,13 @@
  *                       the same tables for a lattice handed over as its axes: from a template of
  *                       one group computed on the host (cvf_lattice_template), no sort, nothing
  *                       read back
- *   cvf_profile_kernel  K1: one warp per (group, 16 copy numbers): profiles over all bins
+ *   cvf_profile_kernel  K1: one warp per (group, 16 copy numbers): profiles over all bins; a row
+ *                       keeps the 64-bin lines that hold a count, the others leave as 32 sums
+ *                       (factored.h, CvfSlots: they enter the result through the mass only)
  *   cvf_prefix_kernel   K2p: one CTA per tile of up to four q-runs: running sums over the copy
  *                       numbers, per point the three-term combination + epilogue (the default for
- *                       batches whose points share q, as lattices do)
+ *                       batches whose points share q, as lattices do); warps per CTA and slots per
+ *                       thread are template parameters picked to cover a row in one pass
  *   cvf_prefix2_kernel  the same on bulk copies (TMA) through an mbarrier ring, 8 slots per
  *                       thread; selectable, slower
  *   cvf_weights_kernel, cvf_gemm_kernel   K1b, K2: one CTA per tile of 128 points: copy weights and
