@@ -478,6 +478,17 @@ def run_b200(args, rank, world, local_rank):
             return ctx.lattice_eval(axes, first=rank, stride=world, count=count, block=block, k_best=K_BEST)
         e2e_steps = max(steps, 30)  # wall-clock timed: enough steps that one hiccup of a rank does not decide it
         e2e_s = timed_host(step_host_lattice, e2e_steps, 3)
+
+        # the call the sharded search makes (grid.lattice_search, CoverageEstimator.compute_coverage_from_lattice):
+        # axes in, only the best rows out -- what end to end costs when the caller does not ask for every value
+        def step_host_search():
+            if world > 1:
+                _, rows = ctx.lattice_eval(axes, first=rank, stride=world, count=count, block=block, k_best=K_BEST,
+                                           want_ll=False, out_rows=dev_rows, stream=stream)
+                return parallel.merge_topk(parallel.allgather_rows(rows), K_BEST).cpu().numpy()
+            return ctx.lattice_eval(axes, first=rank, stride=world, count=count, block=block, k_best=K_BEST,
+                                    want_ll=False)[1]
+        search_s = timed_host(step_host_search, e2e_steps, 3)
         rec = {
             'cfg': cfg, 'model': model, 'ctx': ctx, 'hist': hist, 'axes': axes, 'count': count, 'block': block,
             'n_bins': n_bins, 'counted_bins': counted_bins, 'work': work, 'value': value, 'total_ms': total_ms,
@@ -488,6 +499,11 @@ def run_b200(args, rank, world, local_rank):
                     'd2h_bytes_per_step': int(count * 8 + K_BEST * 6 * 8),
                     'call': 'cvb_lattice_eval: the candidate lattice handed over as its axes (host), all values '
                             'and the best rows returned to host memory'},
+            'e2e_search': {'value': world * count * n_bins * e2e_steps / search_s, 'unit': UNIT, 'steps': e2e_steps,
+                           'h2d_bytes_per_step': int(8 * sum(len(a) for a in axes)),
+                           'd2h_bytes_per_step': int(K_BEST * 6 * 8),
+                           'call': 'cvb_lattice_eval with out_ll = NULL: axes in, the best rows out (what '
+                                   'lattice_search / compute_coverage_from_lattice call)'},
         }
         if with_points:
             # the same batch as an explicit point array (the general plan: keys, radix sort, group tables)
@@ -678,7 +694,7 @@ def run_b200(args, rank, world, local_rank):
             cfg5 = {'metric': METRIC, 'value': c5['value'], 'unit': UNIT, 'n_gpus': world, 'steps': len(c5['step_ms']),
                     'ms_per_step': c5['total_ms'] / len(c5['step_ms']),
                     'config': workload_config('cfg5', world, c5['n_bins'], c5['axes']),
-                    'e2e': c5['e2e'], 'sustained': c5['sustained'], 'roofline': roof5, 'phases': phases5,
+                    'e2e': c5['e2e'], 'e2e_search': c5['e2e_search'], 'sustained': c5['sustained'], 'roofline': roof5, 'phases': phases5,
                     'gpu_launches': c5['launches'], 'best_row': [float(v) for v in c5['best'][0]],
                     'refinement': {
                         'flow': 'lattice -> per-rank top-64 -> NCCL all-gather -> merge -> starts dealt round-robin -> '
@@ -698,7 +714,7 @@ def run_b200(args, rank, world, local_rank):
             'warmup': args.warmup, 'ms_per_step': main['total_ms'] / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(args.workload, world, main['n_bins'], main['axes']),
-            'e2e': main['e2e'], 'gpu_launches': main['launches'], 'clocks': clocks.summary(),
+            'e2e': main['e2e'], 'e2e_search': main['e2e_search'], 'gpu_launches': main['launches'], 'clocks': clocks.summary(),
             'sustained': dict(main['sustained'], clocks=main['clocks']),
             'roofline': roof, 'phases': phases, 'best_row': [float(v) for v in main['best'][0]],
         }
