@@ -93,3 +93,43 @@ def test_the_mass_of_the_summed_lines_is_the_mass_of_their_bins(monkeypatch):
     assert np.array_equal(fin, np.isfinite(b))
     assert rel_err_ll(a, b).max() <= 1e-12
     assert np.abs(tail_term[fin]).max() > 1e4   # the tail term is there and large
+
+
+def _lined_hist(lines, bins):
+    """Counts in every bin of the first `lines` 64-bin lines, zeros up to `bins`."""
+    rng = np.random.default_rng(1000 + lines)
+    return {j: (int(rng.integers(1, 5000)) if j <= 64 * lines else 0) for j in range(1, bins + 1)}
+
+
+@pytest.mark.parametrize('lines,bins,tail', [(1, 1000, 0), (2, 1000, 7), (2, 128, 0), (3, 1000, 0), (4, 1000, 11), (5, 1000, 0),
+                                             (6, 1000, 0), (7, 1000, 5), (8, 1000, 0), (9, 1000, 0), (11, 1000, 3),
+                                             (12, 1000, 0), (13, 1000, 0), (16, 1024, 0), (20, 2000, 9)])
+def test_every_geometry_of_the_prefix_kernel(lines, bins, tail):
+    """The prefix kernel picks warps per CTA and slots per thread by the length of a profile row
+    (factored.cu, cvf_eval): 3, 5, 4, 7, 9, ... half-lines here.  Every geometry gives the values of the
+    GEMM path and of the per-point kernel (which is checked against the oracle elsewhere)."""
+    hist = _lined_hist(lines, bins)
+    model = RepeatsModel(K, R, hist, tail, max_error=8)
+    try:
+        ctx = model.device_context
+        # coverage grows with the bins that have counts; at most ~60 copies of at most 150 x 0.8 per copy
+        # stay below the rates where the reference overflows (~11 360)
+        ax = [np.array([min(12. * lines, 150.), min(25. * lines, 150.)]), np.array([.02, .06]), np.array([.4, .7, 1.0]),
+              np.array([0., .5, 1.]), np.linspace(.3, 1, 14)]
+        got = {}
+        for path in (ctx.PATH_FACTORED_PREFIX, ctx.PATH_FACTORED_GEMM, ctx.PATH_PER_POINT):
+            ctx.set_path(path)
+            got[path], _ = ctx.lattice_eval(ax)
+            if path == ctx.PATH_FACTORED_PREFIX:
+                info = ctx.last_path_info()
+                assert info['kernel'] == 'cvf_prefix_kernel'
+                table_lines = -(-bins // 64) if bins > 128 else 2
+                table_lines = 16 * -(-table_lines // 16) if bins > 128 else table_lines
+                assert info['row_slots'] == (64 * lines + 32 if lines < table_lines else 64 * lines)
+        want = got[ctx.PATH_PER_POINT]
+        assert np.isfinite(want).sum() >= 30   # (one or two copies cannot reach the far bins: -inf there)
+        for path in (ctx.PATH_FACTORED_PREFIX, ctx.PATH_FACTORED_GEMM):
+            assert np.array_equal(np.isfinite(got[path]), np.isfinite(want))
+            assert rel_err_ll(got[path], want).max() <= 1e-11, (path, float(rel_err_ll(got[path], want).max()))
+    finally:
+        model.close()
