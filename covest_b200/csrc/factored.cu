@@ -1561,9 +1561,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             CVF_CASE(1)
                             CVF_CASE(2)
 #if CVF_PNQ > 3
-    #if CVF_PNQ > 3
-                        CVF_CASE(3)
-#endif
+                            CVF_CASE(3)
 #endif
 #undef CVF_CASE
                         }
@@ -1581,9 +1579,7 @@ cvf_prefix_kernel(const __grid_constant__ CvModelDesc m, const __grid_constant__
                             CVF_CASE(1)
                             CVF_CASE(2)
 #if CVF_PNQ > 3
-    #if CVF_PNQ > 3
-                        CVF_CASE(3)
-#endif
+                            CVF_CASE(3)
 #endif
 #undef CVF_CASE
                         }
